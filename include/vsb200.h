@@ -1,0 +1,185 @@
+/* vsb200.h -- C ABI of libvsb200.so, the B200 (sm_100a) engine that replaces the
+ * prediction hot path of DiamondLightSource/volume-segmantics.
+ *
+ * The reference has no FFI of its own: its boundary is the Python class
+ * VolSeg2dPredictor (volume_segmantics/model/operations/vol_seg_2d_predictor.py).
+ * Each entry point below names the reference statements it replaces
+ * (file:line relative to the reference repository).  All pointers are
+ * caller-owned, all sizes explicit, no C++ or torch types cross this line.
+ * Every function returns VSB_OK (0) or a negative error code; the message is
+ * available from vsb_last_error().  Nothing here ever aborts the process and
+ * nothing here has a CPU fallback: without a CUDA device vsb_create() fails.
+ *
+ * Threading: a handle is not thread-safe; one handle per process per GPU.
+ */
+#ifndef VSB200_H_
+#define VSB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSB_ABI_VERSION 1
+
+#define VSB_OK 0
+#define VSB_ERR_INVALID -1   /* bad argument / plan */
+#define VSB_ERR_CUDA -2      /* CUDA runtime / driver error */
+#define VSB_ERR_STATE -3     /* call order (no plan, no volume, ...) */
+#define VSB_ERR_UNSUPPORTED -4
+
+typedef struct vsb_engine vsb_engine;
+
+/* ---- network plan ------------------------------------------------------
+ * The host (Python) folds BatchNorm into the convolutions and lowers the
+ * smp network (model_2d.py:10-39) into a flat op list over numbered tensors.
+ * Tensor 0 is the network input: [nb, Hp, Wp, 1] bf16, written by the slicer.
+ * Spatial size of tensor t is (Hp >> ds_log2, Wp >> ds_log2); ds_log2 == -1
+ * means 1x1 (global pooled).  Layout of every tensor is NHWC.               */
+typedef struct {
+  int32_t channels;
+  int32_t ds_log2;
+  int32_t dtype; /* 0 = bf16, 1 = f32 */
+  int32_t reserved;
+} vsb_tensor_desc;
+
+enum {
+  VSB_OP_CONV = 1,      /* conv (+folded BN bias) (+residual) (+ReLU)        */
+  VSB_OP_MAXPOOL = 2,   /* 3x3 stride 2 pad 1                                 */
+  VSB_OP_GAP = 3,       /* global average pool -> 1x1                         */
+  VSB_OP_UPSAMPLE = 4,  /* mode 0: bilinear x`factor` align_corners=True;
+                           mode 1: broadcast a 1x1 tensor to the out size     */
+  VSB_OP_HEAD = 5       /* logits -> softmax -> argmax -> fp16 -> merge       */
+};
+
+#define VSB_MAX_SRC 6
+
+typedef struct {
+  int32_t kind;
+  int32_t out;                 /* output tensor id (HEAD: unused, -1)         */
+  int32_t n_src;               /* conv input = channel concat of the sources  */
+  int32_t src[VSB_MAX_SRC];
+  int32_t src_up[VSB_MAX_SRC]; /* 1: source is nearest-upsampled x2 first     */
+  int32_t res;                 /* residual tensor id added before ReLU, or -1 */
+  int32_t cin, cout;
+  int32_t kh, kw, stride, pad, dil, groups;
+  int32_t relu;
+  int32_t mode, factor;        /* UPSAMPLE: mode/factor. HEAD: factor = bilinear
+                                  upsampling of the logits (1 = none)         */
+  int64_t w_off;               /* byte offset in the weight blob of bf16
+                                  [cout][kh][kw][cin/groups] (OHWI)           */
+  int64_t b_off;               /* byte offset of f32 [cout] bias              */
+} vsb_op;
+
+/* Direction d = 3*k + a: k quarter turns of np.rot90 in the Z-Y plane
+ * (vol_seg_2d_predictor.py:108), a = Axis.Z/Y/X swap (base_data_utils.py:132-138).
+ * A slice-space pixel (s, r, c) of direction d is voxel
+ *     base + s*stride_s + r*stride_r + c*stride_c      (element offsets)
+ * of the C-ordered (Z,Y,X) volume.                                           */
+typedef struct {
+  int64_t S, H, W;          /* slices, rows, cols of the direction's images   */
+  int64_t Hp, Wp;           /* padded to multiples of 32 (augmentations.py:30-44) */
+  int64_t pad_top, pad_left;   /* int(p/2): albumentations PadIfNeeded centre */
+  int64_t crop_top, crop_left; /* round-half-even(p/2): torchvision center_crop
+                                  (base_data_utils.py:125-129)                */
+  int64_t base, stride_s, stride_r, stride_c;
+} vsb_direction;
+
+int vsb_abi_version(void);
+const char* vsb_last_error(void);
+
+/* VolSeg2dPredictor.__init__ (vol_seg_2d_predictor.py:19-26): bind a GPU.   */
+int vsb_create(int device, vsb_engine** out);
+void vsb_destroy(vsb_engine* e);
+
+/* create_model_from_file (model_2d.py:42-57) after host-side BN folding.    */
+int vsb_load_plan(vsb_engine* e, const vsb_tensor_desc* tensors, int32_t n_tensors,
+                  const vsb_op* ops, int32_t n_ops, const void* weights, size_t weight_bytes,
+                  int32_t num_classes);
+
+/* Geometry of one direction; pure host arithmetic (also used by the tests). */
+int vsb_direction_geometry(int64_t Z, int64_t Y, int64_t X, int32_t d, vsb_direction* out);
+
+/* data_vol handed to _predict_* (vol_seg_2d_predictor.py:31,67,100): a uint8
+ * (Z,Y,X) C-ordered volume.  on_device != 0: `vol` is a device pointer that is
+ * adopted without a copy (caller keeps it alive); else it is copied H2D.
+ * Allocates and zeroes the packed-key volume (8 B / voxel).                  */
+int vsb_set_volume(vsb_engine* e, const uint8_t* vol, int32_t on_device, int64_t Z, int64_t Y,
+                   int64_t X);
+
+/* Zero the key volume (start of a new prediction on the same data).         */
+int vsb_reset_keys(vsb_engine* e);
+
+/* The inner hot loop, vol_seg_2d_predictor.py:40-58 + :60-64 + :90-98, for the
+ * slices [s_begin, s_end) of direction d (a multi-GPU work item):
+ * slicer -> network -> softmax/argmax -> fp16 -> inverse rotation -> packed
+ * key atomicMax.  Asynchronous on the engine's stream.                       */
+int vsb_predict_range(vsb_engine* e, int32_t d, int64_t s_begin, int64_t s_end);
+
+/* _predict_single_axis / _predict_3_ways_max_probs / _predict_12_ways_max_probs
+ * (vol_seg_2d_predictor.py:31-116): every direction whose bit is set in
+ * dir_mask, all slices.  skip_duplicates != 0 drops directions 3,6,9,10 whose
+ * images duplicate an earlier direction (result-identical).      */
+int vsb_predict(vsb_engine* e, uint32_t dir_mask, int32_t skip_duplicates);
+
+/* Device pointer / element count of the uint64 key volume, so the host can
+ * run the one NCCL max-reduce over it.  vsb_bind_keys lets the
+ * host substitute its own device buffer (e.g. a torch tensor) of the same
+ * size, which the engine then uses instead of its own.                       */
+int vsb_keys(vsb_engine* e, void** dev_ptr, int64_t* count);
+int vsb_bind_keys(vsb_engine* e, void* dev_ptr);
+
+/* Unpack keys -> labels uint8 (Z,Y,X) [+ probs fp16 bits] and copy to host
+ * (the `return labels, probs` of vol_seg_2d_predictor.py:65,88,116).
+ * probs may be NULL.  Synchronises the stream.                              */
+int vsb_fetch(vsb_engine* e, uint8_t* labels, uint16_t* probs_fp16);
+/* Same, into device buffers (no D2H, asynchronous).                         */
+int vsb_unpack_device(vsb_engine* e, uint8_t* labels_dev, uint16_t* probs_fp16_dev);
+
+/* One-hot vote path (vol_seg_2d_predictor.py:118-136): per-class uint8 vote
+ * counts (C,Z,Y,X).  vsb_predict* with vote mode on accumulates votes
+ * instead of keys.                                                           */
+int vsb_set_vote_mode(vsb_engine* e, int32_t on);
+int vsb_fetch_votes(vsb_engine* e, uint8_t* votes);
+
+int vsb_synchronize(vsb_engine* e);
+
+/* Slices processed per launch (reference: 4, config.py:31). 0 = automatic.   */
+int vsb_set_batch(vsb_engine* e, int32_t slices_per_batch);
+/* 0: tcgen05 implicit-GEMM convolutions wherever legal (default);
+ * 1: CUDA-core convolutions everywhere (bring-up / cross-check);
+ * 2: as 1 but also without the dedicated 7x7 stem kernel.                   */
+int vsb_set_conv_impl(vsb_engine* e, int32_t impl);
+
+/* ---- test hooks (bit-exact criteria of BASELINE.json) ---------------------
+ * Slicer only: padded+normalised bf16 images [nb, Hp, Wp] of direction d,
+ * slices [s0, s0+nb) (datasets.py:120-142 + augmentations.py:46-65).         */
+int vsb_slice_batch(vsb_engine* e, int32_t d, int64_t s0, int32_t nb, uint16_t* out_bf16_host);
+/* Merge only: inject per-direction slice-space results [S,H,W] (cropped
+ * dims) fp32 max-prob + uint8 label (host pointers) for direction d.         */
+int vsb_merge_injected(vsb_engine* e, int32_t d, const float* probs, const uint8_t* labels);
+/* Network only: images f32 [nb,Hp,Wp] (host, already padded+normalised; they
+ * are rounded to bf16 as the slicer would) -> logits f32 [nb,Hp,Wp,C] (host). */
+int vsb_forward_logits(vsb_engine* e, const float* images, int32_t nb, int32_t Hp, int32_t Wp,
+                       float* logits_out);
+/* Copy tensor `t` of the last vsb_forward_logits call to host as f32 NHWC.   */
+int vsb_debug_tensor(vsb_engine* e, int32_t t, float* out, int64_t capacity_elems,
+                     int64_t* shape4);
+
+/* With profiling on, every kernel launch is bracketed by CUDA events on the
+ * engine's stream; vsb_stage_ms returns the summed milliseconds and launch
+ * count per kernel class since profiling was switched on:
+ * 0 slicer, 1 tcgen05 conv, 2 CUDA-core conv, 3 stem, 4 max-pool,
+ * 5 head+merge, 6 other (pool / up-sample).                                  */
+int vsb_stage_ms(vsb_engine* e, int32_t stage, float* ms, int64_t* launches);
+int vsb_set_profiling(vsb_engine* e, int32_t on);
+
+/* ---- clip_to_uint8 (base_data_utils.py:243-287), SURVEY 8f-1 -------------- */
+/* (declared when implemented) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSB200_H_ */

@@ -1,0 +1,146 @@
+"""Host-side logic that needs no GPU: enums / pickled model format, settings,
+BatchNorm folding, plan lowering, work partitioning, key packing."""
+import pickle
+import sys
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.smp_models import make_random_model
+from volume_segmantics_b200 import _lib, sharding
+from volume_segmantics_b200.plan import B200SegmentationModel, _fold, conv_macs_per_pixel, lower_to_plan
+
+
+def test_reference_import_paths_and_enum_pickling():
+    import volume_segmantics.utilities.base_data_utils as utils
+    from volume_segmantics.data import get_settings_data
+    from volume_segmantics.model import VolSeg2DPredictionManager
+    from volume_segmantics.model.operations.vol_seg_2d_predictor import VolSeg2dPredictor
+    from volume_segmantics.utilities import Quality, get_2d_prediction_parser
+
+    assert Quality.HIGH.value == 12 and utils.Axis.X.value == 2 and utils.ModelType.DEEPLABV3_PLUS.value == 5
+    blob = pickle.dumps(utils.ModelType.U_NET)
+    assert b"volume_segmantics.utilities.base_data_utils" in blob
+    assert pickle.loads(blob) is utils.ModelType.U_NET
+    assert callable(get_settings_data) and callable(get_2d_prediction_parser)
+    assert VolSeg2DPredictionManager and VolSeg2dPredictor
+
+
+def test_settings_loader(tmp_path):
+    from volume_segmantics.data import get_settings_data
+
+    p = tmp_path / "s.yaml"
+    p.write_text("quality: high\ncuda_device: 0\none_hot: False\n")
+    s = get_settings_data(p)
+    assert s.quality == "high" and s.cuda_device == 0
+    assert get_settings_data({"a": 1}).a == 1
+    assert get_settings_data(None) == SimpleNamespace()
+    with pytest.raises(SystemExit) as ex:  # reference tests/test_settings_data.py
+        get_settings_data(tmp_path / "missing.yaml")
+    assert ex.value.code == 1
+
+
+def test_invalid_quality_exits_1():
+    import volume_segmantics.utilities.base_data_utils as utils
+
+    with pytest.raises(SystemExit) as ex:
+        utils.get_prediction_quality(SimpleNamespace(quality="ultra"))
+    assert ex.value.code == 1
+    assert utils.get_prediction_axis(SimpleNamespace()) == utils.Axis.Z
+
+
+def test_model_file_roundtrip(tmp_path):
+    """The .pytorch dict written like reference tests/conftest.py:184-190 loads."""
+    import volume_segmantics.utilities.base_data_utils as utils
+    from volume_segmantics.model.model_2d import create_model_from_file
+
+    oracle = make_random_model("unet", "resnet34", 4, seed=3)
+    struc = {"type": utils.ModelType.U_NET, "encoder_name": "resnet34", "encoder_weights": "imagenet",
+             "in_channels": 1, "classes": 4}
+    path = tmp_path / "m.pytorch"
+    torch.save({"model_state_dict": oracle.state_dict(), "model_struc_dict": struc, "label_codes": {"a": 1}}, path)
+    model, n, codes = create_model_from_file(path)
+    assert isinstance(model, torch.nn.Module) and n == 4 and codes == {"a": 1}
+    for k, v in oracle.state_dict().items():
+        assert torch.equal(model.state_dict()[k], v)
+
+
+@pytest.mark.parametrize("mt,arch,enc,c,macs", [
+    ("U_NET", "unet", "resnet34", 4, 118096),
+    ("U_NET", "unet", "resnet34", 2, 117808),
+    ("U_NET_PLUS_PLUS", "unetplusplus", "resnext50_32x4d", 6, 878448),
+    ("DEEPLABV3_PLUS", "deeplabv3plus", "resnet50", 4, 137948),
+])
+def test_state_dict_keys_and_mac_counts(mt, arch, enc, c, macs):
+    """smp key names == oracle key names; MAC/px equals SURVEY.md 8a-T."""
+    from oracle.smp_models import OracleSegModel
+
+    m = B200SegmentationModel(mt, enc, c)
+    o = OracleSegModel(arch, enc, c)
+    assert set(m.state_dict()) == set(o.state_dict())
+    m.load_state_dict(o.state_dict())
+    assert conv_macs_per_pixel(m.spec) == macs
+
+
+def test_bn_folding_matches_torch():
+    oracle = make_random_model("unet", "resnet34", 4, seed=0)
+    m = B200SegmentationModel("U_NET", "resnet34", 4)
+    m.load_state_dict(oracle.state_dict())
+    L = next(l for l in m.spec.layers if l.name == "encoder.layer2.0.conv1")
+    w_bits, b = _fold(m.state_dict(), L)
+    w = torch.from_numpy(w_bits.view(np.int16).copy()).view(torch.bfloat16).float().permute(0, 3, 1, 2)
+    x = torch.randn(1, 64, 9, 9)
+    blk = oracle.encoder.layer2[0]
+    with torch.no_grad():
+        want = blk.bn1(blk.conv1(x))
+        got = torch.nn.functional.conv2d(x, w, torch.from_numpy(b), stride=2, padding=1)
+    assert torch.allclose(got, want, atol=3e-2, rtol=1e-2)  # bf16 weight rounding only
+
+
+def test_plan_lowering_tables():
+    m = B200SegmentationModel("U_NET", "resnet34", 4)
+    p = lower_to_plan(m)
+    kinds = [op.kind for op in p.ops]
+    assert kinds.count(_lib.VSB_OP_CONV) == 47 and kinds.count(_lib.VSB_OP_MAXPOOL) == 1
+    assert kinds[-1] == _lib.VSB_OP_HEAD
+    dec = [op for op in p.ops if op.kind == _lib.VSB_OP_CONV and op.n_src == 2]
+    assert len(dec) == 4 and all(op.src_up[0] == 1 and op.src_up[1] == 0 for op in dec)
+    for op in p.ops:
+        if op.kind == _lib.VSB_OP_CONV:
+            assert op.w_off % 256 == 0 and op.b_off % 256 == 0
+            assert op.w_off + op.cout * op.kh * op.kw * (op.cin // op.groups) * 2 <= p.blob.size
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("shape", [(64, 64, 64), (20, 40, 45), (2048, 2048, 512)])
+def test_partition_covers_everything_once(world, shape):
+    dirs = sharding.direction_list((1 << 12) - 1, skip_duplicates=True)
+    assert dirs == [0, 1, 2, 4, 5, 7, 8, 11]
+    shares = sharding.partition(shape, dirs, world)
+    seen = {d: np.zeros(sharding.direction_dims(shape, d)[0], int) for d in dirs}
+    for sh in shares:
+        for it in sh:
+            seen[it.d][it.s0:it.s1] += 1
+    assert all((v == 1).all() for v in seen.values())
+    costs = [sum(it.cost for it in sh) for sh in shares]
+    assert max(costs) <= 1.15 * (sum(costs) / world) + max(it.cost for sh in shares for it in sh) / max(1, min(it.slices for sh in shares for it in sh)) * 8
+
+
+def test_key_packing_reproduces_first_max_rule():
+    rng = np.random.default_rng(0)
+    n = 4096
+    pal = np.array([0.9999, 0.99995, 1.0, 0.5, 0.50001, 0.25], np.float32)
+    p = pal[rng.integers(0, len(pal), (12, n))]
+    lab = rng.integers(0, 7, (12, n)).astype(np.uint8)
+    keys = np.zeros(n, np.uint64)
+    for d in rng.permutation(12):  # any order: max is commutative
+        keys = np.maximum(keys, sharding.pack_keys_np(p[d], lab[d], int(d)))
+    got_l, got_p = sharding.unpack_keys_np(keys)
+    p16 = p.astype(np.float16)
+    idx = np.argmax(p16, axis=0)  # numpy first-max, as _merge_vols_in_mem
+    assert np.array_equal(got_l, lab[idx, np.arange(n)])
+    assert np.array_equal(got_p, p16[idx, np.arange(n)])
+    assert (keys < np.uint64(1) << np.uint64(63)).all()

@@ -1,0 +1,3 @@
+from volume_segmantics_b200.host.settings_data import get_settings_data
+
+__all__ = ["get_settings_data"]

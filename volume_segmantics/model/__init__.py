@@ -1,0 +1,3 @@
+from volume_segmantics_b200.host.manager import VolSeg2DPredictionManager
+
+__all__ = ["VolSeg2DPredictionManager"]

@@ -1,0 +1,124 @@
+"""ctypes binding of libvsb200.so (the C ABI in include/vsb200.h).
+
+The library is built in-tree by ``volume_segmantics_b200.build``.  There is no
+fallback: if the shared object is missing, cannot be loaded, or lacks a symbol
+the header declares, importing the binding raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libvsb200.so"
+
+VSB_MAX_SRC = 6
+VSB_OP_CONV, VSB_OP_MAXPOOL, VSB_OP_GAP, VSB_OP_UPSAMPLE, VSB_OP_HEAD = 1, 2, 3, 4, 5
+
+PROF_CLASSES = ("slicer", "conv_tc", "conv_simt", "stem", "pool", "head", "other")
+
+
+class TensorDesc(C.Structure):
+    _fields_ = [("channels", C.c_int32), ("ds_log2", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Op(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("out", C.c_int32),
+        ("n_src", C.c_int32),
+        ("src", C.c_int32 * VSB_MAX_SRC),
+        ("src_up", C.c_int32 * VSB_MAX_SRC),
+        ("res", C.c_int32),
+        ("cin", C.c_int32),
+        ("cout", C.c_int32),
+        ("kh", C.c_int32),
+        ("kw", C.c_int32),
+        ("stride", C.c_int32),
+        ("pad", C.c_int32),
+        ("dil", C.c_int32),
+        ("groups", C.c_int32),
+        ("relu", C.c_int32),
+        ("mode", C.c_int32),
+        ("factor", C.c_int32),
+        ("w_off", C.c_int64),
+        ("b_off", C.c_int64),
+    ]
+
+
+class Direction(C.Structure):
+    _fields_ = [
+        (n, C.c_int64)
+        for n in (
+            "S", "H", "W", "Hp", "Wp", "pad_top", "pad_left", "crop_top", "crop_left",
+            "base", "stride_s", "stride_r", "stride_c",
+        )
+    ]
+
+
+class VsbError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); must list every symbol include/vsb200.h declares
+_P = C.c_void_p
+SIGNATURES = {
+    "vsb_abi_version": (C.c_int, []),
+    "vsb_last_error": (C.c_char_p, []),
+    "vsb_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "vsb_destroy": (None, [_P]),
+    "vsb_load_plan": (C.c_int, [_P, C.POINTER(TensorDesc), C.c_int32, C.POINTER(Op), C.c_int32, _P, C.c_size_t, C.c_int32]),
+    "vsb_direction_geometry": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.POINTER(Direction)]),
+    "vsb_set_volume": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64]),
+    "vsb_reset_keys": (C.c_int, [_P]),
+    "vsb_predict_range": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64]),
+    "vsb_predict": (C.c_int, [_P, C.c_uint32, C.c_int32]),
+    "vsb_keys": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "vsb_bind_keys": (C.c_int, [_P, _P]),
+    "vsb_fetch": (C.c_int, [_P, _P, _P]),
+    "vsb_unpack_device": (C.c_int, [_P, _P, _P]),
+    "vsb_set_vote_mode": (C.c_int, [_P, C.c_int32]),
+    "vsb_fetch_votes": (C.c_int, [_P, _P]),
+    "vsb_synchronize": (C.c_int, [_P]),
+    "vsb_set_batch": (C.c_int, [_P, C.c_int32]),
+    "vsb_set_conv_impl": (C.c_int, [_P, C.c_int32]),
+    "vsb_slice_batch": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int32, _P]),
+    "vsb_merge_injected": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "vsb_forward_logits": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "vsb_debug_tensor": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "vsb_stage_ms": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    "vsb_set_profiling": (C.c_int, [_P, C.c_int32]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libvsb200.so and bind every declared symbol; raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise VsbError(
+            f"{LIB_PATH} not found: build it with `python -m volume_segmantics_b200.build` "
+            "(the B200 engine has no CPU or PyTorch fallback)"
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is absent
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().vsb_last_error()
+        raise VsbError(f"libvsb200 error {rc}: {msg.decode() if msg else ''}")
+
+
+def direction_geometry(Z: int, Y: int, X: int, d: int) -> Direction:
+    g = Direction()
+    check(load().vsb_direction_geometry(Z, Y, X, d, C.byref(g)))
+    return g

@@ -1,0 +1,64 @@
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a -- parameter block shared
+// between the kernel (conv_tc.cu) and the host-side planner (engine.cu).
+//
+// GEMM view of a convolution on NHWC bf16 activations:
+//   D[M = output pixels, N = Cout] = sum over K-slabs  A_slab[M, KB] * W_slab[N, KB]^T
+// A K-slab is (filter tap, source tensor, block of KB = 16/32/64 input channels).
+// Its A operand is fetched by ONE 5-D TMA box load per "pixel class" straight
+// from the activation tensor: the tap offset is a coordinate shift and the
+// zero padding of the convolution is TMA's out-of-bounds zero fill -- there is
+// no im2col buffer.  Every activation tensor is described by 5-D tensor maps
+//   plain :  (c,       x,     1,  y,     n)
+//   folded:  (px*C+c,  x/2,   py, y/2,   n)     (H, W even)
+// The folded view makes stride-2 sampling a unit-stride box, which gives
+// stride-2 convolutions and -- together with the 4-class "parity split" of
+// the M tile -- the nearest-x2 up-sampled sources and the skip concat of the
+// smp decoder blocks without materialising either.
+#pragma once
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace vsb {
+
+struct TcSlab {
+  int32_t map;        // index into the tensor-map array
+  int32_t c0;         // first channel of the slab within its source
+  int32_t dy, dx;     // tap offset in source pixels
+  int32_t flags;      // bit0: folded map, bit1: halve (coords are (t >> 1), parity = t & 1)
+  int32_t cfold;      // channel count C of the source (parity_x * C is added to c0)
+  int32_t row_bytes;  // 32 / 64 / 128 = 2 * KB
+  int32_t w_off16;    // offset (16-byte units) of this slab's [Npad][KB] weight image
+};
+
+enum { TC_FOLDED = 1, TC_HALVE = 2 };
+
+struct ConvTcParams {
+  const TmaDesc* maps;
+  const TcSlab* slabs;
+  int32_t num_slabs;
+  const uint8_t* wpacked;
+  const float* bias;          // [n_tiles * BN] (zero padded)
+  const uint16_t* residual;   // bf16 NHWC [NB,H,W,cout] or null
+  void* out;                  // bf16 / f32 NHWC [NB,H,W,cout]
+  int32_t out_f32;
+  int32_t relu;
+  int32_t cout;               // channels actually stored
+  int32_t BN, n_tiles;        // N tile and number of N tiles
+  int32_t NB, H, W;           // output dims
+  int32_t ncls_log2;          // 0: one pixel class, 2: four parity classes
+  int32_t bw_log2, bh_log2, nt_log2;  // box (per class), bw*bh*nt*ncls == 128
+  int32_t tiles_x, tiles_y, tiles_n;  // box-grid tile counts
+  int32_t num_stages;
+  int32_t stage_bytes;        // A (128 * 128 B) + B (BN * 128 B), 1024-aligned
+  int32_t a_bytes;            // 16384
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 12;
+
+size_t conv_tc_smem_bytes(const ConvTcParams& p);
+cudaError_t launch_conv_tc(const ConvTcParams& p, int num_sms, cudaStream_t st);
+cudaError_t conv_tc_configure();  // cudaFuncSetAttribute(max dynamic smem)
+
+}  // namespace vsb

@@ -1,0 +1,1025 @@
+// libvsb200 engine: plan loading, workspace / tensor-map construction, the
+// per-direction prediction loop and the C ABI declared in include/vsb200.h.
+//
+// Host-side mirror of VolSeg2dPredictor (reference
+// volume_segmantics/model/operations/vol_seg_2d_predictor.py:16-136); the Python
+// shim above this library only folds BatchNorm, lowers the network to the op
+// list and forwards calls.  There is no CPU fallback anywhere in this file.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vsb200.h"
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t err__ = (call);                                                           \
+    if (err__ != cudaSuccess)                                                             \
+      return fail(VSB_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,      \
+                  cudaGetErrorString(err__));                                             \
+  } while (0)
+
+using vsb::TcSlab;
+using vsb::TmaDesc;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int pow2ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+enum ProfClass { PC_SLICER = 0, PC_CONV_TC, PC_CONV_SIMT, PC_STEM, PC_POOL, PC_HEAD, PC_OTHER, PC_N };
+
+struct TensorBuf {
+  int C = 0, ds = 0, dtype = 0;
+  int H = 0, W = 0;
+  size_t bytes = 0;
+  void* ptr = nullptr;
+  int first_def = -1, last_use = -1;
+};
+
+// Per-conv state that depends only on the plan (not on the spatial size).
+struct ConvPlan {
+  bool tc = false;
+  bool ps = false;        // parity-split (some source is nearest-x2 up-sampled)
+  bool s2 = false;        // stride 2
+  int BN = 0, n_tiles = 0;
+  std::vector<TcSlab> slabs;       // map index = source index
+  std::vector<int> src_kb;         // KB per source
+  TcSlab* d_slabs = nullptr;
+  uint8_t* d_wpacked = nullptr;
+  float* d_bias_pad = nullptr;
+  // spatial-size dependent
+  TmaDesc* d_maps = nullptr;
+  vsb::ConvTcParams params{};
+};
+
+}  // namespace
+
+struct vsb_engine {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  EncodeTiledFn encode = nullptr;
+
+  // plan
+  std::vector<vsb_tensor_desc> tdesc;
+  std::vector<vsb_op> ops;
+  std::vector<ConvPlan> conv;  // parallel to ops
+  uint8_t* d_weights = nullptr;
+  size_t weight_bytes = 0;
+  std::vector<uint8_t> h_weights;
+  int num_classes = 0;
+  bool has_plan = false;
+
+  // volume
+  const uint8_t* d_vol = nullptr;
+  uint8_t* d_vol_owned = nullptr;
+  int64_t Z = 0, Y = 0, X = 0;
+  unsigned long long* d_keys = nullptr;
+  unsigned long long* d_keys_owned = nullptr;
+  uint8_t* d_votes = nullptr;
+  int vote_mode = 0;
+  uint8_t* d_labels = nullptr;
+  uint16_t* d_probs = nullptr;
+
+  // workspace
+  int ws_Hp = 0, ws_Wp = 0, ws_nb = 0;
+  std::vector<TensorBuf> tens;
+  std::vector<void*> ws_allocs;
+  bool keep_all = false;
+  bool ws_keep = false;
+
+  int batch_override = 0;
+  int conv_impl = 0;
+  bool profiling = false;
+  float prof_ms[PC_N] = {0};
+  int64_t prof_launches[PC_N] = {0};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  std::vector<int> ev_cls;
+  size_t ev_used = 0;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// Direction geometry (host arithmetic).  d = 3k + a.
+//   np.rot90(V, k) in the (axis0, axis1) plane   vol_seg_2d_predictor.py:108
+//   rotate_array_to_axis                          base_data_utils.py:132-138
+// ---------------------------------------------------------------------------
+int round_half_even_half(int64_t p) {
+  // Python round(p / 2.0): banker's rounding of a half-integer
+  if ((p & 1) == 0) return (int)(p / 2);
+  const int64_t lo = p / 2;  // floor for p >= 0
+  return (int)((lo & 1) ? lo + 1 : lo);
+}
+
+int direction_geometry(int64_t Z, int64_t Y, int64_t X, int d, vsb_direction* g) {
+  if (d < 0 || d > 11 || Z <= 0 || Y <= 0 || X <= 0) return fail(VSB_ERR_INVALID, "bad direction/shape");
+  const int k = d / 3, a = d % 3;
+  const int64_t ni = (k & 1) ? Y : Z, nj = (k & 1) ? Z : Y;
+  auto vox = [&](int64_t s, int64_t r, int64_t c) -> int64_t {
+    int64_t i, j, x;
+    if (a == 0) { i = s; j = r; x = c; }
+    else if (a == 1) { i = r; j = s; x = c; }
+    else { i = c; j = r; x = s; }
+    int64_t z, y;
+    switch (k) {
+      case 0: z = i; y = j; break;
+      case 1: z = j; y = Y - 1 - i; break;
+      case 2: z = Z - 1 - i; y = Y - 1 - j; break;
+      default: z = Z - 1 - j; y = i; break;
+    }
+    return (z * Y + y) * X + x;
+  };
+  if (a == 0) { g->S = ni; g->H = nj; g->W = X; }
+  else if (a == 1) { g->S = nj; g->H = ni; g->W = X; }
+  else { g->S = X; g->H = nj; g->W = ni; }
+  g->Hp = (g->H + 31) / 32 * 32;
+  g->Wp = (g->W + 31) / 32 * 32;
+  const int64_t ph = g->Hp - g->H, pw = g->Wp - g->W;
+  g->pad_top = ph / 2;
+  g->pad_left = pw / 2;
+  g->crop_top = round_half_even_half(ph);
+  g->crop_left = round_half_even_half(pw);
+  g->base = vox(0, 0, 0);
+  g->stride_s = vox(1, 0, 0) - g->base;
+  g->stride_r = vox(0, 1, 0) - g->base;
+  g->stride_c = vox(0, 0, 1) - g->base;
+  return VSB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Plan-time preparation of a tcgen05 convolution: eligibility, N tiling, the
+// K-slab table and the pre-swizzled weight image.
+// ---------------------------------------------------------------------------
+uint16_t h_bf16(const std::vector<uint8_t>& blob, int64_t byte_off, int64_t idx) {
+  uint16_t v;
+  memcpy(&v, blob.data() + byte_off + idx * 2, 2);
+  return v;
+}
+
+bool conv_tc_eligible(const vsb_engine* e, const vsb_op& op) {
+  if (op.kind != VSB_OP_CONV) return false;
+  if (op.groups != 1) return false;
+  if (op.stride != 1 && op.stride != 2) return false;
+  bool any_up = false;
+  for (int s = 0; s < op.n_src; ++s) {
+    const vsb_tensor_desc& t = e->tdesc[op.src[s]];
+    if (t.channels % 16 != 0 || t.dtype != 0 || t.ds_log2 < 0) return false;
+    any_up |= op.src_up[s] != 0;
+  }
+  if (any_up && op.stride != 1) return false;
+  if (e->tdesc[op.out].ds_log2 < 0) return false;
+  if ((op.cout + 15) / 16 * 16 > 2048) return false;
+  return true;
+}
+
+int prepare_conv_plan(vsb_engine* e, int oi) {
+  const vsb_op& op = e->ops[oi];
+  ConvPlan& cp = e->conv[oi];
+  cp.tc = conv_tc_eligible(e, op);
+  if (!cp.tc) return VSB_OK;
+  cp.ps = false;
+  for (int s = 0; s < op.n_src; ++s) cp.ps |= op.src_up[s] != 0;
+  cp.s2 = op.stride == 2;
+  const int n_pad16 = (op.cout + 15) / 16 * 16;
+  cp.n_tiles = (n_pad16 + 255) / 256;
+  cp.BN = ((n_pad16 + cp.n_tiles - 1) / cp.n_tiles + 15) / 16 * 16;
+  const int n_total = cp.BN * cp.n_tiles;
+
+  cp.src_kb.clear();
+  std::vector<int> src_c0;  // channel offset of each source in the concat
+  int coff = 0;
+  for (int s = 0; s < op.n_src; ++s) {
+    const int C = e->tdesc[op.src[s]].channels;
+    cp.src_kb.push_back(C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16));
+    src_c0.push_back(coff);
+    coff += C;
+  }
+  if (coff != op.cin) return fail(VSB_ERR_INVALID, "op %d: cin %d != sum of sources %d", oi, op.cin, coff);
+
+  // slab table + packed weights
+  cp.slabs.clear();
+  size_t wbytes = 0;
+  for (int ky = 0; ky < op.kh; ++ky)
+    for (int kx = 0; kx < op.kw; ++kx)
+      for (int s = 0; s < op.n_src; ++s) {
+        const int C = e->tdesc[op.src[s]].channels, KB = cp.src_kb[s];
+        for (int cb = 0; cb < C / KB; ++cb) {
+          TcSlab sl{};
+          sl.map = s;
+          sl.c0 = cb * KB;
+          sl.dy = ky * op.dil - op.pad;
+          sl.dx = kx * op.dil - op.pad;
+          sl.cfold = C;
+          sl.row_bytes = KB * 2;
+          if (cp.ps) sl.flags = op.src_up[s] ? vsb::TC_HALVE : (vsb::TC_HALVE | vsb::TC_FOLDED);
+          else if (cp.s2) sl.flags = vsb::TC_HALVE | vsb::TC_FOLDED;
+          else sl.flags = 0;
+          sl.w_off16 = (int32_t)(wbytes / 16);
+          wbytes += (size_t)n_total * sl.row_bytes;
+          cp.slabs.push_back(sl);
+        }
+      }
+  std::vector<uint8_t> packed(wbytes, 0);
+  const int cin_g = op.cin;  // groups == 1
+  size_t si = 0;
+  for (int ky = 0; ky < op.kh; ++ky)
+    for (int kx = 0; kx < op.kw; ++kx)
+      for (int s = 0; s < op.n_src; ++s) {
+        const int C = e->tdesc[op.src[s]].channels, KB = cp.src_kb[s];
+        for (int cb = 0; cb < C / KB; ++cb, ++si) {
+          const TcSlab& sl = cp.slabs[si];
+          uint8_t* img = packed.data() + (size_t)sl.w_off16 * 16;
+          const int rb = sl.row_bytes;
+          for (int n = 0; n < op.cout; ++n) {
+            const int64_t wrow = (((int64_t)n * op.kh + ky) * op.kw + kx) * cin_g + src_c0[s] + cb * KB;
+            for (int ch = 0; ch < rb / 16; ++ch) {  // 16-byte chunks of 8 channels
+              int sw;  // Swizzle<B,4,3> on the byte address within the slab image
+              if (rb == 128) sw = ch ^ (n & 7);
+              else if (rb == 64) sw = ch ^ ((n >> 1) & 3);
+              else sw = ch ^ ((n >> 2) & 1);
+              uint8_t* dst = img + (size_t)n * rb + sw * 16;
+              memcpy(dst, e->h_weights.data() + op.w_off + (wrow + ch * 8) * 2, 16);
+            }
+          }
+        }
+      }
+  CK(cudaMalloc(&cp.d_wpacked, wbytes));
+  CK(cudaMemcpy(cp.d_wpacked, packed.data(), wbytes, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&cp.d_slabs, cp.slabs.size() * sizeof(TcSlab)));
+  CK(cudaMemcpy(cp.d_slabs, cp.slabs.data(), cp.slabs.size() * sizeof(TcSlab), cudaMemcpyHostToDevice));
+  std::vector<float> bias(n_total, 0.f);
+  if (op.b_off >= 0) memcpy(bias.data(), e->h_weights.data() + op.b_off, (size_t)op.cout * 4);
+  CK(cudaMalloc(&cp.d_bias_pad, n_total * 4));
+  CK(cudaMemcpy(cp.d_bias_pad, bias.data(), n_total * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * VSB_MAX_SRC));
+  return VSB_OK;
+}
+
+void free_workspace(vsb_engine* e) {
+  for (void* p : e->ws_allocs) cudaFree(p);
+  e->ws_allocs.clear();
+  e->tens.clear();
+  e->ws_Hp = e->ws_Wp = e->ws_nb = 0;
+}
+
+int make_tensor_map(vsb_engine* e, TmaDesc* out_host, const TensorBuf& t, int nb, bool folded, int KB,
+                    int bw, int bh, int nt) {
+  CUtensorMap m;
+  const cuuint64_t C = t.C, W = t.W, H = t.H;
+  cuuint64_t dims[5], strides[4];
+  if (!folded) {
+    dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = nb;
+    strides[0] = C * 2; strides[1] = W * C * 2; strides[2] = W * C * 2; strides[3] = H * W * C * 2;
+  } else {
+    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = nb;
+    strides[0] = 2 * C * 2; strides[1] = W * C * 2; strides[2] = 2 * W * C * 2; strides[3] = H * W * C * 2;
+  }
+  cuuint32_t box[5] = {(cuuint32_t)KB, (cuuint32_t)bw, 1u, (cuuint32_t)bh, (cuuint32_t)nt};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                         : (KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUresult r = e->encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, t.ptr, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(VSB_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d): C=%d W=%d H=%d nb=%d folded=%d KB=%d box=%dx%dx%d", (int)r,
+                t.C, t.W, t.H, nb, (int)folded, KB, bw, bh, nt);
+  static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "tensor map size");
+  memcpy(out_host, &m, sizeof(m));
+  return VSB_OK;
+}
+
+int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
+  if (e->ws_Hp == Hp && e->ws_Wp == Wp && e->ws_nb >= nb && e->ws_keep == e->keep_all) return VSB_OK;
+  CK(cudaStreamSynchronize(e->stream));
+  free_workspace(e);
+  const int nt_ = (int)e->tdesc.size();
+  e->tens.assign(nt_, TensorBuf());
+  for (int t = 0; t < nt_; ++t) {
+    TensorBuf& b = e->tens[t];
+    b.C = e->tdesc[t].channels;
+    b.ds = e->tdesc[t].ds_log2;
+    b.dtype = e->tdesc[t].dtype;
+    b.H = b.ds < 0 ? 1 : Hp >> b.ds;
+    b.W = b.ds < 0 ? 1 : Wp >> b.ds;
+    b.bytes = align_up((size_t)nb * b.H * b.W * b.C * (b.dtype ? 4 : 2), 1024);
+  }
+  // liveness
+  e->tens[0].first_def = -1;
+  for (int i = 0; i < (int)e->ops.size(); ++i) {
+    const vsb_op& op = e->ops[i];
+    if (op.out >= 0 && e->tens[op.out].first_def < 0 && op.out != 0) e->tens[op.out].first_def = i;
+    for (int s = 0; s < op.n_src; ++s) e->tens[op.src[s]].last_use = i;
+    if (op.res >= 0) e->tens[op.res].last_use = i;
+  }
+  // allocation with reuse of dead buffers (best fit)
+  struct Block { void* p; size_t bytes; };
+  std::vector<Block> freeb;
+  auto alloc = [&](size_t bytes, void** out) -> int {
+    int best = -1;
+    if (!e->keep_all)
+      for (int i = 0; i < (int)freeb.size(); ++i)
+        if (freeb[i].bytes >= bytes && (best < 0 || freeb[i].bytes < freeb[best].bytes)) best = i;
+    if (best >= 0 && freeb[best].bytes <= bytes * 2) {
+      *out = freeb[best].p;
+      freeb.erase(freeb.begin() + best);
+      return VSB_OK;
+    }
+    CK(cudaMalloc(out, bytes));
+    e->ws_allocs.push_back(*out);
+    return VSB_OK;
+  };
+  std::map<void*, size_t> size_of;
+  {
+    int rc = alloc(e->tens[0].bytes, &e->tens[0].ptr);
+    if (rc) return rc;
+    size_of[e->tens[0].ptr] = e->tens[0].bytes;
+  }
+  for (int i = 0; i < (int)e->ops.size(); ++i) {
+    const vsb_op& op = e->ops[i];
+    if (op.out > 0 && e->tens[op.out].first_def == i) {
+      TensorBuf& b = e->tens[op.out];
+      void* p = nullptr;
+      int rc = alloc(b.bytes, &p);
+      if (rc) return rc;
+      b.ptr = p;
+      if (!size_of.count(p)) size_of[p] = b.bytes;
+    }
+    // free tensors whose last use is this op
+    for (int t = 0; t < nt_; ++t)
+      if (e->tens[t].ptr && e->tens[t].last_use == i && e->tdesc[t].dtype == 0)
+        freeb.push_back({e->tens[t].ptr, size_of[e->tens[t].ptr]});
+  }
+  e->ws_Hp = Hp; e->ws_Wp = Wp; e->ws_nb = nb; e->ws_keep = e->keep_all;
+
+  // tensor maps + tile geometry of the tcgen05 convolutions
+  for (int i = 0; i < (int)e->ops.size(); ++i) {
+    ConvPlan& cp = e->conv[i];
+    if (!cp.tc) continue;
+    const vsb_op& op = e->ops[i];
+    const TensorBuf& ot = e->tens[op.out];
+    const int gw = cp.ps ? ot.W / 2 : ot.W, gh = cp.ps ? ot.H / 2 : ot.H;  // box grid
+    const int per_cls = cp.ps ? 32 : 128;
+    int bw = std::min(pow2ceil(gw), cp.ps ? 8 : 16);
+    int bh = std::min(pow2ceil(gh), per_cls / bw);
+    int ntile = per_cls / (bw * bh);
+    TmaDesc maps[VSB_MAX_SRC];
+    memset(maps, 0, sizeof(maps));
+    for (int s = 0; s < op.n_src; ++s) {
+      const TensorBuf& st = e->tens[op.src[s]];
+      bool folded;
+      if (cp.ps) folded = !op.src_up[s];
+      else folded = cp.s2;
+      if (folded && ((st.H & 1) || (st.W & 1)))
+        return fail(VSB_ERR_UNSUPPORTED, "op %d: folded source with odd dims %dx%d", i, st.H, st.W);
+      int rc = make_tensor_map(e, &maps[s], st, nb, folded, cp.src_kb[s], bw, bh, ntile);
+      if (rc) return rc;
+    }
+    CK(cudaMemcpy(cp.d_maps, maps, sizeof(maps), cudaMemcpyHostToDevice));
+    vsb::ConvTcParams& p = cp.params;
+    p.maps = cp.d_maps;
+    p.slabs = cp.d_slabs;
+    p.num_slabs = (int)cp.slabs.size();
+    p.wpacked = cp.d_wpacked;
+    p.bias = cp.d_bias_pad;
+    p.residual = op.res >= 0 ? (const uint16_t*)e->tens[op.res].ptr : nullptr;
+    p.out = ot.ptr;
+    p.out_f32 = ot.dtype;
+    p.relu = op.relu;
+    p.cout = op.cout;
+    p.BN = cp.BN;
+    p.n_tiles = cp.n_tiles;
+    p.NB = nb;
+    p.H = ot.H;
+    p.W = ot.W;
+    p.ncls_log2 = cp.ps ? 2 : 0;
+    p.bw_log2 = ilog2(bw);
+    p.bh_log2 = ilog2(bh);
+    p.nt_log2 = ilog2(ntile);
+    p.tiles_x = (gw + bw - 1) / bw;
+    p.tiles_y = (gh + bh - 1) / bh;
+    p.tiles_n = (nb + ntile - 1) / ntile;
+    p.a_bytes = 128 * 128;
+    p.stage_bytes = p.a_bytes + cp.BN * 128;
+    p.num_stages = std::min<int>(vsb::TC_MAX_STAGES, (int)((216 * 1024) / p.stage_bytes));
+    if (p.num_stages < 2) return fail(VSB_ERR_UNSUPPORTED, "op %d: too few pipeline stages", i);
+  }
+  return VSB_OK;
+}
+
+// ---- profiling helpers -----------------------------------------------------
+struct ProfScope {
+  vsb_engine* e;
+  int idx = -1;
+  ProfScope(vsb_engine* e_, int cls) : e(e_) {
+    if (!e->profiling) return;
+    if (e->ev_used == e->ev_pool.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      e->ev_pool.push_back({a, b});
+      e->ev_cls.push_back(cls);
+    }
+    idx = (int)e->ev_used++;
+    e->ev_cls[idx] = cls;
+    cudaEventRecord(e->ev_pool[idx].first, e->stream);
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(e->ev_pool[idx].second, e->stream);
+  }
+};
+
+void prof_collect(vsb_engine* e) {
+  if (!e->profiling) return;
+  cudaStreamSynchronize(e->stream);
+  for (size_t i = 0; i < e->ev_used; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->ev_pool[i].first, e->ev_pool[i].second);
+    e->prof_ms[e->ev_cls[i]] += ms;
+    e->prof_launches[e->ev_cls[i]] += 1;
+  }
+  e->ev_used = 0;
+}
+
+// ---- executor ----------------------------------------------------------------
+int run_conv(vsb_engine* e, int oi, int nb) {
+  const vsb_op& op = e->ops[oi];
+  ConvPlan& cp = e->conv[oi];
+  const TensorBuf& ot = e->tens[op.out];
+  if (cp.tc && e->conv_impl == 0) {
+    vsb::ConvTcParams p = cp.params;
+    p.NB = nb;
+    p.tiles_n = (nb + (1 << p.nt_log2) - 1) >> p.nt_log2;
+    ProfScope ps(e, PC_CONV_TC);
+    CK(vsb::launch_conv_tc(p, e->num_sms, e->stream));
+    return VSB_OK;
+  }
+  const TensorBuf& s0 = e->tens[op.src[0]];
+  if (e->conv_impl != 2 && op.cin == 1 && op.kh == 7 && op.kw == 7 && op.stride == 2 && op.pad == 3 &&
+      op.cout == 64 && op.n_src == 1 && ot.dtype == 0 && op.res < 0) {
+    ProfScope ps(e, PC_STEM);
+    vsb::launch_stem7x7((const uint16_t*)s0.ptr, nb, s0.H, s0.W, e->d_weights + op.w_off,
+                        (const float*)(e->d_weights + op.b_off), (uint16_t*)ot.ptr, op.relu, e->stream);
+    CK(cudaGetLastError());
+    return VSB_OK;
+  }
+  vsb::ConvArgs a{};
+  a.n_src = op.n_src;
+  for (int s = 0; s < op.n_src; ++s) {
+    const TensorBuf& st = e->tens[op.src[s]];
+    a.src[s].ptr = st.ptr;
+    a.src[s].C = st.C;
+    a.src[s].H = st.H;
+    a.src[s].W = st.W;
+    a.src[s].up = op.src_up[s];
+  }
+  a.NB = nb; a.H = ot.H; a.W = ot.W;
+  a.cin = op.cin; a.cout = op.cout; a.kh = op.kh; a.kw = op.kw;
+  a.stride = op.stride; a.pad = op.pad; a.dil = op.dil; a.groups = op.groups; a.relu = op.relu;
+  a.weights = e->d_weights + op.w_off;
+  a.bias = op.b_off >= 0 ? (const float*)(e->d_weights + op.b_off) : nullptr;
+  a.residual = op.res >= 0 ? e->tens[op.res].ptr : nullptr;
+  a.out = ot.ptr;
+  a.out_f32 = ot.dtype;
+  ProfScope ps(e, PC_CONV_SIMT);
+  vsb::launch_conv_simt(a, e->stream);
+  CK(cudaGetLastError());
+  return VSB_OK;
+}
+
+// Runs every op except HEAD on tensor 0 (already filled).  Returns the index of
+// the HEAD op through *head_idx (or -1).
+int run_network(vsb_engine* e, int nb, int* head_idx) {
+  *head_idx = -1;
+  for (int i = 0; i < (int)e->ops.size(); ++i) {
+    const vsb_op& op = e->ops[i];
+    switch (op.kind) {
+      case VSB_OP_CONV: {
+        int rc = run_conv(e, i, nb);
+        if (rc) return rc;
+        break;
+      }
+      case VSB_OP_MAXPOOL: {
+        const TensorBuf& s = e->tens[op.src[0]];
+        ProfScope ps(e, PC_POOL);
+        vsb::launch_maxpool3x3s2((const uint16_t*)s.ptr, nb, s.H, s.W, s.C, (uint16_t*)e->tens[op.out].ptr,
+                                 e->stream);
+        CK(cudaGetLastError());
+        break;
+      }
+      case VSB_OP_GAP: {
+        const TensorBuf& s = e->tens[op.src[0]];
+        ProfScope ps(e, PC_OTHER);
+        vsb::launch_gap((const uint16_t*)s.ptr, nb, s.H, s.W, s.C, (uint16_t*)e->tens[op.out].ptr, e->stream);
+        CK(cudaGetLastError());
+        break;
+      }
+      case VSB_OP_UPSAMPLE: {
+        const TensorBuf& s = e->tens[op.src[0]];
+        const TensorBuf& o = e->tens[op.out];
+        ProfScope ps(e, PC_OTHER);
+        vsb::launch_upsample((const uint16_t*)s.ptr, nb, s.H, s.W, s.C, o.H, o.W, op.mode, (uint16_t*)o.ptr,
+                             e->stream);
+        CK(cudaGetLastError());
+        break;
+      }
+      case VSB_OP_HEAD:
+        *head_idx = i;
+        break;
+      default:
+        return fail(VSB_ERR_INVALID, "unknown op kind %d", op.kind);
+    }
+  }
+  return VSB_OK;
+}
+
+int auto_batch(const vsb_engine* e, int64_t Hp, int64_t Wp, int64_t S) {
+  if (e->batch_override > 0) return (int)std::min<int64_t>(e->batch_override, S);
+  const int64_t target_px = 16ll << 20;
+  int64_t nb = std::max<int64_t>(1, target_px / (Hp * Wp));
+  nb = std::min<int64_t>(nb, 256);
+  if (nb >= 32) nb = nb / 32 * 32;
+  else if (nb >= 8) nb = nb / 8 * 8;
+  return (int)std::min<int64_t>(nb, S);
+}
+
+int predict_range(vsb_engine* e, int d, int64_t s_begin, int64_t s_end) {
+  if (!e->has_plan) return fail(VSB_ERR_STATE, "no plan loaded");
+  if (!e->d_vol) return fail(VSB_ERR_STATE, "no volume set");
+  vsb_direction g;
+  int rc = direction_geometry(e->Z, e->Y, e->X, d, &g);
+  if (rc) return rc;
+  if (s_begin < 0 || s_end > g.S || s_begin > s_end) return fail(VSB_ERR_INVALID, "bad slice range");
+  if (s_begin == s_end) return VSB_OK;
+  if (e->vote_mode && !e->d_votes) return fail(VSB_ERR_STATE, "vote buffer missing");
+  const int nbmax = auto_batch(e, g.Hp, g.Wp, s_end - s_begin);
+  e->keep_all = false;
+  rc = build_workspace(e, (int)g.Hp, (int)g.Wp, nbmax);
+  if (rc) return rc;
+  const int nbw = e->ws_nb;
+  (void)nbw;
+  for (int64_t s0 = s_begin; s0 < s_end; s0 += nbmax) {
+    const int nb = (int)std::min<int64_t>(nbmax, s_end - s0);
+    {
+      ProfScope ps(e, PC_SLICER);
+      vsb::launch_slicer(e->d_vol, g, s0, nb, (uint16_t*)e->tens[0].ptr, e->stream);
+      CK(cudaGetLastError());
+    }
+    int head = -1;
+    rc = run_network(e, nb, &head);
+    if (rc) return rc;
+    if (head < 0) return fail(VSB_ERR_INVALID, "plan has no HEAD op");
+    const vsb_op& hop = e->ops[head];
+    vsb::HeadArgs h{};
+    h.logits = (const float*)e->tens[hop.src[0]].ptr;
+    h.C = e->num_classes;
+    h.factor = hop.factor > 0 ? hop.factor : 1;
+    h.nb = nb;
+    h.g = g;
+    h.d = d;
+    h.s0 = s0;
+    h.keys = e->vote_mode ? nullptr : e->d_keys;
+    h.votes = e->vote_mode ? e->d_votes : nullptr;
+    h.nvox = e->Z * e->Y * e->X;
+    {
+      ProfScope ps(e, PC_HEAD);
+      vsb::launch_head(h, e->stream);
+      CK(cudaGetLastError());
+    }
+  }
+  return VSB_OK;
+}
+
+}  // namespace
+
+// ============================== C ABI ========================================
+extern "C" {
+
+int vsb_abi_version(void) { return VSB_ABI_VERSION; }
+const char* vsb_last_error(void) { return g_err.c_str(); }
+
+int vsb_direction_geometry(int64_t Z, int64_t Y, int64_t X, int32_t d, vsb_direction* out) {
+  if (!out) return fail(VSB_ERR_INVALID, "null out");
+  return direction_geometry(Z, Y, X, d, out);
+}
+
+int vsb_create(int device, vsb_engine** out) {
+  if (!out) return fail(VSB_ERR_INVALID, "null out");
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess || n == 0)
+    return fail(VSB_ERR_CUDA, "no CUDA device available (%s); libvsb200 has no CPU fallback",
+                cudaGetErrorString(err));
+  if (device < 0 || device >= n) return fail(VSB_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(VSB_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  vsb_engine* e = new vsb_engine();
+  e->device = device;
+  e->num_sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(VSB_ERR_CUDA, "cuTensorMapEncodeTiled not found");
+  e->encode = (EncodeTiledFn)fn;
+  CK(vsb::conv_tc_configure());
+  *out = e;
+  return VSB_OK;
+}
+
+static void free_plan(vsb_engine* e) {
+  for (ConvPlan& cp : e->conv) {
+    cudaFree(cp.d_slabs);
+    cudaFree(cp.d_wpacked);
+    cudaFree(cp.d_bias_pad);
+    cudaFree(cp.d_maps);
+  }
+  e->conv.clear();
+  cudaFree(e->d_weights);
+  e->d_weights = nullptr;
+  e->has_plan = false;
+}
+
+void vsb_destroy(vsb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  free_workspace(e);
+  free_plan(e);
+  cudaFree(e->d_vol_owned);
+  cudaFree(e->d_keys_owned);
+  cudaFree(e->d_votes);
+  cudaFree(e->d_labels);
+  cudaFree(e->d_probs);
+  for (auto& ev : e->ev_pool) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int vsb_load_plan(vsb_engine* e, const vsb_tensor_desc* tensors, int32_t n_tensors, const vsb_op* ops,
+                  int32_t n_ops, const void* weights, size_t weight_bytes, int32_t num_classes) {
+  if (!e || !tensors || !ops || !weights || n_tensors < 1 || n_ops < 1)
+    return fail(VSB_ERR_INVALID, "bad plan arguments");
+  if (num_classes < 1 || num_classes > 32) return fail(VSB_ERR_UNSUPPORTED, "num_classes %d not in [1,32]", num_classes);
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  free_workspace(e);
+  free_plan(e);
+  e->tdesc.assign(tensors, tensors + n_tensors);
+  e->ops.assign(ops, ops + n_ops);
+  e->num_classes = num_classes;
+  for (int i = 0; i < n_ops; ++i) {
+    const vsb_op& op = e->ops[i];
+    if (op.n_src < 0 || op.n_src > VSB_MAX_SRC) return fail(VSB_ERR_INVALID, "op %d: n_src", i);
+    for (int s = 0; s < op.n_src; ++s)
+      if (op.src[s] < 0 || op.src[s] >= n_tensors) return fail(VSB_ERR_INVALID, "op %d: src id", i);
+    if (op.kind != VSB_OP_HEAD && (op.out <= 0 || op.out >= n_tensors)) return fail(VSB_ERR_INVALID, "op %d: out id", i);
+    if (op.res >= n_tensors) return fail(VSB_ERR_INVALID, "op %d: res id", i);
+    if (op.kind == VSB_OP_CONV) {
+      if (op.groups < 1 || op.cin % op.groups || op.cout % op.groups) return fail(VSB_ERR_INVALID, "op %d: groups", i);
+      const size_t wb = (size_t)op.cout * op.kh * op.kw * (op.cin / op.groups) * 2;
+      if (op.w_off < 0 || (size_t)op.w_off + wb > weight_bytes) return fail(VSB_ERR_INVALID, "op %d: weight range", i);
+      if (op.b_off >= 0 && (size_t)op.b_off + (size_t)op.cout * 4 > weight_bytes)
+        return fail(VSB_ERR_INVALID, "op %d: bias range", i);
+    }
+  }
+  e->h_weights.assign((const uint8_t*)weights, (const uint8_t*)weights + weight_bytes);
+  e->weight_bytes = weight_bytes;
+  CK(cudaMalloc(&e->d_weights, weight_bytes));
+  CK(cudaMemcpy(e->d_weights, weights, weight_bytes, cudaMemcpyHostToDevice));
+  e->conv.assign(n_ops, ConvPlan());
+  for (int i = 0; i < n_ops; ++i) {
+    int rc = prepare_conv_plan(e, i);
+    if (rc) return rc;
+  }
+  e->has_plan = true;
+  return VSB_OK;
+}
+
+int vsb_set_volume(vsb_engine* e, const uint8_t* vol, int32_t on_device, int64_t Z, int64_t Y, int64_t X) {
+  if (!e || !vol || Z <= 0 || Y <= 0 || X <= 0) return fail(VSB_ERR_INVALID, "bad volume arguments");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  const int64_t n = Z * Y * X;
+  const bool resize = n != e->Z * e->Y * e->X;
+  if (on_device) {
+    cudaFree(e->d_vol_owned);
+    e->d_vol_owned = nullptr;
+    e->d_vol = vol;
+  } else {
+    if (resize || !e->d_vol_owned) {
+      cudaFree(e->d_vol_owned);
+      e->d_vol_owned = nullptr;
+      CK(cudaMalloc(&e->d_vol_owned, align_up(n, 256)));
+    }
+    CK(cudaMemcpyAsync(e->d_vol_owned, vol, n, cudaMemcpyHostToDevice, e->stream));
+    e->d_vol = e->d_vol_owned;
+  }
+  if (resize) {
+    cudaFree(e->d_keys_owned);
+    e->d_keys_owned = nullptr;
+    cudaFree(e->d_votes);
+    e->d_votes = nullptr;
+    cudaFree(e->d_labels);
+    e->d_labels = nullptr;
+    cudaFree(e->d_probs);
+    e->d_probs = nullptr;
+    CK(cudaMalloc(&e->d_keys_owned, n * 8));
+    e->d_keys = e->d_keys_owned;
+  }
+  e->Z = Z; e->Y = Y; e->X = X;
+  CK(cudaMemsetAsync(e->d_keys, 0, n * 8, e->stream));
+  if (e->d_votes) CK(cudaMemsetAsync(e->d_votes, 0, align_up((size_t)n * e->num_classes, 4), e->stream));
+  return VSB_OK;
+}
+
+int vsb_reset_keys(vsb_engine* e) {
+  if (!e || !e->d_keys) return fail(VSB_ERR_STATE, "no volume set");
+  CK(cudaSetDevice(e->device));
+  const int64_t n = e->Z * e->Y * e->X;
+  CK(cudaMemsetAsync(e->d_keys, 0, n * 8, e->stream));
+  if (e->d_votes) CK(cudaMemsetAsync(e->d_votes, 0, align_up((size_t)n * e->num_classes, 4), e->stream));
+  return VSB_OK;
+}
+
+int vsb_predict_range(vsb_engine* e, int32_t d, int64_t s_begin, int64_t s_end) {
+  if (!e) return fail(VSB_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->device));
+  return predict_range(e, d, s_begin, s_end);
+}
+
+int vsb_predict(vsb_engine* e, uint32_t dir_mask, int32_t skip_duplicates) {
+  if (!e) return fail(VSB_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->device));
+  if (dir_mask == 0 || dir_mask >= (1u << 12)) return fail(VSB_ERR_INVALID, "bad direction mask");
+  for (int d = 0; d < 12; ++d) {
+    if (!(dir_mask & (1u << d))) continue;
+    if (skip_duplicates && !e->vote_mode && (d == 3 || d == 6 || d == 9 || d == 10)) {
+      // identical image sets to d = 1, 4, 7, 0; only skipped
+      // when the earlier twin is part of the same request
+      const int twin = d == 3 ? 1 : (d == 6 ? 4 : (d == 9 ? 7 : 0));
+      if (dir_mask & (1u << twin)) continue;
+    }
+    vsb_direction g;
+    int rc = direction_geometry(e->Z, e->Y, e->X, d, &g);
+    if (rc) return rc;
+    rc = predict_range(e, d, 0, g.S);
+    if (rc) return rc;
+  }
+  return VSB_OK;
+}
+
+int vsb_keys(vsb_engine* e, void** dev_ptr, int64_t* count) {
+  if (!e || !e->d_keys) return fail(VSB_ERR_STATE, "no volume set");
+  if (dev_ptr) *dev_ptr = e->d_keys;
+  if (count) *count = e->Z * e->Y * e->X;
+  return VSB_OK;
+}
+
+int vsb_bind_keys(vsb_engine* e, void* dev_ptr) {
+  if (!e || !e->d_keys_owned) return fail(VSB_ERR_STATE, "no volume set");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  e->d_keys = dev_ptr ? (unsigned long long*)dev_ptr : e->d_keys_owned;
+  return VSB_OK;
+}
+
+int vsb_unpack_device(vsb_engine* e, uint8_t* labels_dev, uint16_t* probs_dev) {
+  if (!e || !e->d_keys) return fail(VSB_ERR_STATE, "no volume set");
+  CK(cudaSetDevice(e->device));
+  vsb::launch_unpack(e->d_keys, e->Z * e->Y * e->X, labels_dev, probs_dev, e->stream);
+  CK(cudaGetLastError());
+  return VSB_OK;
+}
+
+int vsb_fetch(vsb_engine* e, uint8_t* labels, uint16_t* probs) {
+  if (!e || !e->d_keys) return fail(VSB_ERR_STATE, "no volume set");
+  if (!labels) return fail(VSB_ERR_INVALID, "null labels");
+  CK(cudaSetDevice(e->device));
+  const int64_t n = e->Z * e->Y * e->X;
+  if (!e->d_labels) CK(cudaMalloc(&e->d_labels, align_up(n, 256)));
+  if (probs && !e->d_probs) CK(cudaMalloc(&e->d_probs, align_up(n * 2, 256)));
+  vsb::launch_unpack(e->d_keys, n, e->d_labels, probs ? e->d_probs : nullptr, e->stream);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(labels, e->d_labels, n, cudaMemcpyDeviceToHost, e->stream));
+  if (probs) CK(cudaMemcpyAsync(probs, e->d_probs, n * 2, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  prof_collect(e);
+  return VSB_OK;
+}
+
+int vsb_set_vote_mode(vsb_engine* e, int32_t on) {
+  if (!e) return fail(VSB_ERR_INVALID, "null engine");
+  if (on && !e->has_plan) return fail(VSB_ERR_STATE, "no plan loaded");
+  if (on && !e->d_keys) return fail(VSB_ERR_STATE, "no volume set");
+  CK(cudaSetDevice(e->device));
+  e->vote_mode = on ? 1 : 0;
+  if (on && !e->d_votes) {
+    const size_t n = align_up((size_t)e->Z * e->Y * e->X * e->num_classes, 4);
+    CK(cudaMalloc(&e->d_votes, n));
+    CK(cudaMemsetAsync(e->d_votes, 0, n, e->stream));
+  }
+  return VSB_OK;
+}
+
+int vsb_fetch_votes(vsb_engine* e, uint8_t* votes) {
+  if (!e || !e->d_votes || !votes) return fail(VSB_ERR_STATE, "vote mode not active");
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyAsync(votes, e->d_votes, (size_t)e->Z * e->Y * e->X * e->num_classes, cudaMemcpyDeviceToHost,
+                     e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  prof_collect(e);
+  return VSB_OK;
+}
+
+int vsb_synchronize(vsb_engine* e) {
+  if (!e) return fail(VSB_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  prof_collect(e);
+  return VSB_OK;
+}
+
+int vsb_set_batch(vsb_engine* e, int32_t n) {
+  if (!e || n < 0 || n > 1024) return fail(VSB_ERR_INVALID, "bad batch");
+  e->batch_override = n;
+  return VSB_OK;
+}
+
+int vsb_set_conv_impl(vsb_engine* e, int32_t impl) {
+  if (!e || impl < 0 || impl > 2) return fail(VSB_ERR_INVALID, "bad impl");
+  e->conv_impl = impl;
+  return VSB_OK;
+}
+
+int vsb_slice_batch(vsb_engine* e, int32_t d, int64_t s0, int32_t nb, uint16_t* out) {
+  if (!e || !e->d_vol || !out || nb < 1) return fail(VSB_ERR_STATE, "no volume set / bad args");
+  CK(cudaSetDevice(e->device));
+  vsb_direction g;
+  int rc = direction_geometry(e->Z, e->Y, e->X, d, &g);
+  if (rc) return rc;
+  if (s0 < 0 || s0 + nb > g.S) return fail(VSB_ERR_INVALID, "bad slice range");
+  uint16_t* dbuf = nullptr;
+  const size_t bytes = (size_t)nb * g.Hp * g.Wp * 2;
+  CK(cudaMalloc(&dbuf, bytes));
+  vsb::launch_slicer(e->d_vol, g, s0, nb, dbuf, e->stream);
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess) err = cudaMemcpyAsync(out, dbuf, bytes, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  cudaFree(dbuf);
+  CK(err);
+  return VSB_OK;
+}
+
+int vsb_merge_injected(vsb_engine* e, int32_t d, const float* probs, const uint8_t* labels) {
+  if (!e || !e->d_keys || !probs || !labels) return fail(VSB_ERR_STATE, "no volume set / bad args");
+  CK(cudaSetDevice(e->device));
+  vsb_direction g;
+  int rc = direction_geometry(e->Z, e->Y, e->X, d, &g);
+  if (rc) return rc;
+  const int64_t n = g.S * g.H * g.W;
+  float* dp = nullptr;
+  uint8_t* dl = nullptr;
+  CK(cudaMalloc(&dp, n * 4));
+  cudaError_t err = cudaMalloc(&dl, align_up(n, 256));
+  if (err == cudaSuccess) err = cudaMemcpyAsync(dp, probs, n * 4, cudaMemcpyHostToDevice, e->stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(dl, labels, n, cudaMemcpyHostToDevice, e->stream);
+  if (err == cudaSuccess) {
+    vsb::launch_merge_injected(dp, dl, g, d, e->d_keys, e->stream);
+    err = cudaGetLastError();
+  }
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  cudaFree(dp);
+  cudaFree(dl);
+  CK(err);
+  return VSB_OK;
+}
+
+int vsb_forward_logits(vsb_engine* e, const float* images, int32_t nb, int32_t Hp, int32_t Wp, float* logits) {
+  if (!e || !e->has_plan) return fail(VSB_ERR_STATE, "no plan loaded");
+  if (!images || !logits || nb < 1 || Hp < 32 || Wp < 32 || (Hp & 31) || (Wp & 31))
+    return fail(VSB_ERR_INVALID, "bad forward arguments (dims must be multiples of 32)");
+  CK(cudaSetDevice(e->device));
+  e->keep_all = true;  // debug tensors stay addressable
+  int rc = build_workspace(e, Hp, Wp, nb);
+  if (rc) return rc;
+  const int64_t n = (int64_t)nb * Hp * Wp;
+  float* dimg = nullptr;
+  CK(cudaMalloc(&dimg, n * 4));
+  cudaError_t err = cudaMemcpyAsync(dimg, images, n * 4, cudaMemcpyHostToDevice, e->stream);
+  if (err == cudaSuccess) {
+    vsb::launch_f32_to_bf16(dimg, (uint16_t*)e->tens[0].ptr, n, e->stream);
+    err = cudaGetLastError();
+  }
+  int head = -1;
+  if (err == cudaSuccess) {
+    rc = run_network(e, nb, &head);
+    if (rc) {
+      cudaStreamSynchronize(e->stream);
+      cudaFree(dimg);
+      return rc;
+    }
+  }
+  if (err == cudaSuccess && head >= 0) {
+    const vsb_op& hop = e->ops[head];
+    const TensorBuf& lt = e->tens[hop.src[0]];
+    err = cudaMemcpyAsync(logits, lt.ptr, (size_t)nb * lt.H * lt.W * lt.C * 4, cudaMemcpyDeviceToHost, e->stream);
+  }
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  cudaFree(dimg);
+  CK(err);
+  prof_collect(e);
+  if (head < 0) return fail(VSB_ERR_INVALID, "plan has no HEAD op");
+  return VSB_OK;
+}
+
+int vsb_debug_tensor(vsb_engine* e, int32_t t, float* out, int64_t capacity, int64_t* shape4) {
+  if (!e || e->tens.empty() || t < 0 || t >= (int)e->tens.size() || !e->tens[t].ptr)
+    return fail(VSB_ERR_STATE, "tensor not available");
+  CK(cudaSetDevice(e->device));
+  const TensorBuf& b = e->tens[t];
+  const int64_t n = (int64_t)e->ws_nb * b.H * b.W * b.C;
+  if (shape4) {
+    shape4[0] = e->ws_nb; shape4[1] = b.H; shape4[2] = b.W; shape4[3] = b.C;
+  }
+  if (!out) return VSB_OK;
+  if (capacity < n) return fail(VSB_ERR_INVALID, "capacity %lld < %lld", (long long)capacity, (long long)n);
+  float* d = nullptr;
+  CK(cudaMalloc(&d, n * 4));
+  vsb::launch_to_f32(b.ptr, b.dtype, d, n, e->stream);
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess) err = cudaMemcpyAsync(out, d, n * 4, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  cudaFree(d);
+  CK(err);
+  return VSB_OK;
+}
+
+int vsb_set_profiling(vsb_engine* e, int32_t on) {
+  if (!e) return fail(VSB_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  prof_collect(e);
+  e->profiling = on != 0;
+  for (int i = 0; i < PC_N; ++i) {
+    e->prof_ms[i] = 0.f;
+    e->prof_launches[i] = 0;
+  }
+  return VSB_OK;
+}
+
+int vsb_stage_ms(vsb_engine* e, int32_t stage, float* ms, int64_t* launches) {
+  if (!e || stage < 0 || stage >= PC_N) return fail(VSB_ERR_INVALID, "bad stage");
+  prof_collect(e);
+  if (ms) *ms = e->prof_ms[stage];
+  if (launches) *launches = e->prof_launches[stage];
+  return VSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// Internal launcher prototypes shared by the engine and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vsb200.h"
+
+namespace vsb {
+
+// ---- packed key --------------------------------------------
+//  [63:48] fp16 bits of p_max (RNE from fp32; order-isomorphic for p >= 0)
+//  [47:44] 15 - d        (earliest direction wins ties, as numpy argmax does)
+//  [43:36] label
+//  [35:32] 0
+//  [31: 0] fp32 bits of p_max (diagnostic only; below every tie-break field)
+__host__ __device__ inline unsigned long long pack_key(uint16_t h, int d, uint32_t label,
+                                                       uint32_t f32bits) {
+  return ((unsigned long long)h << 48) | ((unsigned long long)(15 - d) << 44) |
+         ((unsigned long long)(label & 0xffu) << 36) | (unsigned long long)f32bits;
+}
+
+struct SrcView {
+  const void* ptr;  // NHWC bf16
+  int C, H, W;      // stored dims (before the optional x2 nearest upsample)
+  int up;
+};
+
+struct ConvArgs {
+  SrcView src[VSB_MAX_SRC];
+  int n_src;
+  int NB, H, W;  // output dims
+  int cin, cout, kh, kw, stride, pad, dil, groups, relu;
+  const void* weights;   // bf16 OHWI [cout][kh][kw][cin/groups]
+  const float* bias;     // f32 [cout]
+  const void* residual;  // bf16 NHWC [NB,H,W,cout] or null
+  void* out;             // bf16 or f32 NHWC [NB,H,W,cout]
+  int out_f32;
+};
+
+struct HeadArgs {
+  const float* logits;  // f32 [nb, Hl, Wl, C]   (Hl = Hp/factor)
+  int C, factor;        // factor > 1: bilinear align_corners=True upsampling
+  int nb;
+  vsb_direction g;
+  int d;
+  int64_t s0;
+  unsigned long long* keys;  // or null in vote mode
+  uint8_t* votes;            // [C][Z*Y*X] or null
+  int64_t nvox;
+};
+
+void launch_slicer(const uint8_t* vol, const vsb_direction& g, int64_t s0, int nb, uint16_t* out,
+                   cudaStream_t st);
+void launch_stem7x7(const uint16_t* in, int NB, int Hin, int Win, const void* w_bf16,
+                    const float* bias, uint16_t* out, int relu, cudaStream_t st);
+void launch_maxpool3x3s2(const uint16_t* in, int NB, int Hin, int Win, int C, uint16_t* out,
+                         cudaStream_t st);
+void launch_conv_simt(const ConvArgs& a, cudaStream_t st);
+void launch_gap(const uint16_t* in, int NB, int H, int W, int C, uint16_t* out, cudaStream_t st);
+void launch_upsample(const uint16_t* in, int NB, int Hin, int Win, int C, int Hout, int Wout,
+                     int mode, uint16_t* out, cudaStream_t st);
+void launch_head(const HeadArgs& a, cudaStream_t st);
+void launch_merge_injected(const float* probs, const uint8_t* labels, const vsb_direction& g, int d,
+                           unsigned long long* keys, cudaStream_t st);
+void launch_unpack(const unsigned long long* keys, int64_t n, uint8_t* labels, uint16_t* probs,
+                   cudaStream_t st);
+void launch_f32_to_bf16(const float* in, uint16_t* out, int64_t n, cudaStream_t st);
+void launch_to_f32(const void* in, int is_f32, float* out, int64_t n, cudaStream_t st);
+
+}  // namespace vsb

@@ -1,0 +1,175 @@
+"""Python handle over one libvsb200 engine (one GPU).
+
+Only marshals numpy buffers and plans across the C ABI (include/vsb200.h); all
+arithmetic of the hot path happens in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .plan import B200SegmentationModel, Plan, lower_to_plan
+
+ALL_12 = (1 << 12) - 1
+# directions whose image sets duplicate an earlier one
+DUPLICATE_OF = {3: 1, 6: 4, 9: 7, 10: 0}
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.vsb_create(int(device), C.byref(h)))
+        self.h = h
+        self.device = int(device)
+        self._plan: Optional[Plan] = None
+        self._plan_key = None
+        self.shape: Optional[Tuple[int, int, int]] = None
+        self.classes = 0
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.vsb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plan -------------------------------------------------------------------
+    def load_model(self, model: B200SegmentationModel) -> None:
+        """(Re)lower the module's current weights.  Called whenever ``.model`` is
+        replaced (reference vol_seg_2d_predictor.py:28-29)."""
+        plan = lower_to_plan(model)
+        _lib.check(
+            self.lib.vsb_load_plan(self.h, plan.tensors, len(plan.tensors), plan.ops, len(plan.ops),
+                                   _ptr(plan.blob), plan.blob.size, plan.classes)
+        )
+        self._plan = plan
+        self._plan_key = id(model)
+        self.classes = plan.classes
+        self.shape = None
+
+    def ensure_model(self, model: B200SegmentationModel) -> None:
+        if self._plan_key != id(model):
+            self.load_model(model)
+
+    # -- volume -------------------------------------------------------------------
+    def set_volume(self, vol: np.ndarray) -> None:
+        if vol.dtype != np.uint8 or vol.ndim != 3:
+            raise ValueError("set_volume expects a 3-D uint8 array")
+        vol = np.ascontiguousarray(vol)
+        z, y, x = vol.shape
+        _lib.check(self.lib.vsb_set_volume(self.h, _ptr(vol), 0, z, y, x))
+        _lib.check(self.lib.vsb_synchronize(self.h))  # host buffer may go away
+        self.shape = (z, y, x)
+
+    def set_volume_device(self, dev_ptr: int, shape: Tuple[int, int, int]) -> None:
+        z, y, x = shape
+        _lib.check(self.lib.vsb_set_volume(self.h, C.c_void_p(dev_ptr), 1, z, y, x))
+        self.shape = (z, y, x)
+
+    def reset(self) -> None:
+        _lib.check(self.lib.vsb_reset_keys(self.h))
+
+    # -- prediction ---------------------------------------------------------------
+    def predict(self, dir_mask: int, skip_duplicates: bool = True) -> None:
+        _lib.check(self.lib.vsb_predict(self.h, dir_mask, int(skip_duplicates)))
+
+    def predict_range(self, d: int, s0: int, s1: int) -> None:
+        _lib.check(self.lib.vsb_predict_range(self.h, d, s0, s1))
+
+    def synchronize(self) -> None:
+        _lib.check(self.lib.vsb_synchronize(self.h))
+
+    def fetch(self, want_probs: bool = True):
+        z, y, x = self.shape
+        labels = np.empty((z, y, x), np.uint8)
+        probs = np.empty((z, y, x), np.float16) if want_probs else None
+        _lib.check(self.lib.vsb_fetch(self.h, _ptr(labels), _ptr(probs) if want_probs else None))
+        return labels, probs
+
+    def keys_ptr(self) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.vsb_keys(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def bind_keys(self, dev_ptr: int) -> None:
+        _lib.check(self.lib.vsb_bind_keys(self.h, C.c_void_p(dev_ptr)))
+
+    def unpack_device(self, labels_ptr: int, probs_ptr: int = 0) -> None:
+        _lib.check(self.lib.vsb_unpack_device(self.h, C.c_void_p(labels_ptr),
+                                              C.c_void_p(probs_ptr) if probs_ptr else None))
+
+    def set_vote_mode(self, on: bool) -> None:
+        _lib.check(self.lib.vsb_set_vote_mode(self.h, int(on)))
+
+    def fetch_votes(self) -> np.ndarray:
+        z, y, x = self.shape
+        votes = np.empty((self.classes, z, y, x), np.uint8)
+        _lib.check(self.lib.vsb_fetch_votes(self.h, _ptr(votes)))
+        return votes
+
+    def set_batch(self, n: int) -> None:
+        _lib.check(self.lib.vsb_set_batch(self.h, n))
+
+    def set_conv_impl(self, impl: str) -> None:
+        _lib.check(self.lib.vsb_set_conv_impl(self.h, {"tc": 0, "simt": 1, "generic": 2}[impl]))
+
+    # -- test hooks ---------------------------------------------------------------
+    def geometry(self, d: int) -> _lib.Direction:
+        z, y, x = self.shape
+        return _lib.direction_geometry(z, y, x, d)
+
+    def slice_batch(self, d: int, s0: int, nb: int) -> np.ndarray:
+        g = self.geometry(d)
+        out = np.empty((nb, g.Hp, g.Wp), np.uint16)
+        _lib.check(self.lib.vsb_slice_batch(self.h, d, s0, nb, _ptr(out)))
+        return out
+
+    def merge_injected(self, d: int, probs: np.ndarray, labels: np.ndarray) -> None:
+        g = self.geometry(d)
+        probs = np.ascontiguousarray(probs, np.float32)
+        labels = np.ascontiguousarray(labels, np.uint8)
+        if probs.shape != (g.S, g.H, g.W) or labels.shape != probs.shape:
+            raise ValueError(f"direction {d} expects shape {(g.S, g.H, g.W)}, got {probs.shape}")
+        _lib.check(self.lib.vsb_merge_injected(self.h, d, _ptr(probs), _ptr(labels)))
+
+    def forward_logits(self, model: B200SegmentationModel, images: np.ndarray) -> np.ndarray:
+        """images f32 [nb,Hp,Wp] (padded + normalised) -> logits f32 [nb,Hl,Wl,C]."""
+        self.ensure_model(model)
+        images = np.ascontiguousarray(images, np.float32)
+        nb, hp, wp = images.shape
+        head = model.spec.layers[-1]
+        f = head.factor
+        out = np.empty((nb, hp // f, wp // f, self.classes), np.float32)
+        _lib.check(self.lib.vsb_forward_logits(self.h, _ptr(images), nb, hp, wp, _ptr(out)))
+        return out
+
+    def debug_tensor(self, t: int) -> np.ndarray:
+        shp = (C.c_int64 * 4)()
+        _lib.check(self.lib.vsb_debug_tensor(self.h, t, None, 0, shp))
+        out = np.empty(tuple(shp), np.float32)
+        _lib.check(self.lib.vsb_debug_tensor(self.h, t, _ptr(out), out.size, shp))
+        return out
+
+    # -- profiling ------------------------------------------------------------------
+    def set_profiling(self, on: bool) -> None:
+        _lib.check(self.lib.vsb_set_profiling(self.h, int(on)))
+
+    def stage_times(self) -> Dict[str, Tuple[float, int]]:
+        out = {}
+        for i, name in enumerate(_lib.PROF_CLASSES):
+            ms, n = C.c_float(), C.c_int64()
+            _lib.check(self.lib.vsb_stage_ms(self.h, i, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
