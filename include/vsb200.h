@@ -88,6 +88,9 @@ typedef struct {
 } vsb_direction;
 
 int vsb_abi_version(void);
+/* 16-bit format of activations and weights in this build: 0 = bfloat16,
+ * 1 = IEEE half.  The weight blob handed to vsb_load_plan must use it.       */
+int vsb_act_dtype(void);
 const char* vsb_last_error(void);
 
 /* VolSeg2dPredictor.__init__ (vol_seg_2d_predictor.py:19-26): bind a GPU.   */
@@ -145,6 +148,13 @@ int vsb_set_vote_mode(vsb_engine* e, int32_t on);
 int vsb_fetch_votes(vsb_engine* e, uint8_t* votes);
 
 int vsb_synchronize(vsb_engine* e);
+
+/* Run on a caller-owned CUDA stream (cudaStream_t), e.g. torch's current stream,
+ * so host-side events and NCCL collectives order with the engine's kernels.
+ * NULL returns to the engine's own stream.                                   */
+int vsb_set_stream(vsb_engine* e, void* cuda_stream);
+/* Number of kernels this engine has launched (optionally reset).            */
+int vsb_launch_count(vsb_engine* e, int64_t* count, int32_t reset);
 
 /* Slices processed per launch (reference: 4, config.py:31). 0 = automatic.   */
 int vsb_set_batch(vsb_engine* e, int32_t slices_per_batch);

@@ -20,8 +20,9 @@ from .smp_models import make_random_model
 OUT = Path(__file__).resolve().parents[1] / "tests" / "golden"
 
 
-def bf16_bits(a: np.ndarray) -> np.ndarray:
-    return torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+def act_bits(a: np.ndarray, dtype=torch.bfloat16) -> np.ndarray:
+    """16-bit RNE encoding (bfloat16 or float16) of an fp32 array, as uint16 bits."""
+    return torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(dtype).view(torch.int16).numpy().view(np.uint16)
 
 
 def synth_volume(shape, seed):
@@ -46,13 +47,14 @@ def make_slicer():
     for si, shape in enumerate(SLICER_SHAPES):
         vol = synth_volume(shape, 100 + si)
         for d in range(12):
-            bits = bf16_bits(po.slicer_oracle(vol, d))
+            ref = po.slicer_oracle(vol, d)
             digests[f"{shape}|{d}"] = {
-                "shape": list(bits.shape),
-                "sha256": hashlib.sha256(bits.tobytes()).hexdigest(),
+                "shape": list(ref.shape),
+                "sha256_bf16": hashlib.sha256(act_bits(ref, torch.bfloat16).tobytes()).hexdigest(),
+                "sha256_f16": hashlib.sha256(act_bits(ref, torch.float16).tobytes()).hexdigest(),
             }
             if si == 0:
-                full[f"d{d}"] = bits
+                full[f"d{d}"] = ref.astype(np.float32)
     (OUT / "slicer_digests.json").write_text(json.dumps(digests, indent=1))
     np.savez_compressed(OUT / "slicer_small.npz", **full)
 

@@ -114,11 +114,19 @@ def main():
         ("PS up(128)+skip(64)->256", dict(cin=128, cout=256, up=True, skip=64)),
         ("3x3 48->48 (KB16 x3)", dict(cin=48, cout=48)),
     ]
-    for name, kw in probes:
-        ok &= run_probe(eng, name, 64, 96, 3, **kw)
-    for name, kw in probes[:3] + probes[7:8] + probes[10:11]:
-        ok &= run_probe(eng, name + " [32x32,nb5]", 32, 32, 5, **kw)
-    print("probes", "ALL OK" if ok else "SOME FAILED", time.time() - t0)
+    allp = [(n, 64, 96, 3, kw) for n, kw in probes]
+    allp += [(n + " [32x32,nb5]", 32, 32, 5, kw) for n, kw in probes[:3] + probes[7:8] + probes[10:11]]
+    allp += [(n + " [160x224,nb2]", 160, 224, 2, kw) for n, kw in probes[:1] + probes[10:11]]
+    args = sys.argv[1:]
+    if args and args[0] == "--count":
+        print(len(allp))
+        return
+    if args and args[0] == "--probe":
+        for i in args[1].split(","):
+            n, hp, wp, nb, kw = allp[int(i)]
+            ok &= run_probe(eng, f"#{i} " + n, hp, wp, nb, **kw)
+        print("probes", "ALL OK" if ok else "SOME FAILED", time.time() - t0)
+        return
 
     # ---- whole network vs oracle ------------------------------------------------
     torch.set_num_threads(8)

@@ -43,7 +43,35 @@ def unet_r34():
     return oracle, model
 
 
-def bf16_bits(a):
+@pytest.fixture(scope="session")
+def trained_unet_r34():
+    """(oracle model, B200 model) after ~40 Adam steps on synthetic labels, so the
+    network is decisive like a real checkpoint (oracle/train_synth.py)."""
     import torch
 
-    return torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    from oracle.train_synth import make_trained_model
+    from volume_segmantics_b200.plan import B200SegmentationModel
+
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    oracle, _ = make_trained_model("unet", "resnet34", 4, seed=0, steps=40)
+    model = B200SegmentationModel("U_NET", "resnet34", 4)
+    model.load_state_dict(oracle.state_dict())
+    return oracle, model
+
+
+def act_bits(a, dtype=None):
+    """uint16 bits of `a` rounded (RNE) to the library build's 16-bit format."""
+    import torch
+
+    from volume_segmantics_b200 import _lib
+
+    dtype = dtype or _lib.act_dtype()
+    return torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(dtype).view(torch.int16).numpy().view(np.uint16)
+
+
+def act_tag():
+    import torch
+
+    from volume_segmantics_b200 import _lib
+
+    return "f16" if _lib.act_dtype() == torch.float16 else "bf16"

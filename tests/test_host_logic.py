@@ -91,13 +91,13 @@ def test_bn_folding_matches_torch():
     m.load_state_dict(oracle.state_dict())
     L = next(l for l in m.spec.layers if l.name == "encoder.layer2.0.conv1")
     w_bits, b = _fold(m.state_dict(), L)
-    w = torch.from_numpy(w_bits.view(np.int16).copy()).view(torch.bfloat16).float().permute(0, 3, 1, 2)
+    w = torch.from_numpy(w_bits.view(np.int16).copy()).view(_lib.act_dtype()).float().permute(0, 3, 1, 2)
     x = torch.randn(1, 64, 9, 9)
     blk = oracle.encoder.layer2[0]
     with torch.no_grad():
         want = blk.bn1(blk.conv1(x))
         got = torch.nn.functional.conv2d(x, w, torch.from_numpy(b), stride=2, padding=1)
-    assert torch.allclose(got, want, atol=3e-2, rtol=1e-2)  # bf16 weight rounding only
+    assert torch.allclose(got, want, atol=3e-2, rtol=1e-2)  # 16-bit weight rounding only
 
 
 def test_plan_lowering_tables():

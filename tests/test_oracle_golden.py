@@ -6,7 +6,9 @@ import json
 import numpy as np
 import torch
 
-from conftest import bf16_bits
+import torch as _t
+
+from conftest import act_bits
 from oracle import make_golden as mg
 from oracle import predict_oracle as po
 
@@ -16,10 +18,11 @@ def test_slicer_oracle_digests(golden_dir):
     for si, shape in enumerate(mg.SLICER_SHAPES[:3]):
         vol = mg.synth_volume(shape, 100 + si)
         for d in range(12):
-            bits = bf16_bits(po.slicer_oracle(vol, d))
+            ref = po.slicer_oracle(vol, d)
             rec = digests[f"{shape}|{d}"]
-            assert list(bits.shape) == rec["shape"]
-            assert hashlib.sha256(bits.tobytes()).hexdigest() == rec["sha256"]
+            assert list(ref.shape) == rec["shape"]
+            assert hashlib.sha256(act_bits(ref, _t.bfloat16).tobytes()).hexdigest() == rec["sha256_bf16"]
+            assert hashlib.sha256(act_bits(ref, _t.float16).tobytes()).hexdigest() == rec["sha256_f16"]
 
 
 def test_slicer_oracle_is_reflect101_centre_pad():

@@ -7,10 +7,14 @@ the header declares, importing the binding raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libvsb200.so"
+# VSB200_VARIANT=bf16 selects the bfloat16 build; default is the fp16 build
+# (same tcgen05 rate, 8x finer mantissa -- see DESIGN.md "numeric format").
+VARIANT = os.environ.get("VSB200_VARIANT", "f16")
+LIB_PATH = HERE / ("libvsb200.so" if VARIANT == "f16" else f"libvsb200_{VARIANT}.so")
 
 VSB_MAX_SRC = 6
 VSB_OP_CONV, VSB_OP_MAXPOOL, VSB_OP_GAP, VSB_OP_UPSAMPLE, VSB_OP_HEAD = 1, 2, 3, 4, 5
@@ -64,6 +68,7 @@ class VsbError(RuntimeError):
 _P = C.c_void_p
 SIGNATURES = {
     "vsb_abi_version": (C.c_int, []),
+    "vsb_act_dtype": (C.c_int, []),
     "vsb_last_error": (C.c_char_p, []),
     "vsb_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "vsb_destroy": (None, [_P]),
@@ -80,6 +85,8 @@ SIGNATURES = {
     "vsb_set_vote_mode": (C.c_int, [_P, C.c_int32]),
     "vsb_fetch_votes": (C.c_int, [_P, _P]),
     "vsb_synchronize": (C.c_int, [_P]),
+    "vsb_set_stream": (C.c_int, [_P, _P]),
+    "vsb_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64), C.c_int32]),
     "vsb_set_batch": (C.c_int, [_P, C.c_int32]),
     "vsb_set_conv_impl": (C.c_int, [_P, C.c_int32]),
     "vsb_slice_batch": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int32, _P]),
@@ -116,6 +123,13 @@ def check(rc: int) -> None:
     if rc != 0:
         msg = load().vsb_last_error()
         raise VsbError(f"libvsb200 error {rc}: {msg.decode() if msg else ''}")
+
+
+def act_dtype():
+    """torch dtype of activations/weights in the loaded library build."""
+    import torch
+
+    return torch.float16 if load().vsb_act_dtype() == 1 else torch.bfloat16
 
 
 def direction_geometry(Z: int, Y: int, X: int, d: int) -> Direction:

@@ -13,7 +13,8 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-LIB = HERE / "libvsb200.so"
+LIB = HERE / "libvsb200.so"          # fp16 activations/weights (default)
+LIB_BF16 = HERE / "libvsb200_bf16.so"  # bfloat16 variant (VSB200_VARIANT=bf16)
 SOURCES = ["engine.cu", "conv_tc.cu", "kernels_simple.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -23,9 +24,9 @@ NVCC_FLAGS = [
 
 
 def _stale() -> bool:
-    if not LIB.exists():
+    if not LIB.exists() or not LIB_BF16.exists():
         return True
-    t = LIB.stat().st_mtime
+    t = min(LIB.stat().st_mtime, LIB_BF16.stat().st_mtime)
     deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h"))
     deps.append(HERE.parent / "include" / "vsb200.h")
     return any(d.stat().st_mtime > t for d in deps)
@@ -35,24 +36,26 @@ def build(force: bool = False, verbose: bool = True) -> Path:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    objs = []
-    procs = []
     builddir = HERE / "build"
     builddir.mkdir(exist_ok=True)
-    for src in SOURCES:
-        obj = builddir / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
-        if verbose:
-            print(" ".join(cmd), flush=True)
-        procs.append((src, subprocess.Popen(cmd)))
-        objs.append(str(obj))
+    variants = [("f16", LIB, "-DVSB_ACT_F16=1"), ("bf16", LIB_BF16, "-DVSB_ACT_F16=0")]
+    procs = []
+    for tag, _, define in variants:
+        for src in SOURCES:
+            obj = builddir / f"{src}.{tag}.o"
+            cmd = [nvcc, *NVCC_FLAGS, define, "-c", str(CSRC / src), "-o", str(obj)]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            procs.append((src, subprocess.Popen(cmd)))
     for src, p in procs:
         if p.wait() != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", str(LIB), *objs]
-    if verbose:
-        print(" ".join(cmd), flush=True)
-    subprocess.check_call(cmd)
+    for tag, lib, _ in variants:
+        objs = [str(builddir / f"{src}.{tag}.o") for src in SOURCES]
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", str(lib), *objs]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
     return LIB
 
 

@@ -12,19 +12,42 @@ namespace vsb {
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// ---------------------------------------------------------------- bf16 utils
-__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) {
+// ---------------------------------------------------------------- activation format
+// Activations and weights are 16-bit.  VSB_ACT_F16=0: bfloat16 (8-bit mantissa,
+// fp32 range).  VSB_ACT_F16=1: IEEE half (11-bit mantissa; stores saturate to
+// +-65504 instead of overflowing).  Both run tcgen05 kind::f16 at the same rate.
+#ifndef VSB_ACT_F16
+#define VSB_ACT_F16 0
+#endif
+__device__ __forceinline__ float act_to_float(uint16_t b) {
+#if VSB_ACT_F16
+  return __half2float(__ushort_as_half(b));
+#else
   return __uint_as_float(((uint32_t)b) << 16);
+#endif
 }
-__device__ __forceinline__ uint16_t float_to_bf16_bits(float f) {
+__device__ __forceinline__ uint16_t float_to_act(float f) {
+#if VSB_ACT_F16
+  return __half_as_ushort(__float2half_rn(fminf(fmaxf(f, -65504.f), 65504.f)));
+#else
   return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+#endif
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
+#if VSB_ACT_F16
+  __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+  return *reinterpret_cast<uint32_t*>(&v);
+#else
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+#endif
 }
-__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+__device__ __forceinline__ float2 unpack_act2(uint32_t v) {
+#if VSB_ACT_F16
+  return __half22float2(*reinterpret_cast<__half2*>(&v));
+#else
   return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+#endif
 }
 
 // ---------------------------------------------------------------- smem / mbarrier
@@ -208,9 +231,11 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) |
          (layout << 61);
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N.
-__host__ __device__ inline uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) |
+// kind::f16 instruction descriptor: D=f32, A=B=bf16 (format 1) or f16 (format 0),
+// both K-major, M x N.
+__host__ __device__ inline uint32_t umma_idesc_act(int m, int n) {
+  const uint32_t fmt = VSB_ACT_F16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(m >> 4) << 24);
 }
 

@@ -134,7 +134,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t idesc = umma_idesc_bf16(128, p.BN);
+      const uint32_t idesc = umma_idesc_act(128, p.BN);
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(&ctl->acc_empty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
@@ -215,13 +215,13 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
                 const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const float2 rf = unpack_bf16x2(rw[j]);
+                  const float2 rf = unpack_act2(rw[j]);
                   f[2 * j] += rf.x;
                   f[2 * j + 1] += rf.y;
                 }
               } else {
                 for (int j = 0; j < 8 && ch + j < p.cout; ++j)
-                  f[j] += bf16_bits_to_float(p.residual[pix * p.cout + ch + j]);
+                  f[j] += act_to_float(p.residual[pix * p.cout + ch + j]);
               }
             }
             if (p.relu) {
@@ -240,13 +240,13 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
               uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + pix * p.cout + ch;
               if (full8 && (p.cout & 7) == 0) {
                 uint4 pk;
-                pk.x = pack_bf16x2(f[0], f[1]);
-                pk.y = pack_bf16x2(f[2], f[3]);
-                pk.z = pack_bf16x2(f[4], f[5]);
-                pk.w = pack_bf16x2(f[6], f[7]);
+                pk.x = pack_act2(f[0], f[1]);
+                pk.y = pack_act2(f[2], f[3]);
+                pk.z = pack_act2(f[4], f[5]);
+                pk.w = pack_act2(f[6], f[7]);
                 *reinterpret_cast<uint4*>(o) = pk;
               } else {
-                for (int j = 0; j < 8 && ch + j < p.cout; ++j) o[j] = float_to_bf16_bits(f[j]);
+                for (int j = 0; j < 8 && ch + j < p.cout; ++j) o[j] = float_to_act(f[j]);
               }
             }
           }

@@ -95,6 +95,8 @@ struct vsb_engine {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int64_t launches = 0;
   EncodeTiledFn encode = nullptr;
 
   // plan
@@ -188,12 +190,6 @@ int direction_geometry(int64_t Z, int64_t Y, int64_t X, int d, vsb_direction* g)
 // Plan-time preparation of a tcgen05 convolution: eligibility, N tiling, the
 // K-slab table and the pre-swizzled weight image.
 // ---------------------------------------------------------------------------
-uint16_t h_bf16(const std::vector<uint8_t>& blob, int64_t byte_off, int64_t idx) {
-  uint16_t v;
-  memcpy(&v, blob.data() + byte_off + idx * 2, 2);
-  return v;
-}
-
 bool conv_tc_eligible(const vsb_engine* e, const vsb_op& op) {
   if (op.kind != VSB_OP_CONV) return false;
   if (op.groups != 1) return false;
@@ -316,7 +312,7 @@ int make_tensor_map(vsb_engine* e, TmaDesc* out_host, const TensorBuf& t, int nb
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUtensorMapSwizzle sw = KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                          : (KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  const CUresult r = e->encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, t.ptr, dims, strides, box, estr,
+  const CUresult r = e->encode(&m, (VSB_ACT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 5, t.ptr, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -451,6 +447,7 @@ struct ProfScope {
   vsb_engine* e;
   int idx = -1;
   ProfScope(vsb_engine* e_, int cls) : e(e_) {
+    e->launches += 1;
     if (!e->profiling) return;
     if (e->ev_used == e->ev_pool.size()) {
       cudaEvent_t a, b;
@@ -635,6 +632,7 @@ int predict_range(vsb_engine* e, int d, int64_t s_begin, int64_t s_end) {
 extern "C" {
 
 int vsb_abi_version(void) { return VSB_ABI_VERSION; }
+int vsb_act_dtype(void) { return VSB_ACT_F16 ? 1 : 0; }
 const char* vsb_last_error(void) { return g_err.c_str(); }
 
 int vsb_direction_geometry(int64_t Z, int64_t Y, int64_t X, int32_t d, vsb_direction* out) {
@@ -659,7 +657,8 @@ int vsb_create(int device, vsb_engine** out) {
   vsb_engine* e = new vsb_engine();
   e->device = device;
   e->num_sms = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  e->stream = e->own_stream;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -698,7 +697,7 @@ void vsb_destroy(vsb_engine* e) {
     cudaEventDestroy(ev.first);
     cudaEventDestroy(ev.second);
   }
-  cudaStreamDestroy(e->stream);
+  cudaStreamDestroy(e->own_stream);
   delete e;
 }
 
@@ -833,6 +832,7 @@ int vsb_bind_keys(vsb_engine* e, void* dev_ptr) {
 int vsb_unpack_device(vsb_engine* e, uint8_t* labels_dev, uint16_t* probs_dev) {
   if (!e || !e->d_keys) return fail(VSB_ERR_STATE, "no volume set");
   CK(cudaSetDevice(e->device));
+  e->launches += 1;
   vsb::launch_unpack(e->d_keys, e->Z * e->Y * e->X, labels_dev, probs_dev, e->stream);
   CK(cudaGetLastError());
   return VSB_OK;
@@ -845,6 +845,7 @@ int vsb_fetch(vsb_engine* e, uint8_t* labels, uint16_t* probs) {
   const int64_t n = e->Z * e->Y * e->X;
   if (!e->d_labels) CK(cudaMalloc(&e->d_labels, align_up(n, 256)));
   if (probs && !e->d_probs) CK(cudaMalloc(&e->d_probs, align_up(n * 2, 256)));
+  e->launches += 1;
   vsb::launch_unpack(e->d_keys, n, e->d_labels, probs ? e->d_probs : nullptr, e->stream);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(labels, e->d_labels, n, cudaMemcpyDeviceToHost, e->stream));
@@ -883,6 +884,22 @@ int vsb_synchronize(vsb_engine* e) {
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
   prof_collect(e);
+  return VSB_OK;
+}
+
+int vsb_set_stream(vsb_engine* e, void* stream) {
+  if (!e) return fail(VSB_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  prof_collect(e);
+  e->stream = stream ? (cudaStream_t)stream : e->own_stream;
+  return VSB_OK;
+}
+
+int vsb_launch_count(vsb_engine* e, int64_t* count, int32_t reset) {
+  if (!e || !count) return fail(VSB_ERR_INVALID, "null argument");
+  *count = e->launches;
+  if (reset) e->launches = 0;
   return VSB_OK;
 }
 
@@ -954,7 +971,7 @@ int vsb_forward_logits(vsb_engine* e, const float* images, int32_t nb, int32_t H
   CK(cudaMalloc(&dimg, n * 4));
   cudaError_t err = cudaMemcpyAsync(dimg, images, n * 4, cudaMemcpyHostToDevice, e->stream);
   if (err == cudaSuccess) {
-    vsb::launch_f32_to_bf16(dimg, (uint16_t*)e->tens[0].ptr, n, e->stream);
+    vsb::launch_f32_to_act(dimg, (uint16_t*)e->tens[0].ptr, n, e->stream);
     err = cudaGetLastError();
   }
   int head = -1;

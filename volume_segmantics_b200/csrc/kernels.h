@@ -64,7 +64,7 @@ void launch_merge_injected(const float* probs, const uint8_t* labels, const vsb_
                            unsigned long long* keys, cudaStream_t st);
 void launch_unpack(const unsigned long long* keys, int64_t n, uint8_t* labels, uint16_t* probs,
                    cudaStream_t st);
-void launch_f32_to_bf16(const float* in, uint16_t* out, int64_t n, cudaStream_t st);
+void launch_f32_to_act(const float* in, uint16_t* out, int64_t n, cudaStream_t st);
 void launch_to_f32(const void* in, int is_f32, float* out, int64_t n, cudaStream_t st);
 
 }  // namespace vsb

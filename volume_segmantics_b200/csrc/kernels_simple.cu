@@ -28,7 +28,7 @@ __device__ __forceinline__ uint16_t normalise_u8(int v) {
   float f = __fdiv_rn((float)v, 255.0f);
   f = __fsub_rn(f, 0.449f);
   f = __fdiv_rn(f, 0.226f);
-  return float_to_bf16_bits(f);
+  return float_to_act(f);
 }
 
 // ---------------------------------------------------------------------------
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(128) stem7x7_kernel(const uint16_t* __restrict
   __shared__ float bs[64];
   for (int i = threadIdx.x; i < 49 * 64; i += blockDim.x) {
     const int co = i / 49, t = i % 49;
-    ws[t][co] = bf16_bits_to_float(w[i]);
+    ws[t][co] = act_to_float(w[i]);
   }
   if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(128) stem7x7_kernel(const uint16_t* __restrict
       for (int kx = 0; kx < 7; ++kx) {
         const int ix = 2 * ox + kx - 3;
         const bool ok = iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
-        xin[ky * 7 + kx] = ok ? bf16_bits_to_float(__ldg(img + (int64_t)iy * Win + ix)) : 0.f;
+        xin[ky * 7 + kx] = ok ? act_to_float(__ldg(img + (int64_t)iy * Win + ix)) : 0.f;
       }
     }
     uint16_t* o = out + i * 64;
@@ -200,10 +200,10 @@ __global__ void __launch_bounds__(128) stem7x7_kernel(const uint16_t* __restrict
           if (relu) v[j] = fmaxf(v[j], 0.f);
         }
         uint4 pk;
-        pk.x = pack_bf16x2(v[0], v[1]);
-        pk.y = pack_bf16x2(v[2], v[3]);
-        pk.z = pack_bf16x2(v[4], v[5]);
-        pk.w = pack_bf16x2(v[6], v[7]);
+        pk.x = pack_act2(v[0], v[1]);
+        pk.y = pack_act2(v[2], v[3]);
+        pk.z = pack_act2(v[4], v[5]);
+        pk.w = pack_act2(v[6], v[7]);
         *reinterpret_cast<uint4*>(o + half * 32 + c8 * 8) = pk;
       }
     }
@@ -249,17 +249,17 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const uint16_t* __restrict
         const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16x2(w4[j]);
+          const float2 f = unpack_act2(w4[j]);
           m[2 * j] = fmaxf(m[2 * j], f.x);
           m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
         }
       }
     }
     uint4 pk;
-    pk.x = pack_bf16x2(m[0], m[1]);
-    pk.y = pack_bf16x2(m[2], m[3]);
-    pk.z = pack_bf16x2(m[4], m[5]);
-    pk.w = pack_bf16x2(m[6], m[7]);
+    pk.x = pack_act2(m[0], m[1]);
+    pk.y = pack_act2(m[2], m[3]);
+    pk.z = pack_act2(m[4], m[5]);
+    pk.w = pack_act2(m[6], m[7]);
     *reinterpret_cast<uint4*>(out + i * 8) = pk;
   }
 }
@@ -309,18 +309,18 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
               const uint16_t* px =
                   (const uint16_t*)sv.ptr + ((n * sv.H + sy) * (int64_t)sv.W + sx) * sv.C;
               for (int c = lo; c < hi; ++c)
-                acc = fmaf(bf16_bits_to_float(__ldg(px + (c - cbase))),
-                           bf16_bits_to_float(__ldg(wrow + (c - ci_lo))), acc);
+                acc = fmaf(act_to_float(__ldg(px + (c - cbase))),
+                           act_to_float(__ldg(wrow + (c - ci_lo))), acc);
             }
           }
           cbase += sv.C;
         }
       }
     }
-    if (a.residual) acc += bf16_bits_to_float(((const uint16_t*)a.residual)[i]);
+    if (a.residual) acc += act_to_float(((const uint16_t*)a.residual)[i]);
     if (a.relu) acc = fmaxf(acc, 0.f);
     if (a.out_f32) ((float*)a.out)[i] = acc;
-    else ((uint16_t*)a.out)[i] = float_to_bf16_bits(acc);
+    else ((uint16_t*)a.out)[i] = float_to_act(acc);
   }
 }
 
@@ -343,12 +343,12 @@ __global__ void __launch_bounds__(256) gap_kernel(const uint16_t* __restrict__ i
   float s = 0.f;
   const int64_t hw = (int64_t)H * W;
   if (c < C)
-    for (int64_t p = part; p < hw; p += 4) s += bf16_bits_to_float(in[((int64_t)n * hw + p) * C + c]);
+    for (int64_t p = part; p < hw; p += 4) s += act_to_float(in[((int64_t)n * hw + p) * C + c]);
   red[part][threadIdx.x & 63] = s;
   __syncthreads();
   if (part == 0 && c < C) {
     s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
-    out[(int64_t)n * C + c] = float_to_bf16_bits(s / (float)hw);
+    out[(int64_t)n * C + c] = float_to_act(s / (float)hw);
   }
 }
 void launch_gap(const uint16_t* in, int NB, int H, int W, int C, uint16_t* out, cudaStream_t st) {
@@ -372,20 +372,20 @@ __global__ void __launch_bounds__(256) upsample_kernel(const uint16_t* __restric
     const int64_t n = i / ((int64_t)C * Wout * Hout);
     float v;
     if (mode == 1) {
-      v = bf16_bits_to_float(in[n * C + c]);
+      v = act_to_float(in[n * C + c]);
     } else {
       const float fy = sy * oy, fx = sx * ox;
       const int y0 = (int)fy, x0 = (int)fx;
       const int y1 = min(y0 + 1, Hin - 1), x1 = min(x0 + 1, Win - 1);
       const float ly = fy - y0, lx = fx - x0;
       const uint16_t* b = in + n * (int64_t)Hin * Win * C + c;
-      const float v00 = bf16_bits_to_float(b[((int64_t)y0 * Win + x0) * C]);
-      const float v01 = bf16_bits_to_float(b[((int64_t)y0 * Win + x1) * C]);
-      const float v10 = bf16_bits_to_float(b[((int64_t)y1 * Win + x0) * C]);
-      const float v11 = bf16_bits_to_float(b[((int64_t)y1 * Win + x1) * C]);
+      const float v00 = act_to_float(b[((int64_t)y0 * Win + x0) * C]);
+      const float v01 = act_to_float(b[((int64_t)y0 * Win + x1) * C]);
+      const float v10 = act_to_float(b[((int64_t)y1 * Win + x0) * C]);
+      const float v11 = act_to_float(b[((int64_t)y1 * Win + x1) * C]);
       v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
     }
-    out[i] = float_to_bf16_bits(v);
+    out[i] = float_to_act(v);
   }
 }
 void launch_upsample(const uint16_t* in, int NB, int Hin, int Win, int C, int Hout, int Wout,
@@ -532,19 +532,19 @@ void launch_unpack(const unsigned long long* keys, int64_t n, uint8_t* labels, u
   unpack_kernel<<<grid, 256, 0, st>>>(keys, n, labels, probs);
 }
 
-__global__ void f32_to_bf16_kernel(const float* in, uint16_t* out, int64_t n) {
+__global__ void f32_to_act_kernel(const float* in, uint16_t* out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = float_to_bf16_bits(in[i]);
+    out[i] = float_to_act(in[i]);
 }
-void launch_f32_to_bf16(const float* in, uint16_t* out, int64_t n, cudaStream_t st) {
+void launch_f32_to_act(const float* in, uint16_t* out, int64_t n, cudaStream_t st) {
   const int64_t blocks = (n + 255) / 256;
-  f32_to_bf16_kernel<<<(int)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(in, out, n);
+  f32_to_act_kernel<<<(int)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(in, out, n);
 }
 __global__ void to_f32_kernel(const void* in, int is_f32, float* out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = is_f32 ? ((const float*)in)[i] : bf16_bits_to_float(((const uint16_t*)in)[i]);
+    out[i] = is_f32 ? ((const float*)in)[i] : act_to_float(((const uint16_t*)in)[i]);
 }
 void launch_to_f32(const void* in, int is_f32, float* out, int64_t n, cudaStream_t st) {
   const int64_t blocks = (n + 255) / 256;

@@ -91,10 +91,22 @@ class Engine:
     def synchronize(self) -> None:
         _lib.check(self.lib.vsb_synchronize(self.h))
 
+    @staticmethod
+    def _host_buffer(shape, dtype) -> np.ndarray:
+        """Page-locked host array (torch is the allocator; plumbing only) so the
+        result download runs at PCIe rate instead of through a bounce buffer."""
+        import torch
+
+        tdt = {np.uint8: torch.uint8, np.float16: torch.float16}[dtype]
+        try:
+            return torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
+        except RuntimeError:
+            return np.empty(shape, dtype)
+
     def fetch(self, want_probs: bool = True):
         z, y, x = self.shape
-        labels = np.empty((z, y, x), np.uint8)
-        probs = np.empty((z, y, x), np.float16) if want_probs else None
+        labels = self._host_buffer((z, y, x), np.uint8)
+        probs = self._host_buffer((z, y, x), np.float16) if want_probs else None
         _lib.check(self.lib.vsb_fetch(self.h, _ptr(labels), _ptr(probs) if want_probs else None))
         return labels, probs
 
@@ -118,6 +130,14 @@ class Engine:
         votes = np.empty((self.classes, z, y, x), np.uint8)
         _lib.check(self.lib.vsb_fetch_votes(self.h, _ptr(votes)))
         return votes
+
+    def set_stream(self, cuda_stream: int) -> None:
+        _lib.check(self.lib.vsb_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def launch_count(self, reset: bool = False) -> int:
+        n = C.c_int64()
+        _lib.check(self.lib.vsb_launch_count(self.h, C.byref(n), int(reset)))
+        return n.value
 
     def set_batch(self, n: int) -> None:
         _lib.check(self.lib.vsb_set_batch(self.h, n))

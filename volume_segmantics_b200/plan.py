@@ -8,7 +8,7 @@ pass runs on the B200 engine (no torch compute, no CPU path).
 
 ``lower_to_plan`` folds every eval-mode BatchNorm into its convolution
 (w' = w * g / sqrt(var + eps), b' = beta - mean * g / sqrt(var + eps)) in fp32,
-rounds the weights to bf16 in OHWI order and emits the ctypes tables.
+rounds the weights to the library's 16-bit format in OHWI order and emits the ctypes tables.
 """
 from __future__ import annotations
 
@@ -97,7 +97,10 @@ def _fold(sd: Dict[str, torch.Tensor], L: Layer) -> Tuple[np.ndarray, np.ndarray
         scale = g / torch.sqrt(var + BN_EPS)
         w = w * scale[:, None, None, None]
         b = (b - mean) * scale + beta
-    w_ohwi = w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    w_ohwi = w.permute(0, 2, 3, 1).contiguous()
+    if _lib.act_dtype() == torch.float16:
+        w_ohwi = w_ohwi.clamp(-65504.0, 65504.0)
+    w_ohwi = w_ohwi.to(_lib.act_dtype())
     return w_ohwi.view(torch.int16).numpy().view(np.uint16), b.numpy().astype(np.float32)
 
 
