@@ -185,6 +185,8 @@ int vsb_debug_tensor(vsb_engine* e, int32_t t, float* out, int64_t capacity_elem
  * 5 head+merge, 6 other (pool / up-sample).                                  */
 int vsb_stage_ms(vsb_engine* e, int32_t stage, float* ms, int64_t* launches);
 int vsb_set_profiling(vsb_engine* e, int32_t on);
+/* Same, per op index of the loaded plan (conv / pool ops).                   */
+int vsb_op_ms(vsb_engine* e, int32_t op, float* ms, int64_t* launches);
 
 /* ---- clip_to_uint8 (base_data_utils.py:243-287), SURVEY 8f-1 -------------- */
 /* (declared when implemented) */

@@ -1,0 +1,54 @@
+"""Per-layer timing table of the U-Net/ResNet-34 forward on slices of size^2
+(run by hand under gpurun): ms, TFLOP/s and algorithmic GB/s per conv."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from volume_segmantics_b200.engine import Engine  # noqa: E402
+from volume_segmantics_b200.plan import B200SegmentationModel  # noqa: E402
+
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+nslices = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+batch = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+model = B200SegmentationModel("U_NET", "resnet34", 4)
+eng = Engine(0)
+eng.load_model(model)
+if batch:
+    eng.set_batch(batch)
+vol = np.random.default_rng(0).integers(0, 256, (nslices, size, size), dtype=np.uint8)
+eng.set_volume(vol)
+eng.predict_range(0, 0, nslices)
+eng.synchronize()
+eng.set_profiling(True)
+eng.predict_range(0, 0, nslices)
+eng.synchronize()
+spec = model.spec
+times = eng.op_times(len(spec.layers))
+px = nslices * size * size
+tot_ms = tot_fl = 0
+print(f"size {size} slices {nslices} batch {batch or 'auto'}")
+print(f"{'layer':38s} {'Cin':>5s} {'Cout':>5s} k s {'res':>5s} {'ms':>8s} {'TFLOP/s':>8s} {'GB/s':>7s} {'launch':>6s}")
+for L, (ms, n) in zip(spec.layers, times):
+    if L.kind not in ("conv", "maxpool") or n == 0:
+        continue
+    ds = spec.tensors[L.out].ds_log2
+    opx = px / 4 ** ds
+    if L.kind == "conv":
+        fl = 2.0 * L.k * L.k * (L.cin // L.groups) * L.cout * opx
+        by = 0
+        for t, up in L.srcs:
+            by += spec.tensors[t].channels * 2 * px / 4 ** spec.tensors[t].ds_log2
+        by += L.cout * (4 if spec.tensors[L.out].dtype else 2) * opx
+        if L.res >= 0:
+            by += L.cout * 2 * opx
+    else:
+        fl, by = 0, spec.tensors[L.srcs[0][0]].channels * 2 * px / 4 ** (ds - 1) * 1.25
+    tot_ms += ms
+    tot_fl += fl
+    print(f"{(L.name or L.kind):38s} {L.cin:5d} {L.cout:5d} {L.k} {L.stride} 1/{2**ds:<3d} {ms:8.3f} {fl / ms / 1e9:8.1f} {by / ms / 1e6:7.0f} {n:6d}")
+print(f"total conv+pool ms {tot_ms:.2f}  ->  {tot_fl / tot_ms / 1e9:.1f} TFLOP/s ; per slice {tot_ms / nslices * 1e3:.1f} us")
+print({k: (round(v[0], 2), v[1]) for k, v in eng.stage_times().items()})

@@ -95,6 +95,7 @@ SIGNATURES = {
     "vsb_debug_tensor": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "vsb_stage_ms": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "vsb_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "vsb_op_ms": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
 }
 
 _lib = None

@@ -4,15 +4,20 @@
 //   warp 0      TMA producer: per K-slab, one 5-D box load per pixel class for
 //               the A operand + one linear bulk copy of the pre-swizzled
 //               weights; `full[stage]` mbarrier counts the bytes.
-//   warp 1      TMEM allocator and MMA issuer: one elected lane issues
-//               tcgen05.mma (M=128, N=BN, K=16) row_bytes/32 times per slab,
+//   warp 1      TMEM allocator and MMA issuer: an elected lane issues
+//               tcgen05.mma (M=128, N=BN, K=16) RB/32 times per slab,
 //               tcgen05.commit releases the smem stage (`empty[stage]`) and,
 //               after the last slab, publishes the accumulator (`acc_full`).
-//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator (thread = output
-//               pixel), + folded-BN bias, + residual, ReLU, bf16 (or f32) NHWC
-//               store; `acc_empty` hands the TMEM stage back.  Two accumulator
-//               stages (2 x 256 columns) overlap the epilogue of tile i with
-//               the main loop of tile i+1.
+//   warps 2..9  epilogue: tcgen05.ld the fp32 accumulator (thread = output
+//               pixel; two warps share a TMEM lane quarter and split the
+//               columns), + folded-BN bias, + residual, ReLU, 16-bit (or f32)
+//               NHWC store; `acc_empty` hands the TMEM stage back.  Two
+//               accumulator stages (2 x 256 columns) overlap the epilogue of
+//               tile i with the main loop of tile i+1.
+// The producer and MMA loops run warp-convergent (every lane executes the
+// waits, one elected lane issues), so addresses and descriptors stay in the
+// uniform datapath; the K loop needs no table look-up on the MMA side because
+// the slab width RB is a template parameter.
 //
 // Replaces every cuDNN conv2d + batch_norm + relu_ + add_ + nearest
 // upsample + cat the reference reaches through `self.model(...)`
@@ -32,8 +37,9 @@ struct SmemCtl {
   uint32_t pad[3];
 };
 
-constexpr int kCtlBytes = 1024;      // >= sizeof(SmemCtl)
-constexpr int kBiasBytes = 2048 * 4; // bias for up to 2048 output channels
+constexpr int kCtlBytes = 1024;       // >= sizeof(SmemCtl)
+constexpr int kBiasBytes = 2048 * 4;  // bias for up to 2048 output channels
+constexpr int kRunBytes = TC_MAX_RUNS * (int)sizeof(TcRun);
 
 __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int t, int& n_tile, int& X0,
                                             int& Y0, int& N0) {
@@ -48,8 +54,54 @@ __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int t, int& n
   N0 = tn << p.nt_log2;
 }
 
+// two fp32 -> packed 16-bit pair (lo in the low half), optional ReLU, in one F2FP
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t r;
+#if VSB_ACT_F16
+  if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+#else
+  if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+#endif
+  return r;
+}
+
+template <bool RELU>
+__device__ __forceinline__ void store8(const ConvTcParams& p, const float (&f)[8], int64_t pix,
+                                       int ch, bool full8) {
+  if (p.out_f32) {
+    float* o = reinterpret_cast<float*>(p.out) + pix * p.cout + ch;
+    if (full8 && (p.cout & 3) == 0) {
+      *reinterpret_cast<float4*>(o) =
+          RELU ? make_float4(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f), fmaxf(f[2], 0.f), fmaxf(f[3], 0.f))
+               : make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(o + 4) =
+          RELU ? make_float4(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f), fmaxf(f[6], 0.f), fmaxf(f[7], 0.f))
+               : make_float4(f[4], f[5], f[6], f[7]);
+    } else {
+      for (int j = 0; j < 8 && ch + j < p.cout; ++j) o[j] = RELU ? fmaxf(f[j], 0.f) : f[j];
+    }
+  } else {
+    uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + pix * p.cout + ch;
+    if (full8 && (p.cout & 7) == 0) {
+      uint4 pk;
+      pk.x = pack2<RELU>(f[0], f[1]);
+      pk.y = pack2<RELU>(f[2], f[3]);
+      pk.z = pack2<RELU>(f[4], f[5]);
+      pk.w = pack2<RELU>(f[6], f[7]);
+      *reinterpret_cast<uint4*>(o) = pk;
+    } else {
+      for (int j = 0; j < 8 && ch + j < p.cout; ++j)
+        o[j] = float_to_act(RELU ? fmaxf(f[j], 0.f) : f[j]);
+    }
+  }
+}
+
 }  // namespace
 
+template <int RB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -59,6 +111,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   uint8_t* stages = smem;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + (size_t)p.num_stages * p.stage_bytes);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + kCtlBytes);
+  TcRun* runs_s = reinterpret_cast<TcRun*>(reinterpret_cast<uint8_t*>(bias_s) + kBiasBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,11 +124,17 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->acc_full[i], 1);
-      mbar_init(&ctl->acc_empty[i], 128);
+      mbar_init(&ctl->acc_empty[i], 32 * TC_EPI_WARPS);
     }
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < p.n_tiles * p.BN; i += TC_THREADS) bias_s[i] = p.bias[i];
+  {
+    const int4* src = reinterpret_cast<const int4*>(p.runs);
+    int4* dst = reinterpret_cast<int4*>(runs_s);
+    for (int i = threadIdx.x; i < p.num_runs * (int)(sizeof(TcRun) / 16); i += TC_THREADS)
+      dst[i] = src[i];
+  }
   if (warp == 1) tmem_alloc<512>(&ctl->tmem_base);
   tc_fence_before_sync();
   __syncthreads();
@@ -84,42 +143,34 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int ncls = 1 << p.ncls_log2;
-      const int rows_per_cls = 128 >> p.ncls_log2;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int n_tile, X0, Y0, N0;
-        decode_tile(p, t, n_tile, X0, Y0, N0);
-        for (int s = 0; s < p.num_slabs; ++s) {
-          const TcSlab sl = p.slabs[s];
+    int stage = 0;
+    uint32_t phase = 0;
+    const int ncls = 1 << p.ncls_log2;
+    const uint32_t cls_bytes = (uint32_t)((128 >> p.ncls_log2) * RB);
+    const uint32_t tx_bytes = (uint32_t)((128 + p.BN) * RB);
+    const uint32_t b_bytes = (uint32_t)(p.BN * RB);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n_tile, X0, Y0, N0;
+      decode_tile(p, t, n_tile, X0, Y0, N0);
+      const uint8_t* wtile = p.wpacked + (size_t)n_tile * b_bytes;
+      for (int r = 0; r < p.num_runs; ++r) {
+        const TcRun& run = runs_s[r];
+        const void* map = &p.maps[run.map];
+        const int nblk = run.nblk;
+        const uint8_t* wsrc = wtile + (size_t)run.w_off16 * 16;
+        const size_t wstep = (size_t)run.w_step16 * 16;
+        for (int b = 0; b < nblk; ++b) {
           mbar_wait(&ctl->empty[stage], phase ^ 1);
-          uint8_t* a_dst = stages + (size_t)stage * p.stage_bytes;
-          uint8_t* b_dst = a_dst + p.a_bytes;
-          mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)((128 + p.BN) * sl.row_bytes));
-          const void* map = &p.maps[sl.map];
-          for (int q = 0; q < ncls; ++q) {
-            const int ty = (q >> 1) + sl.dy, tx = (q & 1) + sl.dx;
-            int cy, cx, pary = 0, parx = 0;
-            if (sl.flags & TC_HALVE) {
-              cy = Y0 + (ty >> 1);
-              cx = X0 + (tx >> 1);
-              pary = ty & 1;
-              parx = tx & 1;
-            } else {
-              cy = Y0 + ty;
-              cx = X0 + tx;
-            }
-            const bool folded = (sl.flags & TC_FOLDED) != 0;
-            const int cc = sl.c0 + (folded ? parx * sl.cfold : 0);
-            const int pp = folded ? pary : 0;
-            tma_load_5d(map, &ctl->full[stage], a_dst + (size_t)q * rows_per_cls * sl.row_bytes,
-                        cc, cx, pp, cy, N0);
+          if (elect_one()) {
+            uint8_t* a_dst = stages + (size_t)stage * p.stage_bytes;
+            mbar_arrive_expect_tx(&ctl->full[stage], tx_bytes);
+            for (int q = 0; q < ncls; ++q)
+              tma_load_5d(map, &ctl->full[stage], a_dst + q * cls_bytes,
+                          run.cls[q][0] + b * (RB / 2), X0 + run.cls[q][1], run.cls[q][2],
+                          Y0 + run.cls[q][3], N0);
+            bulk_load_1d(a_dst + p.a_bytes, wsrc + b * wstep, b_bytes, &ctl->full[stage]);
           }
-          bulk_load_1d(b_dst,
-                       p.wpacked + (size_t)sl.w_off16 * 16 + (size_t)n_tile * p.BN * sl.row_bytes,
-                       (uint32_t)(p.BN * sl.row_bytes), &ctl->full[stage]);
+          __syncwarp();
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
@@ -129,46 +180,48 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      const uint32_t idesc = umma_idesc_act(128, p.BN);
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        mbar_wait(&ctl->acc_empty[acc], acc_phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t idesc = umma_idesc_act(128, p.BN);
+    const uint64_t a_desc0 = umma_smem_desc(smem_u32(stages), RB);
+    const uint64_t b_desc0 = umma_smem_desc(smem_u32(stages) + p.a_bytes, RB);
+    const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;  // descriptor address units (16 B)
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      mbar_wait(&ctl->acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+      for (int s = 0; s < p.num_slabs; ++s) {
+        mbar_wait(&ctl->full[stage], phase);
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-        for (int s = 0; s < p.num_slabs; ++s) {
-          const int row_bytes = p.slabs[s].row_bytes;
-          mbar_wait(&ctl->full[stage], phase);
-          tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(stages + (size_t)stage * p.stage_bytes);
-          const uint32_t b_addr = a_addr + p.a_bytes;
-          const int ksteps = row_bytes >> 5;
-          for (int k = 0; k < ksteps; ++k) {
-            umma_bf16_ss(d_tmem, umma_smem_desc(a_addr + k * 32, row_bytes),
-                         umma_smem_desc(b_addr + k * 32, row_bytes), idesc, (s | k) != 0);
-          }
+        if (elect_one()) {
+          const uint64_t a_desc = a_desc0 + (uint64_t)(stage * stage_step);
+          const uint64_t b_desc = b_desc0 + (uint64_t)(stage * stage_step);
+#pragma unroll
+          for (int k = 0; k < RB / 32; ++k)
+            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (s | k) != 0);
           umma_commit(&ctl->empty[stage]);
-          if (++stage == p.num_stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (s == p.num_slabs - 1) umma_commit(&ctl->acc_full[acc]);
         }
-        umma_commit(&ctl->acc_full[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == p.num_stages) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else {
     // ============================ epilogue ================================
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;    // accumulator row == pixel within the tile
+    const int quarter = warp & 3;         // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;     // which half of the column chunks
+    const int row = quarter * 32 + lane;  // accumulator row == pixel within the tile
     const int rpc_log2 = 7 - p.ncls_log2;
     const int r = row & ((1 << rpc_log2) - 1);
     const int q = row >> rpc_log2;
@@ -194,7 +247,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
       mbar_wait(&ctl->acc_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
-      for (int c = 0; c < p.BN; c += 32) {
+      for (int c = half * 32; c < p.BN; c += 64) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c, v);
         tmem_ld_wait();
@@ -204,9 +257,16 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
             const int ch = ch0 + c + g8 * 8;
             if (ch >= p.cout) break;
             float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              f[j] = __uint_as_float(v[g8 * 8 + j]) + bias_s[ch + j];
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch + 4);
+            f[0] = __uint_as_float(v[g8 * 8 + 0]) + b0.x;
+            f[1] = __uint_as_float(v[g8 * 8 + 1]) + b0.y;
+            f[2] = __uint_as_float(v[g8 * 8 + 2]) + b0.z;
+            f[3] = __uint_as_float(v[g8 * 8 + 3]) + b0.w;
+            f[4] = __uint_as_float(v[g8 * 8 + 4]) + b1.x;
+            f[5] = __uint_as_float(v[g8 * 8 + 5]) + b1.y;
+            f[6] = __uint_as_float(v[g8 * 8 + 6]) + b1.z;
+            f[7] = __uint_as_float(v[g8 * 8 + 7]) + b1.w;
             const bool full8 = ch + 8 <= p.cout;
             if (p.residual) {
               if (full8) {
@@ -224,31 +284,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
                   f[j] += act_to_float(p.residual[pix * p.cout + ch + j]);
               }
             }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + pix * p.cout + ch;
-              if (full8 && (p.cout & 3) == 0) {
-                *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-                *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
-              } else {
-                for (int j = 0; j < 8 && ch + j < p.cout; ++j) o[j] = f[j];
-              }
-            } else {
-              uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + pix * p.cout + ch;
-              if (full8 && (p.cout & 7) == 0) {
-                uint4 pk;
-                pk.x = pack_act2(f[0], f[1]);
-                pk.y = pack_act2(f[2], f[3]);
-                pk.z = pack_act2(f[4], f[5]);
-                pk.w = pack_act2(f[6], f[7]);
-                *reinterpret_cast<uint4*>(o) = pk;
-              } else {
-                for (int j = 0; j < 8 && ch + j < p.cout; ++j) o[j] = float_to_act(f[j]);
-              }
-            }
+            if (p.relu) store8<true>(p, f, pix, ch, full8);
+            else store8<false>(p, f, pix, ch, full8);
           }
         }
       }
@@ -270,18 +307,28 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
 }
 
 size_t conv_tc_smem_bytes(const ConvTcParams& p) {
-  return (size_t)p.num_stages * p.stage_bytes + kCtlBytes + kBiasBytes + 1024;
+  return (size_t)p.num_stages * p.stage_bytes + kCtlBytes + kBiasBytes + kRunBytes + 1024;
 }
 
 cudaError_t conv_tc_configure() {
-  return cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<32>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024);
+  return e;
 }
 
 cudaError_t launch_conv_tc(const ConvTcParams& p, int num_sms, cudaStream_t st) {
   const int total_tiles = p.n_tiles * p.tiles_x * p.tiles_y * p.tiles_n;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-  conv_tc_kernel<<<grid, TC_THREADS, conv_tc_smem_bytes(p), st>>>(p);
+  const size_t smem = conv_tc_smem_bytes(p);
+  if (p.row_bytes == 128) conv_tc_kernel<128><<<grid, TC_THREADS, smem, st>>>(p);
+  else if (p.row_bytes == 64) conv_tc_kernel<64><<<grid, TC_THREADS, smem, st>>>(p);
+  else conv_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(p);
   return cudaGetLastError();
 }
 

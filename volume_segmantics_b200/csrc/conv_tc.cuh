@@ -1,7 +1,7 @@
 // tcgen05 / TMEM implicit-GEMM convolution for sm_100a -- parameter block shared
 // between the kernel (conv_tc.cu) and the host-side planner (engine.cu).
 //
-// GEMM view of a convolution on NHWC bf16 activations:
+// GEMM view of a convolution on NHWC 16-bit activations:
 //   D[M = output pixels, N = Cout] = sum over K-slabs  A_slab[M, KB] * W_slab[N, KB]^T
 // A K-slab is (filter tap, source tensor, block of KB = 16/32/64 input channels).
 // Its A operand is fetched by ONE 5-D TMA box load per "pixel class" straight
@@ -14,6 +14,10 @@
 // stride-2 convolutions and -- together with the 4-class "parity split" of
 // the M tile -- the nearest-x2 up-sampled sources and the skip concat of the
 // smp decoder blocks without materialising either.
+//
+// The K loop is described by "runs": one run = (tap, source); its slabs step
+// through the source's channels.  All box coordinates that do not depend on
+// the tile are precomputed on the host, per pixel class.
 #pragma once
 #include <stdint.h>
 
@@ -21,26 +25,24 @@
 
 namespace vsb {
 
-struct TcSlab {
-  int32_t map;        // index into the tensor-map array
-  int32_t c0;         // first channel of the slab within its source
-  int32_t dy, dx;     // tap offset in source pixels
-  int32_t flags;      // bit0: folded map, bit1: halve (coords are (t >> 1), parity = t & 1)
-  int32_t cfold;      // channel count C of the source (parity_x * C is added to c0)
-  int32_t row_bytes;  // 32 / 64 / 128 = 2 * KB
-  int32_t w_off16;    // offset (16-byte units) of this slab's [Npad][KB] weight image
+struct TcRun {
+  int32_t map;        // index into the tensor-map array (= source index)
+  int32_t nblk;       // number of KB-channel slabs in this run
+  int32_t w_off16;    // offset (16-byte units) of the first slab's [Npad][KB] weight image
+  int32_t w_step16;   // distance between consecutive slabs' weight images
+  int32_t cls[4][4];  // per pixel class {c, dx, p, dy}: box at (c + blk*KB, X0+dx, p, Y0+dy, N0)
 };
-
-enum { TC_FOLDED = 1, TC_HALVE = 2 };
 
 struct ConvTcParams {
   const TmaDesc* maps;
-  const TcSlab* slabs;
-  int32_t num_slabs;
+  const TcRun* runs;
+  int32_t num_runs;
+  int32_t num_slabs;          // sum of nblk
+  int32_t row_bytes;          // 2 * KB: 32 / 64 / 128, uniform per launch
   const uint8_t* wpacked;
   const float* bias;          // [n_tiles * BN] (zero padded)
-  const uint16_t* residual;   // bf16 NHWC [NB,H,W,cout] or null
-  void* out;                  // bf16 / f32 NHWC [NB,H,W,cout]
+  const uint16_t* residual;   // NHWC [NB,H,W,cout] or null
+  void* out;                  // 16-bit / f32 NHWC [NB,H,W,cout]
   int32_t out_f32;
   int32_t relu;
   int32_t cout;               // channels actually stored
@@ -50,12 +52,14 @@ struct ConvTcParams {
   int32_t bw_log2, bh_log2, nt_log2;  // box (per class), bw*bh*nt*ncls == 128
   int32_t tiles_x, tiles_y, tiles_n;  // box-grid tile counts
   int32_t num_stages;
-  int32_t stage_bytes;        // A (128 * 128 B) + B (BN * 128 B), 1024-aligned
-  int32_t a_bytes;            // 16384
+  int32_t stage_bytes;        // A (128 rows) + B (BN rows) of row_bytes, 1024-aligned
+  int32_t a_bytes;            // 128 * row_bytes
 };
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_MAX_STAGES = 12;
+constexpr int TC_MAX_RUNS = 128;
 
 size_t conv_tc_smem_bytes(const ConvTcParams& p);
 cudaError_t launch_conv_tc(const ConvTcParams& p, int num_sms, cudaStream_t st);

@@ -43,7 +43,7 @@ int fail(int code, const char* fmt, ...) {
                   cudaGetErrorString(err__));                                             \
   } while (0)
 
-using vsb::TcSlab;
+using vsb::TcRun;
 using vsb::TmaDesc;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -79,9 +79,10 @@ struct ConvPlan {
   bool ps = false;        // parity-split (some source is nearest-x2 up-sampled)
   bool s2 = false;        // stride 2
   int BN = 0, n_tiles = 0;
-  std::vector<TcSlab> slabs;       // map index = source index
-  std::vector<int> src_kb;         // KB per source
-  TcSlab* d_slabs = nullptr;
+  std::vector<TcRun> runs;         // map index = source index
+  int kb = 64;                     // channels per K-slab (uniform per conv)
+  int num_slabs = 0;
+  TcRun* d_runs = nullptr;
   uint8_t* d_wpacked = nullptr;
   float* d_bias_pad = nullptr;
   // spatial-size dependent
@@ -130,6 +131,9 @@ struct vsb_engine {
   int batch_override = 0;
   int conv_impl = 0;
   bool profiling = false;
+  std::vector<float> op_ms;
+  std::vector<int64_t> op_launches;
+  std::vector<int> ev_op;
   float prof_ms[PC_N] = {0};
   int64_t prof_launches[PC_N] = {0};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -219,51 +223,65 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
   cp.BN = ((n_pad16 + cp.n_tiles - 1) / cp.n_tiles + 15) / 16 * 16;
   const int n_total = cp.BN * cp.n_tiles;
 
-  cp.src_kb.clear();
+  // uniform slab width: the largest of 64/32/16 channels dividing every source
+  cp.kb = 64;
   std::vector<int> src_c0;  // channel offset of each source in the concat
   int coff = 0;
   for (int s = 0; s < op.n_src; ++s) {
     const int C = e->tdesc[op.src[s]].channels;
-    cp.src_kb.push_back(C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16));
+    const int kb = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
+    cp.kb = std::min(cp.kb, kb);
     src_c0.push_back(coff);
     coff += C;
   }
   if (coff != op.cin) return fail(VSB_ERR_INVALID, "op %d: cin %d != sum of sources %d", oi, op.cin, coff);
+  const int KB = cp.kb, rb = KB * 2;
+  const int ncls = cp.ps ? 4 : 1;
 
-  // slab table + packed weights
-  cp.slabs.clear();
+  // run table (tap x source) + packed weights: per slab a [n_total][KB] image,
+  // rows pre-swizzled exactly as TMA would have written them
+  cp.runs.clear();
+  cp.num_slabs = 0;
   size_t wbytes = 0;
+  const size_t slab_img = (size_t)n_total * rb;
   for (int ky = 0; ky < op.kh; ++ky)
     for (int kx = 0; kx < op.kw; ++kx)
       for (int s = 0; s < op.n_src; ++s) {
-        const int C = e->tdesc[op.src[s]].channels, KB = cp.src_kb[s];
-        for (int cb = 0; cb < C / KB; ++cb) {
-          TcSlab sl{};
-          sl.map = s;
-          sl.c0 = cb * KB;
-          sl.dy = ky * op.dil - op.pad;
-          sl.dx = kx * op.dil - op.pad;
-          sl.cfold = C;
-          sl.row_bytes = KB * 2;
-          if (cp.ps) sl.flags = op.src_up[s] ? vsb::TC_HALVE : (vsb::TC_HALVE | vsb::TC_FOLDED);
-          else if (cp.s2) sl.flags = vsb::TC_HALVE | vsb::TC_FOLDED;
-          else sl.flags = 0;
-          sl.w_off16 = (int32_t)(wbytes / 16);
-          wbytes += (size_t)n_total * sl.row_bytes;
-          cp.slabs.push_back(sl);
+        const int C = e->tdesc[op.src[s]].channels;
+        TcRun run{};
+        run.map = s;
+        run.nblk = C / KB;
+        run.w_off16 = (int32_t)(wbytes / 16);
+        run.w_step16 = (int32_t)(slab_img / 16);
+        const int dy = ky * op.dil - op.pad, dx = kx * op.dil - op.pad;
+        bool halve, folded;
+        if (cp.ps) { halve = true; folded = !op.src_up[s]; }
+        else if (cp.s2) { halve = true; folded = true; }
+        else { halve = false; folded = false; }
+        for (int q = 0; q < ncls; ++q) {
+          const int ty = (q >> 1) + dy, tx = (q & 1) + dx;
+          int cy, cx, pary = 0, parx = 0;
+          if (halve) { cy = ty >> 1; cx = tx >> 1; pary = ty & 1; parx = tx & 1; }
+          else { cy = ty; cx = tx; }
+          run.cls[q][0] = folded ? parx * C : 0;
+          run.cls[q][1] = cx;
+          run.cls[q][2] = folded ? pary : 0;
+          run.cls[q][3] = cy;
         }
+        wbytes += slab_img * run.nblk;
+        cp.num_slabs += run.nblk;
+        cp.runs.push_back(run);
       }
+  if ((int)cp.runs.size() > vsb::TC_MAX_RUNS) { cp.tc = false; return VSB_OK; }
   std::vector<uint8_t> packed(wbytes, 0);
   const int cin_g = op.cin;  // groups == 1
-  size_t si = 0;
+  size_t ri = 0;
   for (int ky = 0; ky < op.kh; ++ky)
     for (int kx = 0; kx < op.kw; ++kx)
-      for (int s = 0; s < op.n_src; ++s) {
-        const int C = e->tdesc[op.src[s]].channels, KB = cp.src_kb[s];
-        for (int cb = 0; cb < C / KB; ++cb, ++si) {
-          const TcSlab& sl = cp.slabs[si];
-          uint8_t* img = packed.data() + (size_t)sl.w_off16 * 16;
-          const int rb = sl.row_bytes;
+      for (int s = 0; s < op.n_src; ++s, ++ri) {
+        const TcRun& run = cp.runs[ri];
+        for (int cb = 0; cb < run.nblk; ++cb) {
+          uint8_t* img = packed.data() + (size_t)run.w_off16 * 16 + (size_t)cb * slab_img;
           for (int n = 0; n < op.cout; ++n) {
             const int64_t wrow = (((int64_t)n * op.kh + ky) * op.kw + kx) * cin_g + src_c0[s] + cb * KB;
             for (int ch = 0; ch < rb / 16; ++ch) {  // 16-byte chunks of 8 channels
@@ -271,16 +289,15 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
               if (rb == 128) sw = ch ^ (n & 7);
               else if (rb == 64) sw = ch ^ ((n >> 1) & 3);
               else sw = ch ^ ((n >> 2) & 1);
-              uint8_t* dst = img + (size_t)n * rb + sw * 16;
-              memcpy(dst, e->h_weights.data() + op.w_off + (wrow + ch * 8) * 2, 16);
+              memcpy(img + (size_t)n * rb + sw * 16, e->h_weights.data() + op.w_off + (wrow + ch * 8) * 2, 16);
             }
           }
         }
       }
   CK(cudaMalloc(&cp.d_wpacked, wbytes));
   CK(cudaMemcpy(cp.d_wpacked, packed.data(), wbytes, cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&cp.d_slabs, cp.slabs.size() * sizeof(TcSlab)));
-  CK(cudaMemcpy(cp.d_slabs, cp.slabs.data(), cp.slabs.size() * sizeof(TcSlab), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&cp.d_runs, cp.runs.size() * sizeof(TcRun)));
+  CK(cudaMemcpy(cp.d_runs, cp.runs.data(), cp.runs.size() * sizeof(TcRun), cudaMemcpyHostToDevice));
   std::vector<float> bias(n_total, 0.f);
   if (op.b_off >= 0) memcpy(bias.data(), e->h_weights.data() + op.b_off, (size_t)op.cout * 4);
   CK(cudaMalloc(&cp.d_bias_pad, n_total * 4));
@@ -407,14 +424,16 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
       else folded = cp.s2;
       if (folded && ((st.H & 1) || (st.W & 1)))
         return fail(VSB_ERR_UNSUPPORTED, "op %d: folded source with odd dims %dx%d", i, st.H, st.W);
-      int rc = make_tensor_map(e, &maps[s], st, nb, folded, cp.src_kb[s], bw, bh, ntile);
+      int rc = make_tensor_map(e, &maps[s], st, nb, folded, cp.kb, bw, bh, ntile);
       if (rc) return rc;
     }
     CK(cudaMemcpy(cp.d_maps, maps, sizeof(maps), cudaMemcpyHostToDevice));
     vsb::ConvTcParams& p = cp.params;
     p.maps = cp.d_maps;
-    p.slabs = cp.d_slabs;
-    p.num_slabs = (int)cp.slabs.size();
+    p.runs = cp.d_runs;
+    p.num_runs = (int)cp.runs.size();
+    p.num_slabs = cp.num_slabs;
+    p.row_bytes = cp.kb * 2;
     p.wpacked = cp.d_wpacked;
     p.bias = cp.d_bias_pad;
     p.residual = op.res >= 0 ? (const uint16_t*)e->tens[op.res].ptr : nullptr;
@@ -434,9 +453,9 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
     p.tiles_x = (gw + bw - 1) / bw;
     p.tiles_y = (gh + bh - 1) / bh;
     p.tiles_n = (nb + ntile - 1) / ntile;
-    p.a_bytes = 128 * 128;
-    p.stage_bytes = p.a_bytes + cp.BN * 128;
-    p.num_stages = std::min<int>(vsb::TC_MAX_STAGES, (int)((216 * 1024) / p.stage_bytes));
+    p.a_bytes = 128 * p.row_bytes;
+    p.stage_bytes = (128 + cp.BN) * p.row_bytes;
+    p.num_stages = std::min<int>(vsb::TC_MAX_STAGES, (int)((206 * 1024) / p.stage_bytes));
     if (p.num_stages < 2) return fail(VSB_ERR_UNSUPPORTED, "op %d: too few pipeline stages", i);
   }
   return VSB_OK;
@@ -446,7 +465,7 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
 struct ProfScope {
   vsb_engine* e;
   int idx = -1;
-  ProfScope(vsb_engine* e_, int cls) : e(e_) {
+  ProfScope(vsb_engine* e_, int cls, int op = -1) : e(e_) {
     e->launches += 1;
     if (!e->profiling) return;
     if (e->ev_used == e->ev_pool.size()) {
@@ -455,9 +474,11 @@ struct ProfScope {
       cudaEventCreate(&b);
       e->ev_pool.push_back({a, b});
       e->ev_cls.push_back(cls);
+      e->ev_op.push_back(op);
     }
     idx = (int)e->ev_used++;
     e->ev_cls[idx] = cls;
+    e->ev_op[idx] = op;
     cudaEventRecord(e->ev_pool[idx].first, e->stream);
   }
   ~ProfScope() {
@@ -473,6 +494,15 @@ void prof_collect(vsb_engine* e) {
     cudaEventElapsedTime(&ms, e->ev_pool[i].first, e->ev_pool[i].second);
     e->prof_ms[e->ev_cls[i]] += ms;
     e->prof_launches[e->ev_cls[i]] += 1;
+    const int op = e->ev_op[i];
+    if (op >= 0) {
+      if ((int)e->op_ms.size() <= op) {
+        e->op_ms.resize(op + 1, 0.f);
+        e->op_launches.resize(op + 1, 0);
+      }
+      e->op_ms[op] += ms;
+      e->op_launches[op] += 1;
+    }
   }
   e->ev_used = 0;
 }
@@ -486,14 +516,14 @@ int run_conv(vsb_engine* e, int oi, int nb) {
     vsb::ConvTcParams p = cp.params;
     p.NB = nb;
     p.tiles_n = (nb + (1 << p.nt_log2) - 1) >> p.nt_log2;
-    ProfScope ps(e, PC_CONV_TC);
+    ProfScope ps(e, PC_CONV_TC, oi);
     CK(vsb::launch_conv_tc(p, e->num_sms, e->stream));
     return VSB_OK;
   }
   const TensorBuf& s0 = e->tens[op.src[0]];
   if (e->conv_impl != 2 && op.cin == 1 && op.kh == 7 && op.kw == 7 && op.stride == 2 && op.pad == 3 &&
       op.cout == 64 && op.n_src == 1 && ot.dtype == 0 && op.res < 0) {
-    ProfScope ps(e, PC_STEM);
+    ProfScope ps(e, PC_STEM, oi);
     vsb::launch_stem7x7((const uint16_t*)s0.ptr, nb, s0.H, s0.W, e->d_weights + op.w_off,
                         (const float*)(e->d_weights + op.b_off), (uint16_t*)ot.ptr, op.relu, e->stream);
     CK(cudaGetLastError());
@@ -517,7 +547,7 @@ int run_conv(vsb_engine* e, int oi, int nb) {
   a.residual = op.res >= 0 ? e->tens[op.res].ptr : nullptr;
   a.out = ot.ptr;
   a.out_f32 = ot.dtype;
-  ProfScope ps(e, PC_CONV_SIMT);
+  ProfScope ps(e, PC_CONV_SIMT, oi);
   vsb::launch_conv_simt(a, e->stream);
   CK(cudaGetLastError());
   return VSB_OK;
@@ -537,7 +567,7 @@ int run_network(vsb_engine* e, int nb, int* head_idx) {
       }
       case VSB_OP_MAXPOOL: {
         const TensorBuf& s = e->tens[op.src[0]];
-        ProfScope ps(e, PC_POOL);
+        ProfScope ps(e, PC_POOL, i);
         vsb::launch_maxpool3x3s2((const uint16_t*)s.ptr, nb, s.H, s.W, s.C, (uint16_t*)e->tens[op.out].ptr,
                                  e->stream);
         CK(cudaGetLastError());
@@ -671,7 +701,7 @@ int vsb_create(int device, vsb_engine** out) {
 
 static void free_plan(vsb_engine* e) {
   for (ConvPlan& cp : e->conv) {
-    cudaFree(cp.d_slabs);
+    cudaFree(cp.d_runs);
     cudaFree(cp.d_wpacked);
     cudaFree(cp.d_bias_pad);
     cudaFree(cp.d_maps);
@@ -1028,6 +1058,17 @@ int vsb_set_profiling(vsb_engine* e, int32_t on) {
     e->prof_ms[i] = 0.f;
     e->prof_launches[i] = 0;
   }
+  e->op_ms.clear();
+  e->op_launches.clear();
+  return VSB_OK;
+}
+
+int vsb_op_ms(vsb_engine* e, int32_t op, float* ms, int64_t* launches) {
+  if (!e || op < 0) return fail(VSB_ERR_INVALID, "bad op");
+  prof_collect(e);
+  const bool have = op < (int)e->op_ms.size();
+  if (ms) *ms = have ? e->op_ms[op] : 0.f;
+  if (launches) *launches = have ? e->op_launches[op] : 0;
   return VSB_OK;
 }
 

@@ -186,6 +186,14 @@ class Engine:
     def set_profiling(self, on: bool) -> None:
         _lib.check(self.lib.vsb_set_profiling(self.h, int(on)))
 
+    def op_times(self, n_ops: int):
+        out = []
+        for i in range(n_ops):
+            ms, n = C.c_float(), C.c_int64()
+            _lib.check(self.lib.vsb_op_ms(self.h, i, C.byref(ms), C.byref(n)))
+            out.append((ms.value, n.value))
+        return out
+
     def stage_times(self) -> Dict[str, Tuple[float, int]]:
         out = {}
         for i, name in enumerate(_lib.PROF_CLASSES):
