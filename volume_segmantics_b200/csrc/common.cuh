@@ -231,6 +231,15 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) |
          (layout << 61);
 }
+// Same, 128B swizzle, explicit stride between 8-row groups (halo tiles: the 8 rows of
+// a group are 8 x-adjacent pixels, consecutive groups are consecutive image rows of a
+// wider tile, so SBO = tile row pitch).  The swizzle XOR uses absolute smem address
+// bits, so a start address shifted by whole 128-byte rows needs base_offset = 0
+// (verified on B200 by tests/micro/halo_mma_test.cu).
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16 (format 1) or f16 (format 0),
 // both K-major, M x N.
 __host__ __device__ inline uint32_t umma_idesc_act(int m, int n) {

@@ -1,0 +1,83 @@
+// "Halo" tcgen05 convolution: 3x3, stride 1, pad = dilation, one NHWC source with
+// Cin % 64 == 0.  Parameter block shared by conv_halo.cu and engine.cu.
+//
+// An output tile is 8 (x) by 16 (y) pixels = the 128 rows of one UMMA.  Its input
+// window with a `dil`-pixel halo ((8+2d) x (16+2d) pixels x 64 channels) is fetched
+// ONCE per 64-channel slab by a single TMA box load; all nine filter taps then read
+// it in place through shifted shared-memory descriptors:
+//     A(tap ky,kx) = halo + ((ky*d)*(8+2d) + kx*d) * 128 bytes,  SBO = (8+2d)*128
+// (8 x-adjacent pixels form one 8-row swizzle group, consecutive groups are
+// consecutive image rows).  Compared with one box per tap (conv_tc.cu) this moves
+// 6.4x fewer rows through TMA -- the measured limiter there (about 4.5 cycles per box
+// row) -- and reads each input pixel from L2 1.4x instead of 9x.
+// Weights are either resident in shared memory for the whole (persistent) CTA, when
+// 9 * Cin * BN * 2 bytes fit, or streamed one (slab, tap) image at a time through
+// their own mbarrier ring by a second producer warp.
+#pragma once
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace vsb {
+
+struct ConvHaloParams {
+  const TmaDesc* map;        // plain 5-D map (c, x, 1, y, n), box {64, 8+2d, 1, 16+2d, 1}
+  const uint8_t* wpacked;    // [n_tile][slab][tap] images of [BN][64] pre-swizzled rows
+  const float* bias;         // [n_tiles * BN]
+  const uint16_t* residual;  // NHWC [NB,H,W,cout] or null
+  void* out;
+  int32_t out_f32, relu, cout;
+  int32_t BN, n_tiles;
+  int32_t NB, H, W;
+  int32_t ncs;               // Cin / 64
+  int32_t dil;
+  int32_t tiles_x, tiles_y;
+  int32_t a_stages, a_stage_bytes;
+  int32_t b_stages;          // 0: all weights resident in shared memory
+  int32_t b_bytes;           // BN * 128
+};
+
+// ---- generalised variant: the halo tile is assembled by four cp.async producer warps
+// instead of TMA, so a K-slab may come from any of several concatenated sources, may
+// hold 16/32/48/64 channels (rows keep the 128-byte pitch of the SW128 layout; only
+// kc/16 K-steps are issued) and may be a nearest-x2 up-sampled view of a half-
+// resolution tensor (smp DecoderBlock: upsample -> concat -> conv).  dil = 1.
+struct HaloSrc {
+  const uint16_t* ptr;  // NHWC
+  int32_t C, Hs, Ws, up;
+};
+constexpr int HALO2_MAX_SLABS = 32;
+struct ConvHalo2Params {
+  HaloSrc src[6];
+  int32_t n_src, nslabs;
+  int32_t stem;  // 1: 7x7 stride-2 single-channel stem (im2col rows built by the loaders)
+  int8_t slab_src[HALO2_MAX_SLABS];
+  int16_t slab_c0[HALO2_MAX_SLABS];
+  int8_t slab_kc[HALO2_MAX_SLABS];  // channels in the slab: 16..64
+  const uint8_t* wpacked;           // [n_tile][slab][tap] images of [BN][128 B] rows
+  const float* bias;
+  const uint16_t* residual;
+  void* out;
+  int32_t out_f32, relu, cout;
+  int32_t BN, n_tiles;
+  int32_t NB, H, W;
+  int32_t tiles_x, tiles_y;
+  int32_t a_stages, a_stage_bytes;
+  int32_t b_stages, b_bytes;
+};
+constexpr int HALO2_LOAD_WARPS = 4;
+constexpr int HALO2_THREADS = 32 * (HALO2_LOAD_WARPS + 2 + 8);
+
+size_t conv_halo2_smem_bytes(const ConvHalo2Params& p);
+cudaError_t launch_conv_halo2(const ConvHalo2Params& p, int num_sms, cudaStream_t st);
+
+constexpr int HALO_EPI_WARPS = 8;
+constexpr int HALO_THREADS = 96 + 32 * HALO_EPI_WARPS;
+constexpr int HALO_MAX_A_STAGES = 8;
+constexpr int HALO_MAX_B_STAGES = 8;
+
+size_t conv_halo_smem_bytes(const ConvHaloParams& p);
+cudaError_t launch_conv_halo(const ConvHaloParams& p, int num_sms, cudaStream_t st);
+cudaError_t conv_halo_configure();
+
+}  // namespace vsb

@@ -23,6 +23,7 @@
 // upsample + cat the reference reaches through `self.model(...)`
 // (vol_seg_2d_predictor.py:44).
 #include "conv_tc.cuh"
+#include "conv_epilogue.cuh"
 
 namespace vsb {
 
@@ -52,51 +53,6 @@ __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int t, int& n
   X0 = tx << p.bw_log2;
   Y0 = ty << p.bh_log2;
   N0 = tn << p.nt_log2;
-}
-
-// two fp32 -> packed 16-bit pair (lo in the low half), optional ReLU, in one F2FP
-template <bool RELU>
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  uint32_t r;
-#if VSB_ACT_F16
-  if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-#else
-  if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-#endif
-  return r;
-}
-
-template <bool RELU>
-__device__ __forceinline__ void store8(const ConvTcParams& p, const float (&f)[8], int64_t pix,
-                                       int ch, bool full8) {
-  if (p.out_f32) {
-    float* o = reinterpret_cast<float*>(p.out) + pix * p.cout + ch;
-    if (full8 && (p.cout & 3) == 0) {
-      *reinterpret_cast<float4*>(o) =
-          RELU ? make_float4(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f), fmaxf(f[2], 0.f), fmaxf(f[3], 0.f))
-               : make_float4(f[0], f[1], f[2], f[3]);
-      *reinterpret_cast<float4*>(o + 4) =
-          RELU ? make_float4(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f), fmaxf(f[6], 0.f), fmaxf(f[7], 0.f))
-               : make_float4(f[4], f[5], f[6], f[7]);
-    } else {
-      for (int j = 0; j < 8 && ch + j < p.cout; ++j) o[j] = RELU ? fmaxf(f[j], 0.f) : f[j];
-    }
-  } else {
-    uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + pix * p.cout + ch;
-    if (full8 && (p.cout & 7) == 0) {
-      uint4 pk;
-      pk.x = pack2<RELU>(f[0], f[1]);
-      pk.y = pack2<RELU>(f[2], f[3]);
-      pk.z = pack2<RELU>(f[4], f[5]);
-      pk.w = pack2<RELU>(f[6], f[7]);
-      *reinterpret_cast<uint4*>(o) = pk;
-    } else {
-      for (int j = 0; j < 8 && ch + j < p.cout; ++j)
-        o[j] = float_to_act(RELU ? fmaxf(f[j], 0.f) : f[j]);
-    }
-  }
 }
 
 }  // namespace
@@ -228,6 +184,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     const int xi = r & ((1 << p.bw_log2) - 1);
     const int yi = (r >> p.bw_log2) & ((1 << p.bh_log2) - 1);
     const int ni = r >> (p.bw_log2 + p.bh_log2);
+    const EpiOut eo{p.out, p.residual, p.out_f32, p.relu, p.cout};
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n_tile, X0, Y0, N0;
       decode_tile(p, t, n_tile, X0, Y0, N0);
@@ -251,43 +208,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c, v);
         tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            const int ch = ch0 + c + g8 * 8;
-            if (ch >= p.cout) break;
-            float f[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch + 4);
-            f[0] = __uint_as_float(v[g8 * 8 + 0]) + b0.x;
-            f[1] = __uint_as_float(v[g8 * 8 + 1]) + b0.y;
-            f[2] = __uint_as_float(v[g8 * 8 + 2]) + b0.z;
-            f[3] = __uint_as_float(v[g8 * 8 + 3]) + b0.w;
-            f[4] = __uint_as_float(v[g8 * 8 + 4]) + b1.x;
-            f[5] = __uint_as_float(v[g8 * 8 + 5]) + b1.y;
-            f[6] = __uint_as_float(v[g8 * 8 + 6]) + b1.z;
-            f[7] = __uint_as_float(v[g8 * 8 + 7]) + b1.w;
-            const bool full8 = ch + 8 <= p.cout;
-            if (p.residual) {
-              if (full8) {
-                const uint4 rv =
-                    __ldg(reinterpret_cast<const uint4*>(p.residual + pix * p.cout + ch));
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 rf = unpack_act2(rw[j]);
-                  f[2 * j] += rf.x;
-                  f[2 * j + 1] += rf.y;
-                }
-              } else {
-                for (int j = 0; j < 8 && ch + j < p.cout; ++j)
-                  f[j] += act_to_float(p.residual[pix * p.cout + ch + j]);
-              }
-            }
-            if (p.relu) store8<true>(p, f, pix, ch, full8);
-            else store8<false>(p, f, pix, ch, full8);
-          }
-        }
+        if (valid) epilogue_chunk32(eo, v, bias_s, pix, ch0 + c);
       }
       tc_fence_before_sync();
       mbar_arrive(&ctl->acc_empty[acc]);

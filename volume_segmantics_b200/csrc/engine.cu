@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -18,6 +19,7 @@
 
 #include "../../include/vsb200.h"
 #include "common.cuh"
+#include "conv_halo.cuh"
 #include "conv_tc.cuh"
 #include "kernels.h"
 
@@ -85,6 +87,14 @@ struct ConvPlan {
   TcRun* d_runs = nullptr;
   uint8_t* d_wpacked = nullptr;
   float* d_bias_pad = nullptr;
+  // halo kernel (3x3 stride 1, one source, Cin % 64 == 0)
+  bool halo_ok = false;   // plan-level eligibility
+  bool use_halo = false;  // decided per workspace (tile efficiency)
+  uint8_t* d_whalo = nullptr;
+  vsb::ConvHaloParams hparams{};
+  bool stem_tc = false;   // 7x7/2 single-channel stem on tensor cores (halo2 kernel, MODE 1)
+  bool halo2_ok = false, use_halo2 = false;  // cp.async-assembled halo (concat / up-sampled / narrow sources)
+  vsb::ConvHalo2Params h2params{};
   // spatial-size dependent
   TmaDesc* d_maps = nullptr;
   vsb::ConvTcParams params{};
@@ -130,6 +140,7 @@ struct vsb_engine {
 
   int batch_override = 0;
   int conv_impl = 0;
+  bool no_halo = false;
   bool profiling = false;
   std::vector<float> op_ms;
   std::vector<int64_t> op_launches;
@@ -214,6 +225,28 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
   const vsb_op& op = e->ops[oi];
   ConvPlan& cp = e->conv[oi];
   cp.tc = conv_tc_eligible(e, op);
+  cp.stem_tc = false;
+  if (op.kind == VSB_OP_CONV && op.cin == 1 && op.kh == 7 && op.kw == 7 && op.stride == 2 && op.pad == 3 &&
+      op.dil == 1 && op.groups == 1 && op.n_src == 1 && op.res < 0 && op.cout % 16 == 0 && op.cout <= 256 &&
+      e->tdesc[op.out].dtype == 0) {
+    cp.BN = op.cout;
+    cp.n_tiles = 1;
+    std::vector<uint8_t> img((size_t)cp.BN * 128, 0);
+    for (int n = 0; n < op.cout; ++n)
+      for (int k = 0; k < 49; ++k) {
+        const int ch = k / 8;  // 16-byte chunk of 8 taps
+        memcpy(img.data() + (size_t)n * 128 + ((ch ^ (n & 7)) * 16) + (k % 8) * 2,
+               e->h_weights.data() + op.w_off + ((int64_t)n * 49 + k) * 2, 2);
+      }
+    CK(cudaMalloc(&cp.d_whalo, img.size()));
+    CK(cudaMemcpy(cp.d_whalo, img.data(), img.size(), cudaMemcpyHostToDevice));
+    std::vector<float> bias(cp.BN, 0.f);
+    if (op.b_off >= 0) memcpy(bias.data(), e->h_weights.data() + op.b_off, (size_t)op.cout * 4);
+    CK(cudaMalloc(&cp.d_bias_pad, cp.BN * 4));
+    CK(cudaMemcpy(cp.d_bias_pad, bias.data(), cp.BN * 4, cudaMemcpyHostToDevice));
+    cp.stem_tc = true;
+    return VSB_OK;
+  }
   if (!cp.tc) return VSB_OK;
   cp.ps = false;
   for (int s = 0; s < op.n_src; ++s) cp.ps |= op.src_up[s] != 0;
@@ -294,6 +327,66 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
           }
         }
       }
+  cp.halo_ok = op.n_src == 1 && !cp.ps && !cp.s2 && op.kh == 3 && op.kw == 3 && op.pad == op.dil &&
+               (op.dil == 1 || op.dil == 2) && e->tdesc[op.src[0]].channels % 64 == 0;
+  if (cp.halo_ok) {
+    const int ncs = op.cin / 64;
+    const size_t img = (size_t)cp.BN * 128;
+    std::vector<uint8_t> hp((size_t)cp.n_tiles * ncs * 9 * img, 0);
+    for (int nt = 0; nt < cp.n_tiles; ++nt)
+      for (int cs = 0; cs < ncs; ++cs)
+        for (int tap = 0; tap < 9; ++tap) {
+          uint8_t* dst = hp.data() + (((size_t)nt * ncs + cs) * 9 + tap) * img;
+          for (int n = 0; n < cp.BN; ++n) {
+            const int o = nt * cp.BN + n;
+            if (o >= op.cout) break;
+            const int64_t wrow = (((int64_t)o * 3 + tap / 3) * 3 + tap % 3) * op.cin + cs * 64;
+            for (int ch = 0; ch < 8; ++ch)
+              memcpy(dst + (size_t)n * 128 + ((ch ^ (n & 7)) * 16), e->h_weights.data() + op.w_off + (wrow + ch * 8) * 2, 16);
+          }
+        }
+    CK(cudaMalloc(&cp.d_whalo, hp.size()));
+    CK(cudaMemcpy(cp.d_whalo, hp.data(), hp.size(), cudaMemcpyHostToDevice));
+  }
+  cp.halo2_ok = false;
+  if (!cp.halo_ok && !cp.s2 && op.kh == 3 && op.kw == 3 && op.pad == 1 && op.dil == 1) {
+    vsb::ConvHalo2Params& h = cp.h2params;
+    h = vsb::ConvHalo2Params{};
+    int ns = 0;
+    bool fits = true;
+    for (int s = 0; s < op.n_src && fits; ++s) {
+      const int C = e->tdesc[op.src[s]].channels;
+      for (int c0 = 0; c0 < C; c0 += 64) {
+        if (ns >= vsb::HALO2_MAX_SLABS) { fits = false; break; }
+        h.slab_src[ns] = (int8_t)s;
+        h.slab_c0[ns] = (int16_t)c0;
+        h.slab_kc[ns] = (int8_t)std::min(64, C - c0);
+        ++ns;
+      }
+    }
+    if (fits) {
+      h.nslabs = ns;
+      h.n_src = op.n_src;
+      const size_t img = (size_t)cp.BN * 128;
+      std::vector<uint8_t> hp((size_t)cp.n_tiles * ns * 9 * img, 0);
+      for (int nt = 0; nt < cp.n_tiles; ++nt)
+        for (int sl = 0; sl < ns; ++sl)
+          for (int tap = 0; tap < 9; ++tap) {
+            uint8_t* dst = hp.data() + (((size_t)nt * ns + sl) * 9 + tap) * img;
+            const int cbase = src_c0[h.slab_src[sl]] + h.slab_c0[sl];
+            for (int n = 0; n < cp.BN; ++n) {
+              const int o = nt * cp.BN + n;
+              if (o >= op.cout) break;
+              const int64_t wrow = (((int64_t)o * 3 + tap / 3) * 3 + tap % 3) * op.cin + cbase;
+              for (int ch = 0; ch < h.slab_kc[sl] / 8; ++ch)
+                memcpy(dst + (size_t)n * 128 + ((ch ^ (n & 7)) * 16), e->h_weights.data() + op.w_off + (wrow + ch * 8) * 2, 16);
+            }
+          }
+      CK(cudaMalloc(&cp.d_whalo, hp.size()));
+      CK(cudaMemcpy(cp.d_whalo, hp.data(), hp.size(), cudaMemcpyHostToDevice));
+      cp.halo2_ok = true;
+    }
+  }
   CK(cudaMalloc(&cp.d_wpacked, wbytes));
   CK(cudaMemcpy(cp.d_wpacked, packed.data(), wbytes, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&cp.d_runs, cp.runs.size() * sizeof(TcRun)));
@@ -407,6 +500,39 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
   // tensor maps + tile geometry of the tcgen05 convolutions
   for (int i = 0; i < (int)e->ops.size(); ++i) {
     ConvPlan& cp = e->conv[i];
+    if (cp.stem_tc) {
+      const vsb_op& op = e->ops[i];
+      const TensorBuf& ot = e->tens[op.out];
+      const TensorBuf& st = e->tens[op.src[0]];
+      vsb::ConvHalo2Params& h = cp.h2params;
+      h = vsb::ConvHalo2Params{};
+      h.stem = 1;
+      h.n_src = 1;
+      h.nslabs = 1;
+      h.slab_kc[0] = 64;
+      h.src[0].ptr = (const uint16_t*)st.ptr;
+      h.src[0].C = 1;
+      h.src[0].Hs = st.H;
+      h.src[0].Ws = st.W;
+      h.wpacked = cp.d_whalo;
+      h.bias = cp.d_bias_pad;
+      h.out = ot.ptr;
+      h.out_f32 = 0;
+      h.relu = op.relu;
+      h.cout = op.cout;
+      h.BN = cp.BN;
+      h.n_tiles = 1;
+      h.NB = nb;
+      h.H = ot.H;
+      h.W = ot.W;
+      h.tiles_x = (ot.W + 7) / 8;
+      h.tiles_y = (ot.H + 15) / 16;
+      h.a_stage_bytes = 128 * 128;
+      h.a_stages = 4;
+      h.b_stages = 0;
+      h.b_bytes = cp.BN * 128;
+      continue;
+    }
     if (!cp.tc) continue;
     const vsb_op& op = e->ops[i];
     const TensorBuf& ot = e->tens[op.out];
@@ -457,6 +583,92 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
     p.stage_bytes = (128 + cp.BN) * p.row_bytes;
     p.num_stages = std::min<int>(vsb::TC_MAX_STAGES, (int)((206 * 1024) / p.stage_bytes));
     if (p.num_stages < 2) return fail(VSB_ERR_UNSUPPORTED, "op %d: too few pipeline stages", i);
+    cp.use_halo2 = false;
+    if (cp.halo2_ok) {
+      const int tx = (ot.W + 7) / 8, ty = (ot.H + 15) / 16;
+      const double eff = (double)ot.W * ot.H / ((double)tx * 8 * ty * 16);
+      vsb::ConvHalo2Params& h = cp.h2params;
+      h.BN = cp.BN;
+      h.n_tiles = cp.n_tiles;
+      h.b_bytes = cp.BN * 128;
+      h.a_stage_bytes = (int)align_up((size_t)10 * 18 * 128, 1024);
+      const size_t budget = 200 * 1024;
+      const size_t res_bytes = (size_t)h.nslabs * 9 * h.b_bytes;
+      if (cp.n_tiles == 1 && res_bytes + 3 * (size_t)h.a_stage_bytes <= budget) {
+        h.b_stages = 0;
+        h.a_stages = (int)std::min<size_t>(vsb::HALO_MAX_A_STAGES, (budget - res_bytes) / h.a_stage_bytes);
+      } else {
+        h.a_stages = 4;
+        h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, (budget - 4 * (size_t)h.a_stage_bytes) / h.b_bytes);
+      }
+      if (eff >= 0.6 && (h.b_stages == 0 || h.b_stages >= 2)) {
+        for (int s = 0; s < op.n_src; ++s) {
+          const TensorBuf& st = e->tens[op.src[s]];
+          h.src[s].ptr = (const uint16_t*)st.ptr;
+          h.src[s].C = st.C;
+          h.src[s].Hs = st.H;
+          h.src[s].Ws = st.W;
+          h.src[s].up = op.src_up[s];
+        }
+        h.wpacked = cp.d_whalo;
+        h.bias = cp.d_bias_pad;
+        h.residual = p.residual;
+        h.out = ot.ptr;
+        h.out_f32 = ot.dtype;
+        h.relu = op.relu;
+        h.cout = op.cout;
+        h.NB = nb;
+        h.H = ot.H;
+        h.W = ot.W;
+        h.tiles_x = tx;
+        h.tiles_y = ty;
+        cp.use_halo2 = true;
+      }
+    }
+    cp.use_halo = false;
+    if (cp.halo_ok) {
+      const int tx = (ot.W + 7) / 8, ty = (ot.H + 15) / 16;
+      const double eff = (double)ot.W * ot.H / ((double)tx * 8 * ty * 16);
+      vsb::ConvHaloParams& h = cp.hparams;
+      h.dil = op.dil;
+      const int HW = 8 + 2 * op.dil, HH = 16 + 2 * op.dil;
+      h.ncs = op.cin / 64;
+      h.BN = cp.BN;
+      h.n_tiles = cp.n_tiles;
+      h.b_bytes = cp.BN * 128;
+      h.a_stage_bytes = (int)align_up((size_t)HW * HH * 128, 1024);
+      const size_t budget = 200 * 1024;
+      const size_t res_bytes = (size_t)h.ncs * 9 * h.b_bytes;
+      if (cp.n_tiles == 1 && res_bytes + 2 * (size_t)h.a_stage_bytes <= budget) {
+        h.b_stages = 0;
+        h.a_stages = (int)std::min<size_t>(4, (budget - res_bytes) / h.a_stage_bytes);
+      } else {
+        h.a_stages = 2;
+        h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, (budget - 2 * (size_t)h.a_stage_bytes) / h.b_bytes);
+      }
+      if (eff >= 0.6 && (h.b_stages == 0 || h.b_stages >= 2)) {
+        TmaDesc hm;
+        const TensorBuf& st = e->tens[op.src[0]];
+        int rc = make_tensor_map(e, &hm, st, nb, false, 64, HW, HH, 1);
+        if (rc) return rc;
+        // the halo map lives in slot VSB_MAX_SRC - 1 of this op's map array (single-source op)
+        CK(cudaMemcpy(cp.d_maps + (VSB_MAX_SRC - 1), &hm, sizeof(hm), cudaMemcpyHostToDevice));
+        h.map = cp.d_maps + (VSB_MAX_SRC - 1);
+        h.wpacked = cp.d_whalo;
+        h.bias = cp.d_bias_pad;
+        h.residual = p.residual;
+        h.out = ot.ptr;
+        h.out_f32 = ot.dtype;
+        h.relu = op.relu;
+        h.cout = op.cout;
+        h.NB = nb;
+        h.H = ot.H;
+        h.W = ot.W;
+        h.tiles_x = tx;
+        h.tiles_y = ty;
+        cp.use_halo = true;
+      }
+    }
   }
   return VSB_OK;
 }
@@ -512,6 +724,27 @@ int run_conv(vsb_engine* e, int oi, int nb) {
   const vsb_op& op = e->ops[oi];
   ConvPlan& cp = e->conv[oi];
   const TensorBuf& ot = e->tens[op.out];
+  if (cp.tc && cp.use_halo && e->conv_impl == 0 && !e->no_halo) {
+    vsb::ConvHaloParams h = cp.hparams;
+    h.NB = nb;
+    ProfScope ps(e, PC_CONV_TC, oi);
+    CK(vsb::launch_conv_halo(h, e->num_sms, e->stream));
+    return VSB_OK;
+  }
+  if (cp.stem_tc && e->conv_impl == 0 && !e->no_halo) {
+    vsb::ConvHalo2Params h = cp.h2params;
+    h.NB = nb;
+    ProfScope ps(e, PC_STEM, oi);
+    CK(vsb::launch_conv_halo2(h, e->num_sms, e->stream));
+    return VSB_OK;
+  }
+  if (cp.tc && cp.use_halo2 && e->conv_impl == 0 && !e->no_halo) {
+    vsb::ConvHalo2Params h = cp.h2params;
+    h.NB = nb;
+    ProfScope ps(e, PC_CONV_TC, oi);
+    CK(vsb::launch_conv_halo2(h, e->num_sms, e->stream));
+    return VSB_OK;
+  }
   if (cp.tc && e->conv_impl == 0) {
     vsb::ConvTcParams p = cp.params;
     p.NB = nb;
@@ -695,6 +928,8 @@ int vsb_create(int device, vsb_engine** out) {
   if (!fn || qres != cudaDriverEntryPointSuccess) return fail(VSB_ERR_CUDA, "cuTensorMapEncodeTiled not found");
   e->encode = (EncodeTiledFn)fn;
   CK(vsb::conv_tc_configure());
+  CK(vsb::conv_halo_configure());
+  e->no_halo = getenv("VSB_NO_HALO") != nullptr;
   *out = e;
   return VSB_OK;
 }
@@ -703,6 +938,7 @@ static void free_plan(vsb_engine* e) {
   for (ConvPlan& cp : e->conv) {
     cudaFree(cp.d_runs);
     cudaFree(cp.d_wpacked);
+    cudaFree(cp.d_whalo);
     cudaFree(cp.d_bias_pad);
     cudaFree(cp.d_maps);
   }
