@@ -241,8 +241,119 @@ static void run_e1() {
   }
 }
 
+// ---------------------------------------------------------------------------------- E4
+// Compact pitch: C = 16 (32-byte pixels, SW32) and C = 32 (64-byte pixels, SW64) halo tiles,
+// 34 x 18 pixels (four 8-wide M tiles side by side), absolute-address swizzle on write.
+template <int C>
+__global__ void __launch_bounds__(128, 1) halo_compact_kernel(const __half* in, const __half* w, float* out) {
+  constexpr int P = C * 2;            // pixel pitch in bytes
+  constexpr int HWc = 34, HHc = 18, MT = 4, N = 16;
+  constexpr int LAYOUT = C == 16 ? 6 : 4;  // SW32 : SW64
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* halo = smem;                 // 612 px * P
+  uint8_t* wts = smem + 48 * 1024;      // 9 taps x 16 rows x P
+  uint64_t* bar = (uint64_t*)(smem + 60 * 1024);
+  uint32_t* tmem_slot = (uint32_t*)(bar + 1);
+  const int tid = threadIdx.x;
+  auto swz = [](uint32_t addr) -> uint32_t {   // Swizzle<B,4,3> on the absolute address
+    return C == 16 ? (addr ^ (((addr >> 7) & 1) << 4)) : (addr ^ (((addr >> 7) & 3) << 4));
+  };
+  for (int i = tid; i < HWc * HHc * (P / 16); i += 128) {
+    const int pix = i / (P / 16), c = i % (P / 16);
+    const uint32_t a = smem_u32(halo) + pix * P + c * 16;
+    *(uint4*)(halo + (swz(a) - smem_u32(halo))) = *(const uint4*)(in + pix * C + c * 8);
+  }
+  for (int i = tid; i < 9 * N * (P / 16); i += 128) {
+    const int row = i / (P / 16), c = i % (P / 16);
+    const uint32_t a = smem_u32(wts) + row * P + c * 16;
+    *(uint4*)(wts + (swz(a) - smem_u32(wts))) = *(const uint4*)(w + row * C + c * 8);
+  }
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  fence_proxy_async_smem();
+  if (tid < 32) tmem_alloc<64>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  auto desc = [](uint32_t addr, uint32_t sbo) -> uint64_t {
+    return (uint64_t)((addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
+           ((uint64_t)LAYOUT << 61);
+  };
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_act(128, N);
+    for (int mt = 0; mt < MT; ++mt) {
+      bool first = true;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint32_t a0 = smem_u32(halo) + (ky * HWc + kx + mt * 8) * P;
+          const uint32_t b0 = smem_u32(wts) + (ky * 3 + kx) * N * P;
+          for (int k = 0; k < C / 16; ++k) {
+            umma_bf16_ss(tmem + mt * N, desc(a0 + k * 32, HWc * P), desc(b0 + k * 32, 8 * P), idesc, first ? 0u : 1u);
+            first = false;
+          }
+        }
+    }
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after_sync();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int c = 0; c < MT * N; c += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * (MT * N) + c + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc<64>(tmem);
+}
+
+template <int C>
+static void run_e4() {
+  constexpr int HWc = 34, HHc = 18, MT = 4, N = 16;
+  std::vector<__half> in(HHc * HWc * C), w(9 * N * C);
+  std::vector<float> inf(in.size()), wf(w.size());
+  srand(7);
+  for (size_t i = 0; i < in.size(); ++i) { inf[i] = (rand() % 17 - 8) / 8.f; in[i] = __float2half(inf[i]); }
+  for (size_t i = 0; i < w.size(); ++i) { wf[i] = (rand() % 15 - 7) / 16.f; w[i] = __float2half(wf[i]); }
+  std::vector<float> ref(128 * MT * N, 0.f);
+  for (int mt = 0; mt < MT; ++mt)
+    for (int y = 0; y < 16; ++y)
+      for (int x = 0; x < 8; ++x)
+        for (int n = 0; n < N; ++n) {
+          float s = 0;
+          for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx)
+              for (int c = 0; c < C; ++c)
+                s += inf[((y + ky) * HWc + mt * 8 + x + kx) * C + c] * wf[((ky * 3 + kx) * N + n) * C + c];
+          ref[(y * 8 + x) * (MT * N) + mt * N + n] = s;
+        }
+  __half *din, *dw;
+  float* dout;
+  CHECK(cudaMalloc(&din, in.size() * 2));
+  CHECK(cudaMalloc(&dw, w.size() * 2));
+  CHECK(cudaMalloc(&dout, ref.size() * 4));
+  CHECK(cudaMemcpy(din, in.data(), in.size() * 2, cudaMemcpyHostToDevice));
+  CHECK(cudaMemcpy(dw, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+  CHECK(cudaMemset(dout, 0, ref.size() * 4));
+  CHECK(cudaFuncSetAttribute(halo_compact_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+  halo_compact_kernel<C><<<1, 128, 70 * 1024>>>(din, dw, dout);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("E4 C=%d: launch failed: %s\n", C, cudaGetErrorString(e)); exit(1); }
+  std::vector<float> got(ref.size());
+  CHECK(cudaMemcpy(got.data(), dout, ref.size() * 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0; int bad = 0;
+  for (size_t i = 0; i < ref.size(); ++i) { const double d = fabs(got[i] - ref[i]); if (d > maxerr) maxerr = d; if (d > 1e-2) ++bad; }
+  printf("E4 compact pitch C=%d (%s), 4 M-tiles, shifted windows: max err %.5f, bad %d / %zu -> %s\n", C,
+         C == 16 ? "SW32" : "SW64", maxerr, bad, ref.size(), bad ? "MISMATCH" : "OK");
+}
+
 int main() {
   run_e3();
-  run_e1();
+  run_e4<16>();
+  run_e4<32>();
+  if (getenv("RUN_E1")) run_e1();
   return 0;
 }

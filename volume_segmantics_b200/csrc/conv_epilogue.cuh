@@ -57,42 +57,45 @@ __device__ __forceinline__ void store8(const EpiOut& p, const float (&f)[8], int
 }
 
 
-// 32 accumulator columns [c, c+32) of one pixel: + bias, + residual, ReLU, store.
+// 8 accumulator columns of one pixel (channels ch..ch+7): + bias, + residual, ReLU, store.
+__device__ __forceinline__ void epilogue_group8(const EpiOut& p, const uint32_t* v8, const float* bias_s,
+                                                int64_t pix, int ch) {
+  if (ch >= p.cout) return;
+  float f[8];
+  const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch);
+  const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch + 4);
+  f[0] = __uint_as_float(v8[0]) + b0.x;
+  f[1] = __uint_as_float(v8[1]) + b0.y;
+  f[2] = __uint_as_float(v8[2]) + b0.z;
+  f[3] = __uint_as_float(v8[3]) + b0.w;
+  f[4] = __uint_as_float(v8[4]) + b1.x;
+  f[5] = __uint_as_float(v8[5]) + b1.y;
+  f[6] = __uint_as_float(v8[6]) + b1.z;
+  f[7] = __uint_as_float(v8[7]) + b1.w;
+  const bool full8 = ch + 8 <= p.cout;
+  if (p.residual) {
+    if (full8) {
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + pix * p.cout + ch));
+      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 rf = unpack_act2(rw[j]);
+        f[2 * j] += rf.x;
+        f[2 * j + 1] += rf.y;
+      }
+    } else {
+      for (int j = 0; j < 8 && ch + j < p.cout; ++j) f[j] += act_to_float(p.residual[pix * p.cout + ch + j]);
+    }
+  }
+  if (p.relu) store8<true>(p, f, pix, ch, full8);
+  else store8<false>(p, f, pix, ch, full8);
+}
+
+// 32 accumulator columns [c, c+32) of one pixel.
 __device__ __forceinline__ void epilogue_chunk32(const EpiOut& p, const uint32_t (&v)[32], const float* bias_s,
                                                  int64_t pix, int ch_base) {
 #pragma unroll
-  for (int g8 = 0; g8 < 4; ++g8) {
-    const int ch = ch_base + g8 * 8;
-    if (ch >= p.cout) break;
-    float f[8];
-    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch + 4);
-    f[0] = __uint_as_float(v[g8 * 8 + 0]) + b0.x;
-    f[1] = __uint_as_float(v[g8 * 8 + 1]) + b0.y;
-    f[2] = __uint_as_float(v[g8 * 8 + 2]) + b0.z;
-    f[3] = __uint_as_float(v[g8 * 8 + 3]) + b0.w;
-    f[4] = __uint_as_float(v[g8 * 8 + 4]) + b1.x;
-    f[5] = __uint_as_float(v[g8 * 8 + 5]) + b1.y;
-    f[6] = __uint_as_float(v[g8 * 8 + 6]) + b1.z;
-    f[7] = __uint_as_float(v[g8 * 8 + 7]) + b1.w;
-    const bool full8 = ch + 8 <= p.cout;
-    if (p.residual) {
-      if (full8) {
-        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + pix * p.cout + ch));
-        const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 rf = unpack_act2(rw[j]);
-          f[2 * j] += rf.x;
-          f[2 * j + 1] += rf.y;
-        }
-      } else {
-        for (int j = 0; j < 8 && ch + j < p.cout; ++j) f[j] += act_to_float(p.residual[pix * p.cout + ch + j]);
-      }
-    }
-    if (p.relu) store8<true>(p, f, pix, ch, full8);
-    else store8<false>(p, f, pix, ch, full8);
-  }
+  for (int g8 = 0; g8 < 4; ++g8) epilogue_group8(p, &v[g8 * 8], bias_s, pix, ch_base + g8 * 8);
 }
 
 }  // namespace vsb

@@ -266,11 +266,15 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 // =====================================================================================
 // Generalised halo kernel: cp.async-assembled A tiles (see conv_halo.cuh).
 //   warps 0..3   A loaders (128 threads): 16-byte cp.async copies, zero-filled outside
-//                the image, written at the SW128-swizzled position of a 128-byte-pitch
-//                row; a stage is published after cp.async.wait_group + fence.proxy.async
+//                the image, written at the swizzled position of a compact-pitch pixel row;
+//                a stage is published after cp.async.wait_group + fence.proxy.async
 //   warp 4       MMA issuer + TMEM allocator
 //   warp 5       B producer (weights resident or ring, as above)
 //   warps 6..13  epilogue
+// MODE 0: 3x3 convolution, KC channels per slab, MT output tiles per stage.
+// MODE 1: the 7x7 stride-2 single-channel stem (smp ResNetEncoder conv1): the loader
+//         writes the im2col row of each output pixel (49 taps, zero padded to K = 64) and
+//         one tap of four K-steps is issued per tile (KC = 64, MT = 1).
 // =====================================================================================
 namespace {
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -281,40 +285,42 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void halo2_decode(const ConvHalo2Params& p, int t, int& n_tile, int& X0, int& Y0,
-                                             int& n) {
-  n_tile = t % p.n_tiles;
-  int sp = t / p.n_tiles;
-  const int tx = sp % p.tiles_x;
-  sp /= p.tiles_x;
-  const int ty = sp % p.tiles_y;
-  n = sp / p.tiles_y;
-  X0 = tx * 8;
-  Y0 = ty * 16;
+// K-major operand descriptor for the compact layouts: pitch 32 -> SW32 (6), 64 -> SW64 (4),
+// 128 -> SW128 (2); sbo = byte distance between consecutive 8-row groups.
+template <int PITCH>
+__device__ __forceinline__ uint64_t desc_compact(uint32_t addr, uint32_t sbo) {
+  constexpr uint64_t layout = PITCH == 128 ? 2ull : (PITCH == 64 ? 4ull : 6ull);
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
+         (layout << 61);
+}
+// Swizzle<B,4,3> of a byte offset relative to a 1024-byte aligned base.
+template <int PITCH>
+__device__ __forceinline__ uint32_t swz(uint32_t off) {
+  constexpr uint32_t mask = PITCH == 128 ? 7u : (PITCH == 64 ? 3u : 1u);
+  return off ^ (((off >> 7) & mask) << 4);
 }
 }  // namespace
 
-// MODE 0: 3x3 halo convolution.  MODE 1: the 7x7 stride-2 single-channel stem
-// (smp ResNetEncoder conv1): the loader writes the im2col row of each output pixel
-// (49 taps, zero padded to K = 64) and one tap of four K-steps is issued per tile.
-template <int MODE, int KS>
+template <int MODE, int KC, int MT>
 __global__ void __launch_bounds__(HALO2_THREADS, 1)
 conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
+  constexpr int P = 2 * KC;                 // pixel pitch in bytes
+  constexpr int KS = KC / 16;               // K-steps per slab
+  constexpr int HW = 8 * MT + 2, HH = 18;   // halo tile (MODE 0)
+  constexpr int NTAPS = MODE == 0 ? 9 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_ring = smem;
   uint8_t* b_area = smem + (size_t)p.a_stages * p.a_stage_bytes;
   const size_t b_area_bytes =
-      p.b_stages ? (size_t)p.b_stages * p.b_bytes : (size_t)p.nslabs * (MODE == 0 ? 9 : 1) * p.b_bytes;
+      p.b_stages ? (size_t)p.b_stages * p.b_bytes : (size_t)p.nslabs * NTAPS * p.b_bytes;
   HaloCtl* ctl = reinterpret_cast<HaloCtl*>(b_area + b_area_bytes);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + kHaloCtlBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.n_tiles * p.tiles_x * p.tiles_y * p.NB;
-  constexpr int HW = 10, HH = 18;
-  constexpr int NTAPS = MODE == 0 ? 9 : 1;
   const bool resident = p.b_stages == 0;
 
   if (threadIdx.x == 0) {
@@ -340,6 +346,18 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
   tc_fence_after_sync();
   const uint32_t tmem_base = ctl->tmem_base;
 
+  // tile index -> (n_tile, X0, Y0, image)
+  auto decode = [&](int t, int& n_tile, int& X0, int& Y0, int& n) {
+    n_tile = t % p.n_tiles;
+    int sp = t / p.n_tiles;
+    const int tx = sp % p.tiles_x;
+    sp /= p.tiles_x;
+    const int ty = sp % p.tiles_y;
+    n = sp / p.tiles_y;
+    X0 = tx * (8 * MT);
+    Y0 = ty * 16;
+  };
+
   if (warp < HALO2_LOAD_WARPS) {
     // ===================== A loaders =====================
     const int ptid = threadIdx.x;  // 0..127
@@ -354,7 +372,7 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
     const uint32_t ring_addr = smem_u32(a_ring);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n_tile, X0, Y0, n;
-      halo2_decode(p, t, n_tile, X0, Y0, n);
+      decode(t, n_tile, X0, Y0, n);
       if (MODE == 1) {
         const HaloSrc& sv = p.src[0];
         const uint16_t* img = sv.ptr + (int64_t)n * sv.Hs * sv.Ws;
@@ -393,34 +411,19 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
       for (int s = 0; s < p.nslabs; ++s) {
         const HaloSrc& sv = p.src[p.slab_src[s]];
         const int c0 = p.slab_c0[s];
-        const int ch8_log2 = p.slab_kc[s] == 64 ? 3 : (p.slab_kc[s] >= 32 ? 2 : 1);  // 16-B chunks per pixel
-        const int ch8 = p.slab_kc[s] >> 3;
+        constexpr int CH8 = KC / 8;  // 16-byte chunks per pixel
         mbar_wait(&ctl->a_empty[as], aph ^ 1);
         const uint32_t stage_addr = ring_addr + (uint32_t)as * p.a_stage_bytes;
         const uint16_t* img = sv.ptr + (int64_t)n * sv.Hs * sv.Ws * sv.C + c0;
-        if (ch8 == (1 << ch8_log2)) {
-          const int total = (HW * HH) << ch8_log2;
-          for (int idx = ptid; idx < total; idx += 32 * HALO2_LOAD_WARPS) {
-            const int j = idx & (ch8 - 1);
-            const int pix = idx >> ch8_log2;
-            const int hy = pix / HW, hx = pix - hy * HW;
-            const int y = Y0 - 1 + hy, x = X0 - 1 + hx;
-            const bool ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
-            const int sy = sv.up ? y >> 1 : y, sx = sv.up ? x >> 1 : x;
-            const uint16_t* g = img + ((int64_t)sy * sv.Ws + sx) * sv.C + j * 8;
-            cp_async_16(stage_addr + pix * 128 + ((j ^ (pix & 7)) << 4), ok ? g : sv.ptr, ok ? 16u : 0u);
-          }
-        } else {  // 48 channels: 6 chunks per pixel
-          const int total = HW * HH * ch8;
-          for (int idx = ptid; idx < total; idx += 32 * HALO2_LOAD_WARPS) {
-            const int pix = idx / ch8, j = idx - pix * ch8;
-            const int hy = pix / HW, hx = pix - hy * HW;
-            const int y = Y0 - 1 + hy, x = X0 - 1 + hx;
-            const bool ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
-            const int sy = sv.up ? y >> 1 : y, sx = sv.up ? x >> 1 : x;
-            const uint16_t* g = img + ((int64_t)sy * sv.Ws + sx) * sv.C + j * 8;
-            cp_async_16(stage_addr + pix * 128 + ((j ^ (pix & 7)) << 4), ok ? g : sv.ptr, ok ? 16u : 0u);
-          }
+        for (int idx = ptid; idx < HW * HH * CH8; idx += 32 * HALO2_LOAD_WARPS) {
+          const int j = idx % CH8;
+          const int pix = idx / CH8;
+          const int hy = pix / HW, hx = pix - hy * HW;
+          const int y = Y0 - 1 + hy, x = X0 - 1 + hx;
+          const bool ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
+          const int sy = sv.up ? y >> 1 : y, sx = sv.up ? x >> 1 : x;
+          const uint16_t* g = img + ((int64_t)sy * sv.Ws + sx) * sv.C + j * 8;
+          cp_async_16(stage_addr + swz<P>((uint32_t)(pix * P + j * 16)), ok ? g : sv.ptr, ok ? 16u : 0u);
         }
         cp_async_commit();
         if (++inflight > depth) {
@@ -428,10 +431,7 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
             case 1: cp_async_wait<1>(); break;
             case 2: cp_async_wait<2>(); break;
             case 3: cp_async_wait<3>(); break;
-            case 4: cp_async_wait<4>(); break;
-            case 5: cp_async_wait<5>(); break;
-            case 6: cp_async_wait<6>(); break;
-            default: cp_async_wait<7>(); break;
+            default: cp_async_wait<4>(); break;
           }
           fence_proxy_async_smem();
           mbar_arrive(&ctl->a_full[oldest]);
@@ -486,24 +486,36 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
     int as = 0, bs = 0, acc = 0;
     uint32_t aph = 0, bph = 0, acc_phase = 0;
     const uint32_t idesc = umma_idesc_act(128, p.BN);
-    const uint64_t a_desc0 = umma_smem_desc_sw128(smem_u32(a_ring), MODE == 0 ? HW * 128 : 1024);
-    const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(b_area), 1024);
+    const uint64_t a_desc0 = desc_compact<P>(smem_u32(a_ring), MODE == 0 ? HW * P : 8 * P);
+    const uint64_t b_desc0 = desc_compact<P>(smem_u32(b_area), 8 * P);
     const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4;
     const uint32_t b_step = (uint32_t)p.b_bytes >> 4;
+    constexpr uint32_t PX = P / 16;  // one pixel, in descriptor address units
     if (resident) mbar_wait(&ctl->w_full, 0);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       mbar_wait(&ctl->acc_empty[acc], acc_phase ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
       for (int s = 0; s < p.nslabs; ++s) {
-        const int ksteps = KS ? KS : (p.slab_kc[s] >> 4);
         mbar_wait(&ctl->a_full[as], aph);
         tc_fence_after_sync();
         const uint64_t a_stage_desc = desc_add(a_desc0, as * a_step);
-        if (resident && KS != 0) {
+        if (resident) {
           if (elect_one()) {
-            issue_slab_resident<NTAPS, KS ? KS : 1>(d_tmem, a_stage_desc, desc_add(b_desc0, s * NTAPS * b_step),
-                                                    b_step, HW * 8, 8, idesc, s != 0);
+            const uint64_t b_slab = desc_add(b_desc0, s * NTAPS * b_step);
+#pragma unroll
+            for (int tap = 0; tap < NTAPS; ++tap) {
+              const uint64_t bt = desc_add(b_slab, tap * b_step);
+#pragma unroll
+              for (int k = 0; k < KS; ++k) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint64_t at = desc_add(a_stage_desc, ((tap / 3) * HW + (tap % 3) + mt * 8) * PX + 2 * k);
+                  umma_bf16_ss(d_tmem + mt * p.BN, at, desc_add(bt, 2 * k), idesc,
+                               (tap | k) != 0 ? 1u : (s != 0 ? 1u : 0u));
+                }
+              }
+            }
             umma_commit(&ctl->a_empty[as]);
             if (s == p.nslabs - 1) umma_commit(&ctl->acc_full[acc]);
           }
@@ -511,33 +523,27 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
         } else {
 #pragma unroll
           for (int tap = 0; tap < NTAPS; ++tap) {
-            uint64_t bt;
-            if (resident) {
-              bt = desc_add(b_desc0, (s * NTAPS + tap) * b_step);
-            } else {
-              mbar_wait(&ctl->b_full[bs], bph);
-              tc_fence_after_sync();
-              bt = desc_add(b_desc0, bs * b_step);
-            }
+            mbar_wait(&ctl->b_full[bs], bph);
+            tc_fence_after_sync();
             if (elect_one()) {
-              const uint64_t at = desc_add(a_stage_desc, (tap / 3) * (HW * 8) + (tap % 3) * 8);
-              if (KS != 0) {
+              const uint64_t bt = desc_add(b_desc0, bs * b_step);
 #pragma unroll
-                for (int k = 0; k < (KS ? KS : 1); ++k)
-                  umma_bf16_ss(d_tmem, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc,
+              for (int k = 0; k < KS; ++k) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint64_t at = desc_add(a_stage_desc, ((tap / 3) * HW + (tap % 3) + mt * 8) * PX + 2 * k);
+                  umma_bf16_ss(d_tmem + mt * p.BN, at, desc_add(bt, 2 * k), idesc,
                                (tap | k) != 0 ? 1u : (s != 0 ? 1u : 0u));
-              } else {
-                for (int k = 0; k < ksteps; ++k)
-                  umma_bf16_ss(d_tmem, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc, (s | tap | k) != 0);
+                }
               }
-              if (!resident) umma_commit(&ctl->b_empty[bs]);
+              umma_commit(&ctl->b_empty[bs]);
               if (tap == NTAPS - 1) {
                 umma_commit(&ctl->a_empty[as]);
                 if (s == p.nslabs - 1) umma_commit(&ctl->acc_full[acc]);
               }
             }
             __syncwarp();
-            if (!resident && ++bs == p.b_stages) {
+            if (++bs == p.b_stages) {
               bs = 0;
               bph ^= 1;
             }
@@ -562,21 +568,31 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
     const int row = quarter * 32 + lane;
     const int xi = row & 7, yi = row >> 3;
     const EpiOut eo{p.out, p.residual, p.out_f32, p.relu, p.cout};
+    const int ncols = MT * p.BN;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n_tile, X0, Y0, n;
-      halo2_decode(p, t, n_tile, X0, Y0, n);
-      const int ox = X0 + xi, oy = Y0 + yi;
-      const bool valid = ox < p.W && oy < p.H;
-      const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
+      decode(t, n_tile, X0, Y0, n);
+      const int oy = Y0 + yi;
+      const int64_t rowpix = ((int64_t)n * p.H + oy) * p.W;
       const int ch0 = n_tile * p.BN;
       mbar_wait(&ctl->acc_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
-      for (int c = half * 32; c < p.BN; c += 64) {
+      for (int c = half * 32; c < ncols; c += 64) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c, v);
         tmem_ld_wait();
-        if (valid) epilogue_chunk32(eo, v, bias_s, pix, ch0 + c);
+        if (oy < p.H) {
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const int col = c + g8 * 8;
+            if (col >= ncols) break;
+            const int mt = MT == 1 ? 0 : col / p.BN;
+            const int ch = MT == 1 ? col : col - mt * p.BN;
+            const int ox = X0 + mt * 8 + xi;
+            if (ox < p.W) epilogue_group8(eo, &v[g8 * 8], bias_s, rowpix + ox, ch0 + ch);
+          }
+        }
       }
       tc_fence_before_sync();
       mbar_arrive(&ctl->acc_empty[acc]);
@@ -600,19 +616,36 @@ size_t conv_halo2_smem_bytes(const ConvHalo2Params& p) {
   return (size_t)p.a_stages * p.a_stage_bytes + b + kHaloCtlBytes + kHaloBiasBytes + 1024;
 }
 
+namespace {
+template <int MODE, int KC, int MT>
+cudaError_t halo2_launch_one(const ConvHalo2Params& p, int grid, size_t smem, cudaStream_t st, bool configure) {
+  if (configure)
+    return cudaFuncSetAttribute(conv_halo2_kernel<MODE, KC, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                227 * 1024);
+  conv_halo2_kernel<MODE, KC, MT><<<grid, HALO2_THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t halo2_dispatch(const ConvHalo2Params& p, int grid, size_t smem, cudaStream_t st, bool configure) {
+  if (p.stem) return halo2_launch_one<1, 64, 1>(p, grid, smem, st, configure);
+  const int key = p.kc * 10 + p.mt;
+  switch (key) {
+    case 641: return halo2_launch_one<0, 64, 1>(p, grid, smem, st, configure);
+    case 642: return halo2_launch_one<0, 64, 2>(p, grid, smem, st, configure);
+    case 321: return halo2_launch_one<0, 32, 1>(p, grid, smem, st, configure);
+    case 322: return halo2_launch_one<0, 32, 2>(p, grid, smem, st, configure);
+    case 324: return halo2_launch_one<0, 32, 4>(p, grid, smem, st, configure);
+    case 161: return halo2_launch_one<0, 16, 1>(p, grid, smem, st, configure);
+    case 162: return halo2_launch_one<0, 16, 2>(p, grid, smem, st, configure);
+    case 164: return halo2_launch_one<0, 16, 4>(p, grid, smem, st, configure);
+    default: return cudaErrorInvalidValue;
+  }
+}
+}  // namespace
+
 cudaError_t launch_conv_halo2(const ConvHalo2Params& p, int num_sms, cudaStream_t st) {
   const int total_tiles = p.n_tiles * p.tiles_x * p.tiles_y * p.NB;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-  const size_t smem = conv_halo2_smem_bytes(p);
-  int ks = p.slab_kc[0] >> 4;  // uniform K-steps per slab, else 0 (runtime)
-  for (int s = 1; s < p.nslabs; ++s)
-    if ((p.slab_kc[s] >> 4) != ks) ks = 0;
-  if (p.stem) conv_halo2_kernel<1, 4><<<grid, HALO2_THREADS, smem, st>>>(p);
-  else if (ks == 4) conv_halo2_kernel<0, 4><<<grid, HALO2_THREADS, smem, st>>>(p);
-  else if (ks == 2) conv_halo2_kernel<0, 2><<<grid, HALO2_THREADS, smem, st>>>(p);
-  else if (ks == 1) conv_halo2_kernel<0, 1><<<grid, HALO2_THREADS, smem, st>>>(p);
-  else conv_halo2_kernel<0, 0><<<grid, HALO2_THREADS, smem, st>>>(p);
-  return cudaGetLastError();
+  return halo2_dispatch(p, grid, conv_halo2_smem_bytes(p), st, false);
 }
 
 size_t conv_halo_smem_bytes(const ConvHaloParams& p) {
@@ -622,16 +655,17 @@ size_t conv_halo_smem_bytes(const ConvHaloParams& p) {
 
 cudaError_t conv_halo_configure() {
   cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_halo2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_halo2_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_halo2_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_halo2_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_halo2_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  ConvHalo2Params q{};
+  q.stem = 1;
+  if (e == cudaSuccess) e = halo2_dispatch(q, 0, 0, nullptr, true);
+  q.stem = 0;
+  for (int kc : {16, 32, 64})
+    for (int mt : {1, 2, 4}) {
+      if (kc == 64 && mt == 4) continue;
+      q.kc = kc;
+      q.mt = mt;
+      if (e == cudaSuccess) e = halo2_dispatch(q, 0, 0, nullptr, true);
+    }
   return e;
 }
 

@@ -38,22 +38,29 @@ struct ConvHaloParams {
 };
 
 // ---- generalised variant: the halo tile is assembled by four cp.async producer warps
-// instead of TMA, so a K-slab may come from any of several concatenated sources, may
-// hold 16/32/48/64 channels (rows keep the 128-byte pitch of the SW128 layout; only
-// kc/16 K-steps are issued) and may be a nearest-x2 up-sampled view of a half-
-// resolution tensor (smp DecoderBlock: upsample -> concat -> conv).  dil = 1.
+// instead of TMA, so a K-slab may come from any of several concatenated sources and may
+// be a nearest-x2 up-sampled view of a half-resolution tensor (smp DecoderBlock:
+// upsample -> concat -> conv).  dil = 1.  Every slab of a launch holds KC = 16 / 32 / 64
+// channels; pixels are stored with the compact pitch 2*KC bytes in the matching
+// SW32 / SW64 / SW128 layout (the swizzle XOR uses absolute address bits, so the tap
+// windows may start at any pixel; verified by tests/micro/halo_mma_test.cu).
+// One stage covers MT horizontally adjacent 8x16 output tiles: their (8*MT+2) x 18 halo is
+// loaded once, MT x 9 x KC/16 MMAs are issued per slab into MT accumulator column ranges,
+// and each weight image is reused by MT tiles -- this amortises the mbarrier hand-offs
+// that dominate narrow (Cout = 16 / 32) full-resolution layers.
 struct HaloSrc {
   const uint16_t* ptr;  // NHWC
   int32_t C, Hs, Ws, up;
 };
-constexpr int HALO2_MAX_SLABS = 32;
+constexpr int HALO2_MAX_SLABS = 64;
 struct ConvHalo2Params {
   HaloSrc src[6];
   int32_t n_src, nslabs;
   int32_t stem;  // 1: 7x7 stride-2 single-channel stem (im2col rows built by the loaders)
+  int32_t kc;    // channels per slab (16 / 32 / 64), uniform
+  int32_t mt;    // M tiles per stage (1 / 2 / 4)
   int8_t slab_src[HALO2_MAX_SLABS];
   int16_t slab_c0[HALO2_MAX_SLABS];
-  int8_t slab_kc[HALO2_MAX_SLABS];  // channels in the slab: 16..64
   const uint8_t* wpacked;           // [n_tile][slab][tap] images of [BN][128 B] rows
   const float* bias;
   const uint16_t* residual;

@@ -352,22 +352,30 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
   if (!cp.halo_ok && !cp.s2 && op.kh == 3 && op.kw == 3 && op.pad == 1 && op.dil == 1) {
     vsb::ConvHalo2Params& h = cp.h2params;
     h = vsb::ConvHalo2Params{};
+    int kc = 64;
+    for (int s = 0; s < op.n_src; ++s) {
+      const int C = e->tdesc[op.src[s]].channels;
+      kc = std::min(kc, C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16));
+    }
     int ns = 0;
     bool fits = true;
     for (int s = 0; s < op.n_src && fits; ++s) {
       const int C = e->tdesc[op.src[s]].channels;
-      for (int c0 = 0; c0 < C; c0 += 64) {
+      for (int c0 = 0; c0 < C; c0 += kc) {
         if (ns >= vsb::HALO2_MAX_SLABS) { fits = false; break; }
         h.slab_src[ns] = (int8_t)s;
         h.slab_c0[ns] = (int16_t)c0;
-        h.slab_kc[ns] = (int8_t)std::min(64, C - c0);
         ++ns;
       }
     }
     if (fits) {
       h.nslabs = ns;
       h.n_src = op.n_src;
-      const size_t img = (size_t)cp.BN * 128;
+      h.kc = kc;
+      const int P = 2 * kc;
+      const uint32_t mask = P == 128 ? 7u : (P == 64 ? 3u : 1u);
+      const size_t img = align_up((size_t)cp.BN * P, 1024);
+      h.b_bytes = (int32_t)img;
       std::vector<uint8_t> hp((size_t)cp.n_tiles * ns * 9 * img, 0);
       for (int nt = 0; nt < cp.n_tiles; ++nt)
         for (int sl = 0; sl < ns; ++sl)
@@ -378,8 +386,11 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
               const int o = nt * cp.BN + n;
               if (o >= op.cout) break;
               const int64_t wrow = (((int64_t)o * 3 + tap / 3) * 3 + tap % 3) * op.cin + cbase;
-              for (int ch = 0; ch < h.slab_kc[sl] / 8; ++ch)
-                memcpy(dst + (size_t)n * 128 + ((ch ^ (n & 7)) * 16), e->h_weights.data() + op.w_off + (wrow + ch * 8) * 2, 16);
+              for (int ch = 0; ch < kc / 8; ++ch) {
+                uint32_t off = (uint32_t)(n * P + ch * 16);
+                off ^= ((off >> 7) & mask) << 4;  // Swizzle<B,4,3> relative to the 1024-aligned image
+                memcpy(dst + off, e->h_weights.data() + op.w_off + (wrow + ch * 8) * 2, 16);
+              }
             }
           }
       CK(cudaMalloc(&cp.d_whalo, hp.size()));
@@ -507,9 +518,10 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
       vsb::ConvHalo2Params& h = cp.h2params;
       h = vsb::ConvHalo2Params{};
       h.stem = 1;
+      h.kc = 64;
+      h.mt = 1;
       h.n_src = 1;
       h.nslabs = 1;
-      h.slab_kc[0] = 64;
       h.src[0].ptr = (const uint16_t*)st.ptr;
       h.src[0].C = 1;
       h.src[0].Hs = st.H;
@@ -585,21 +597,29 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
     if (p.num_stages < 2) return fail(VSB_ERR_UNSUPPORTED, "op %d: too few pipeline stages", i);
     cp.use_halo2 = false;
     if (cp.halo2_ok) {
-      const int tx = (ot.W + 7) / 8, ty = (ot.H + 15) / 16;
-      const double eff = (double)ot.W * ot.H / ((double)tx * 8 * ty * 16);
       vsb::ConvHalo2Params& h = cp.h2params;
+      const int P = 2 * h.kc;
+      int mt = std::min(h.kc == 64 ? 2 : 4, std::max(1, 256 / cp.BN));
+      mt = mt >= 4 ? 4 : (mt >= 2 ? 2 : 1);
+      int tx = 0, ty = (ot.H + 15) / 16;
+      double eff = 0;
+      for (;; mt /= 2) {
+        tx = (ot.W + 8 * mt - 1) / (8 * mt);
+        eff = (double)ot.W * ot.H / ((double)tx * 8 * mt * ty * 16);
+        if (eff >= 0.6 || mt == 1) break;
+      }
+      h.mt = mt;
       h.BN = cp.BN;
       h.n_tiles = cp.n_tiles;
-      h.b_bytes = cp.BN * 128;
-      h.a_stage_bytes = (int)align_up((size_t)10 * 18 * 128, 1024);
+      h.a_stage_bytes = (int)align_up((size_t)(8 * mt + 2) * 18 * P, 1024);
       const size_t budget = 200 * 1024;
       const size_t res_bytes = (size_t)h.nslabs * 9 * h.b_bytes;
       if (cp.n_tiles == 1 && res_bytes + 3 * (size_t)h.a_stage_bytes <= budget) {
         h.b_stages = 0;
         h.a_stages = (int)std::min<size_t>(vsb::HALO_MAX_A_STAGES, (budget - res_bytes) / h.a_stage_bytes);
       } else {
-        h.a_stages = 4;
-        h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, (budget - 4 * (size_t)h.a_stage_bytes) / h.b_bytes);
+        h.a_stages = 3;
+        h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, (budget - 3 * (size_t)h.a_stage_bytes) / h.b_bytes);
       }
       if (eff >= 0.6 && (h.b_stages == 0 || h.b_stages >= 2)) {
         for (int s = 0; s < op.n_src; ++s) {
