@@ -252,7 +252,7 @@ def run_ours(args):
     roofline = None
     if conv_ms > 0:
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)", "achieved": ach,
+        roofline = {"bound": "tensor", "kernel": "tcgen05 conv kernels (conv_halo_kernel, conv_halo2_kernel<>, conv_tc_kernel<>)", "achieved": ach,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
                     "launches": conv_n, "avg_launch_ms": conv_ms / max(1, conv_n),
                     "flops_per_launch": conv_flops / max(1, conv_n),

@@ -59,7 +59,7 @@ __device__ __forceinline__ void store8(const EpiOut& p, const float (&f)[8], int
 
 // 8 accumulator columns of one pixel (channels ch..ch+7): + bias, + residual, ReLU, store.
 __device__ __forceinline__ void epilogue_group8(const EpiOut& p, const uint32_t* v8, const float* bias_s,
-                                                int64_t pix, int ch) {
+                                                int64_t pix, int ch, const uint4* res_pre = nullptr) {
   if (ch >= p.cout) return;
   float f[8];
   const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch);
@@ -75,7 +75,7 @@ __device__ __forceinline__ void epilogue_group8(const EpiOut& p, const uint32_t*
   const bool full8 = ch + 8 <= p.cout;
   if (p.residual) {
     if (full8) {
-      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + pix * p.cout + ch));
+      const uint4 rv = res_pre ? *res_pre : __ldg(reinterpret_cast<const uint4*>(p.residual + pix * p.cout + ch));
       const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -93,9 +93,20 @@ __device__ __forceinline__ void epilogue_group8(const EpiOut& p, const uint32_t*
 
 // 32 accumulator columns [c, c+32) of one pixel.
 __device__ __forceinline__ void epilogue_chunk32(const EpiOut& p, const uint32_t (&v)[32], const float* bias_s,
-                                                 int64_t pix, int ch_base) {
+                                                 int64_t pix, int ch_base, const uint4* res_pre = nullptr) {
 #pragma unroll
-  for (int g8 = 0; g8 < 4; ++g8) epilogue_group8(p, &v[g8 * 8], bias_s, pix, ch_base + g8 * 8);
+  for (int g8 = 0; g8 < 4; ++g8)
+    epilogue_group8(p, &v[g8 * 8], bias_s, pix, ch_base + g8 * 8, res_pre ? res_pre + g8 : nullptr);
+}
+
+// Issue the residual loads of one 32-channel chunk early (before the accumulator is ready)
+// so their latency hides behind the main loop.  Only whole 8-channel groups are prefetched.
+__device__ __forceinline__ bool prefetch_residual32(const EpiOut& p, int64_t pix, int ch_base, uint4 (&r)[4]) {
+  if (!p.residual || ch_base + 32 > p.cout) return false;
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8)
+    r[g8] = __ldg(reinterpret_cast<const uint4*>(p.residual + pix * p.cout + ch_base + g8 * 8));
+  return true;
 }
 
 }  // namespace vsb

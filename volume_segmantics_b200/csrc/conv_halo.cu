@@ -32,7 +32,7 @@ __device__ __forceinline__ void halo_decode(const ConvHaloParams& p, int t, int&
   const int tx = sp % p.tiles_x;
   sp /= p.tiles_x;
   const int ty = sp % p.tiles_y;
-  n = sp / p.tiles_y;
+  n = sp / p.tiles_y + p.n_base;
   X0 = tx * 8;
   Y0 = ty * 16;
 }
@@ -237,6 +237,12 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       const bool valid = ox < p.W && oy < p.H;
       const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
       const int ch0 = n_tile * p.BN;
+      uint4 rpre0[4], rpre1[4];
+      bool have0 = false, have1 = false;
+      if (valid) {
+        if (half * 32 < p.BN) have0 = prefetch_residual32(eo, pix, ch0 + half * 32, rpre0);
+        if (half * 32 + 64 < p.BN) have1 = prefetch_residual32(eo, pix, ch0 + half * 32 + 64, rpre1);
+      }
       mbar_wait(&ctl->acc_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
@@ -244,7 +250,10 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c, v);
         tmem_ld_wait();
-        if (valid) epilogue_chunk32(eo, v, bias_s, pix, ch0 + c);
+        if (valid) {
+          const uint4* rp = (c == half * 32 && have0) ? rpre0 : ((c == half * 32 + 64 && have1) ? rpre1 : nullptr);
+          epilogue_chunk32(eo, v, bias_s, pix, ch0 + c, rp);
+        }
       }
       tc_fence_before_sync();
       mbar_arrive(&ctl->acc_empty[acc]);
@@ -353,7 +362,7 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
     const int tx = sp % p.tiles_x;
     sp /= p.tiles_x;
     const int ty = sp % p.tiles_y;
-    n = sp / p.tiles_y;
+    n = sp / p.tiles_y + p.n_base;
     X0 = tx * (8 * MT);
     Y0 = ty * 16;
   };
@@ -377,22 +386,22 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
         const HaloSrc& sv = p.src[0];
         const uint16_t* img = sv.ptr + (int64_t)n * sv.Hs * sv.Ws;
         const int m = ptid, ox = X0 + (m & 7), oy = Y0 + (m >> 3);
+        // K layout: chunk ky (16 bytes) = input columns 2*ox-4 .. 2*ox+3 of row 2*oy+ky-3, i.e.
+        // four aligned 32-bit words; column 2*ox-4 is outside the 7x7 window and meets a zero weight.
         uint32_t vals[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) vals[i] = 0;
 #pragma unroll
         for (int ky = 0; ky < 7; ++ky) {
           const int iy = 2 * oy + ky - 3;
           const bool oky = iy >= 0 && iy < sv.Hs;
+          const uint32_t* rowp = reinterpret_cast<const uint32_t*>(img + (int64_t)iy * sv.Ws);
 #pragma unroll
-          for (int kx = 0; kx < 7; ++kx) {
-            const int ix = 2 * ox + kx - 3;
-            const int k = ky * 7 + kx;
-            uint32_t v = 0;
-            if (oky && ix >= 0 && ix < sv.Ws) v = __ldg(img + (int64_t)iy * sv.Ws + ix);
-            vals[k >> 1] |= v << (16 * (k & 1));
+          for (int wq = 0; wq < 4; ++wq) {
+            const int col = 2 * ox - 4 + 2 * wq;  // even; the pair (col, col+1) is inside or outside together
+            vals[ky * 4 + wq] = (oky && col >= 0 && col < sv.Ws) ? __ldg(rowp + (col >> 1)) : 0u;
           }
         }
+#pragma unroll
+        for (int i = 28; i < 32; ++i) vals[i] = 0;
         mbar_wait(&ctl->a_empty[as], aph ^ 1);
         const uint32_t row_addr = ring_addr + (uint32_t)as * p.a_stage_bytes + m * 128;
 #pragma unroll

@@ -29,6 +29,7 @@ struct ConvHaloParams {
   int32_t out_f32, relu, cout;
   int32_t BN, n_tiles;
   int32_t NB, H, W;
+  int32_t n_base;            // first image of this launch
   int32_t ncs;               // Cin / 64
   int32_t dil;
   int32_t tiles_x, tiles_y;
@@ -68,6 +69,7 @@ struct ConvHalo2Params {
   int32_t out_f32, relu, cout;
   int32_t BN, n_tiles;
   int32_t NB, H, W;
+  int32_t n_base;
   int32_t tiles_x, tiles_y;
   int32_t a_stages, a_stage_bytes;
   int32_t b_stages, b_bytes;

@@ -52,7 +52,7 @@ __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int t, int& n
   const int tn = sp / p.tiles_y;
   X0 = tx << p.bw_log2;
   Y0 = ty << p.bh_log2;
-  N0 = tn << p.nt_log2;
+  N0 = (tn << p.nt_log2);
 }
 
 }  // namespace
@@ -123,7 +123,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
             for (int q = 0; q < ncls; ++q)
               tma_load_5d(map, &ctl->full[stage], a_dst + q * cls_bytes,
                           run.cls[q][0] + b * (RB / 2), X0 + run.cls[q][1], run.cls[q][2],
-                          Y0 + run.cls[q][3], N0);
+                          Y0 + run.cls[q][3], N0 + p.n_base);
             bulk_load_1d(a_dst + p.a_bytes, wsrc + b * wstep, b_bytes, &ctl->full[stage]);
           }
           __syncwarp();
@@ -198,7 +198,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
       }
       const int on = N0 + ni;
       const bool valid = on < p.NB && oy < p.H && ox < p.W;
-      const int64_t pix = ((int64_t)on * p.H + oy) * p.W + ox;
+      const int64_t pix = ((int64_t)(on + p.n_base) * p.H + oy) * p.W + ox;
       const int ch0 = n_tile * p.BN;
 
       mbar_wait(&ctl->acc_full[acc], acc_phase);

@@ -141,6 +141,7 @@ struct vsb_engine {
   int batch_override = 0;
   int conv_impl = 0;
   bool no_halo = false;
+  int sub_batch_mb = 0;  // L2 budget (MB) per tensor for depth-first sub-batches; 0 = off (measured slower: per-launch prologue dominates)
   bool profiling = false;
   std::vector<float> op_ms;
   std::vector<int64_t> op_launches;
@@ -232,12 +233,12 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
     cp.BN = op.cout;
     cp.n_tiles = 1;
     std::vector<uint8_t> img((size_t)cp.BN * 128, 0);
+    // K index = ky * 8 + j with j = kx + 1 (j = 0 is input column 2*ox-4, outside the window: weight 0)
     for (int n = 0; n < op.cout; ++n)
-      for (int k = 0; k < 49; ++k) {
-        const int ch = k / 8;  // 16-byte chunk of 8 taps
-        memcpy(img.data() + (size_t)n * 128 + ((ch ^ (n & 7)) * 16) + (k % 8) * 2,
-               e->h_weights.data() + op.w_off + ((int64_t)n * 49 + k) * 2, 2);
-      }
+      for (int ky = 0; ky < 7; ++ky)
+        for (int kx = 0; kx < 7; ++kx)
+          memcpy(img.data() + (size_t)n * 128 + ((ky ^ (n & 7)) * 16) + (kx + 1) * 2,
+                 e->h_weights.data() + op.w_off + ((int64_t)n * 49 + ky * 7 + kx) * 2, 2);
     CK(cudaMalloc(&cp.d_whalo, img.size()));
     CK(cudaMemcpy(cp.d_whalo, img.data(), img.size(), cudaMemcpyHostToDevice));
     std::vector<float> bias(cp.BN, 0.f);
@@ -740,13 +741,15 @@ void prof_collect(vsb_engine* e) {
 }
 
 // ---- executor ----------------------------------------------------------------
-int run_conv(vsb_engine* e, int oi, int nb) {
+// Runs op `oi` on images [n0, n0 + nb) of the current batch.
+int run_conv(vsb_engine* e, int oi, int n0, int nb) {
   const vsb_op& op = e->ops[oi];
   ConvPlan& cp = e->conv[oi];
   const TensorBuf& ot = e->tens[op.out];
   if (cp.tc && cp.use_halo && e->conv_impl == 0 && !e->no_halo) {
     vsb::ConvHaloParams h = cp.hparams;
     h.NB = nb;
+    h.n_base = n0;
     ProfScope ps(e, PC_CONV_TC, oi);
     CK(vsb::launch_conv_halo(h, e->num_sms, e->stream));
     return VSB_OK;
@@ -754,6 +757,7 @@ int run_conv(vsb_engine* e, int oi, int nb) {
   if (cp.stem_tc && e->conv_impl == 0 && !e->no_halo) {
     vsb::ConvHalo2Params h = cp.h2params;
     h.NB = nb;
+    h.n_base = n0;
     ProfScope ps(e, PC_STEM, oi);
     CK(vsb::launch_conv_halo2(h, e->num_sms, e->stream));
     return VSB_OK;
@@ -761,6 +765,7 @@ int run_conv(vsb_engine* e, int oi, int nb) {
   if (cp.tc && cp.use_halo2 && e->conv_impl == 0 && !e->no_halo) {
     vsb::ConvHalo2Params h = cp.h2params;
     h.NB = nb;
+    h.n_base = n0;
     ProfScope ps(e, PC_CONV_TC, oi);
     CK(vsb::launch_conv_halo2(h, e->num_sms, e->stream));
     return VSB_OK;
@@ -768,6 +773,7 @@ int run_conv(vsb_engine* e, int oi, int nb) {
   if (cp.tc && e->conv_impl == 0) {
     vsb::ConvTcParams p = cp.params;
     p.NB = nb;
+    p.n_base = n0;
     p.tiles_n = (nb + (1 << p.nt_log2) - 1) >> p.nt_log2;
     ProfScope ps(e, PC_CONV_TC, oi);
     CK(vsb::launch_conv_tc(p, e->num_sms, e->stream));
@@ -777,8 +783,9 @@ int run_conv(vsb_engine* e, int oi, int nb) {
   if (e->conv_impl != 2 && op.cin == 1 && op.kh == 7 && op.kw == 7 && op.stride == 2 && op.pad == 3 &&
       op.cout == 64 && op.n_src == 1 && ot.dtype == 0 && op.res < 0) {
     ProfScope ps(e, PC_STEM, oi);
-    vsb::launch_stem7x7((const uint16_t*)s0.ptr, nb, s0.H, s0.W, e->d_weights + op.w_off,
-                        (const float*)(e->d_weights + op.b_off), (uint16_t*)ot.ptr, op.relu, e->stream);
+    vsb::launch_stem7x7((const uint16_t*)s0.ptr + (size_t)n0 * s0.H * s0.W, nb, s0.H, s0.W, e->d_weights + op.w_off,
+                        (const float*)(e->d_weights + op.b_off),
+                        (uint16_t*)ot.ptr + (size_t)n0 * ot.H * ot.W * ot.C, op.relu, e->stream);
     CK(cudaGetLastError());
     return VSB_OK;
   }
@@ -786,7 +793,7 @@ int run_conv(vsb_engine* e, int oi, int nb) {
   a.n_src = op.n_src;
   for (int s = 0; s < op.n_src; ++s) {
     const TensorBuf& st = e->tens[op.src[s]];
-    a.src[s].ptr = st.ptr;
+    a.src[s].ptr = (const uint8_t*)st.ptr + (size_t)n0 * st.H * st.W * st.C * 2;
     a.src[s].C = st.C;
     a.src[s].H = st.H;
     a.src[s].W = st.W;
@@ -797,8 +804,9 @@ int run_conv(vsb_engine* e, int oi, int nb) {
   a.stride = op.stride; a.pad = op.pad; a.dil = op.dil; a.groups = op.groups; a.relu = op.relu;
   a.weights = e->d_weights + op.w_off;
   a.bias = op.b_off >= 0 ? (const float*)(e->d_weights + op.b_off) : nullptr;
-  a.residual = op.res >= 0 ? e->tens[op.res].ptr : nullptr;
-  a.out = ot.ptr;
+  const size_t out_off = (size_t)n0 * ot.H * ot.W * ot.C;
+  a.residual = op.res >= 0 ? (const uint8_t*)e->tens[op.res].ptr + out_off * 2 : nullptr;
+  a.out = (uint8_t*)ot.ptr + out_off * (ot.dtype ? 4 : 2);
   a.out_f32 = ot.dtype;
   ProfScope ps(e, PC_CONV_SIMT, oi);
   vsb::launch_conv_simt(a, e->stream);
@@ -806,48 +814,84 @@ int run_conv(vsb_engine* e, int oi, int nb) {
   return VSB_OK;
 }
 
-// Runs every op except HEAD on tensor 0 (already filled).  Returns the index of
-// the HEAD op through *head_idx (or -1).
+// Runs one op (not HEAD) on images [n0, n0 + nb) of the batch.
+int run_op(vsb_engine* e, int i, int n0, int nb) {
+  const vsb_op& op = e->ops[i];
+  switch (op.kind) {
+    case VSB_OP_CONV:
+      return run_conv(e, i, n0, nb);
+    case VSB_OP_MAXPOOL: {
+      const TensorBuf& s = e->tens[op.src[0]];
+      const TensorBuf& o = e->tens[op.out];
+      ProfScope ps(e, PC_POOL, i);
+      vsb::launch_maxpool3x3s2((const uint16_t*)s.ptr + (size_t)n0 * s.H * s.W * s.C, nb, s.H, s.W, s.C,
+                               (uint16_t*)o.ptr + (size_t)n0 * o.H * o.W * o.C, e->stream);
+      CK(cudaGetLastError());
+      return VSB_OK;
+    }
+    case VSB_OP_GAP: {
+      const TensorBuf& s = e->tens[op.src[0]];
+      const TensorBuf& o = e->tens[op.out];
+      ProfScope ps(e, PC_OTHER);
+      vsb::launch_gap((const uint16_t*)s.ptr + (size_t)n0 * s.H * s.W * s.C, nb, s.H, s.W, s.C,
+                      (uint16_t*)o.ptr + (size_t)n0 * o.C, e->stream);
+      CK(cudaGetLastError());
+      return VSB_OK;
+    }
+    case VSB_OP_UPSAMPLE: {
+      const TensorBuf& s = e->tens[op.src[0]];
+      const TensorBuf& o = e->tens[op.out];
+      ProfScope ps(e, PC_OTHER);
+      vsb::launch_upsample((const uint16_t*)s.ptr + (size_t)n0 * s.H * s.W * s.C, nb, s.H, s.W, s.C, o.H, o.W,
+                           op.mode, (uint16_t*)o.ptr + (size_t)n0 * o.H * o.W * o.C, e->stream);
+      CK(cudaGetLastError());
+      return VSB_OK;
+    }
+    default:
+      return fail(VSB_ERR_INVALID, "unknown op kind %d", op.kind);
+  }
+}
+
+// Runs every op except HEAD on tensor 0 (already filled).  Returns the index of the
+// HEAD op through *head_idx (or -1).
+// Ops are grouped into segments of "shallow" (output at >= 1/4 resolution) and "deep"
+// ops.  Deep segments run on the whole batch (they need many images to fill 148 SMs);
+// shallow segments run depth-first over sub-batches small enough that the tensors a
+// layer hands to the next one stay in the 126 MB L2 instead of streaming through HBM.
 int run_network(vsb_engine* e, int nb, int* head_idx) {
   *head_idx = -1;
-  for (int i = 0; i < (int)e->ops.size(); ++i) {
+  const int n_ops = (int)e->ops.size();
+  auto shallow = [&](int i) {
     const vsb_op& op = e->ops[i];
-    switch (op.kind) {
-      case VSB_OP_CONV: {
-        int rc = run_conv(e, i, nb);
-        if (rc) return rc;
-        break;
-      }
-      case VSB_OP_MAXPOOL: {
-        const TensorBuf& s = e->tens[op.src[0]];
-        ProfScope ps(e, PC_POOL, i);
-        vsb::launch_maxpool3x3s2((const uint16_t*)s.ptr, nb, s.H, s.W, s.C, (uint16_t*)e->tens[op.out].ptr,
-                                 e->stream);
-        CK(cudaGetLastError());
-        break;
-      }
-      case VSB_OP_GAP: {
-        const TensorBuf& s = e->tens[op.src[0]];
-        ProfScope ps(e, PC_OTHER);
-        vsb::launch_gap((const uint16_t*)s.ptr, nb, s.H, s.W, s.C, (uint16_t*)e->tens[op.out].ptr, e->stream);
-        CK(cudaGetLastError());
-        break;
-      }
-      case VSB_OP_UPSAMPLE: {
-        const TensorBuf& s = e->tens[op.src[0]];
-        const TensorBuf& o = e->tens[op.out];
-        ProfScope ps(e, PC_OTHER);
-        vsb::launch_upsample((const uint16_t*)s.ptr, nb, s.H, s.W, s.C, o.H, o.W, op.mode, (uint16_t*)o.ptr,
-                             e->stream);
-        CK(cudaGetLastError());
-        break;
-      }
-      case VSB_OP_HEAD:
-        *head_idx = i;
-        break;
-      default:
-        return fail(VSB_ERR_INVALID, "unknown op kind %d", op.kind);
+    if (op.kind == VSB_OP_HEAD || op.out < 0) return false;
+    const int ds = e->tdesc[op.out].ds_log2;
+    return ds >= 0 && ds <= 2;
+  };
+  int i = 0;
+  while (i < n_ops) {
+    if (e->ops[i].kind == VSB_OP_HEAD) {
+      *head_idx = i++;
+      continue;
     }
+    const bool sh = shallow(i);
+    int j = i;
+    size_t max_bytes = 1;
+    while (j < n_ops && e->ops[j].kind != VSB_OP_HEAD && shallow(j) == sh) {
+      const TensorBuf& o = e->tens[e->ops[j].out];
+      max_bytes = std::max(max_bytes, (size_t)o.H * o.W * o.C * (o.dtype ? 4 : 2));
+      ++j;
+    }
+    int sub = nb;
+    if (sh && e->sub_batch_mb > 0)
+      sub = (int)std::max<size_t>(1, std::min<size_t>(nb, ((size_t)e->sub_batch_mb << 20) / max_bytes));
+    for (int n0 = 0; n0 < nb; n0 += sub) {
+      const int cnt = std::min(sub, nb - n0);
+      for (int k = i; k < j; ++k) {
+        int rc = run_op(e, k, n0, cnt);
+        if (rc) return rc;
+      }
+    }
+    i = j;
   }
   return VSB_OK;
 }
@@ -950,6 +994,7 @@ int vsb_create(int device, vsb_engine** out) {
   CK(vsb::conv_tc_configure());
   CK(vsb::conv_halo_configure());
   e->no_halo = getenv("VSB_NO_HALO") != nullptr;
+  if (const char* sb = getenv("VSB_SUB_BATCH_MB")) e->sub_batch_mb = atoi(sb);
   *out = e;
   return VSB_OK;
 }

@@ -91,17 +91,32 @@ class Engine:
     def synchronize(self) -> None:
         _lib.check(self.lib.vsb_synchronize(self.h))
 
-    @staticmethod
-    def _host_buffer(shape, dtype) -> np.ndarray:
+    def _host_buffer(self, shape, dtype) -> np.ndarray:
         """Page-locked host array (torch is the allocator; plumbing only) so the
-        result download runs at PCIe rate instead of through a bounce buffer."""
+        result download runs at PCIe rate instead of through a bounce buffer.
+        Pinning gigabytes costs more than the copy, so blocks are pooled: a block is
+        handed out again only once the ndarray previously returned to the caller has
+        been garbage-collected (results never alias a live array)."""
+        import weakref
+
         import torch
 
         tdt = {np.uint8: torch.uint8, np.float16: torch.float16}[dtype]
+        pool = self.__dict__.setdefault("_pinned_pool", [])
+        for entry in pool:
+            tensor, ref = entry
+            if tensor.dtype == tdt and tuple(tensor.shape) == tuple(shape) and ref() is None:
+                arr = tensor.numpy()
+                entry[1] = weakref.ref(arr)
+                return arr
         try:
-            return torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
+            tensor = torch.empty(shape, dtype=tdt, pin_memory=True)
         except RuntimeError:
             return np.empty(shape, dtype)
+        arr = tensor.numpy()
+        pool.append([tensor, weakref.ref(arr)])
+        del pool[:-6]  # bound the pool
+        return arr
 
     def fetch(self, want_probs: bool = True):
         z, y, x = self.shape
