@@ -57,38 +57,58 @@ __device__ __forceinline__ void store8(const EpiOut& p, const float (&f)[8], int
 }
 
 
-// 8 accumulator columns of one pixel (channels ch..ch+7): + bias, + residual, ReLU, store.
-__device__ __forceinline__ void epilogue_group8(const EpiOut& p, const uint32_t* v8, const float* bias_s,
-                                                int64_t pix, int ch, const uint4* res_pre = nullptr) {
+// Generic (slow-path) 8-channel group: f32 output, partial groups, odd channel counts.
+// Kept out of line so the hot epilogue loop stays small (the fully inlined version
+// suffered instruction-cache misses -- ncu "no_inst" stalls).
+// Values are passed in registers (not by pointer) so the caller's accumulator array is
+// never forced into local memory.
+static __device__ __noinline__ void epilogue_group8_generic(EpiOut p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                     uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7,
+                                                     const float* bias_s, int64_t pix, int ch) {
   if (ch >= p.cout) return;
+  const uint32_t v8[8] = {a0, a1, a2, a3, a4, a5, a6, a7};
   float f[8];
-  const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch);
-  const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch + 4);
-  f[0] = __uint_as_float(v8[0]) + b0.x;
-  f[1] = __uint_as_float(v8[1]) + b0.y;
-  f[2] = __uint_as_float(v8[2]) + b0.z;
-  f[3] = __uint_as_float(v8[3]) + b0.w;
-  f[4] = __uint_as_float(v8[4]) + b1.x;
-  f[5] = __uint_as_float(v8[5]) + b1.y;
-  f[6] = __uint_as_float(v8[6]) + b1.z;
-  f[7] = __uint_as_float(v8[7]) + b1.w;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v8[j]) + bias_s[ch + j];
   const bool full8 = ch + 8 <= p.cout;
   if (p.residual) {
-    if (full8) {
-      const uint4 rv = res_pre ? *res_pre : __ldg(reinterpret_cast<const uint4*>(p.residual + pix * p.cout + ch));
-      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 rf = unpack_act2(rw[j]);
-        f[2 * j] += rf.x;
-        f[2 * j + 1] += rf.y;
-      }
-    } else {
-      for (int j = 0; j < 8 && ch + j < p.cout; ++j) f[j] += act_to_float(p.residual[pix * p.cout + ch + j]);
-    }
+    for (int j = 0; j < 8 && ch + j < p.cout; ++j) f[j] += act_to_float(p.residual[pix * p.cout + ch + j]);
   }
   if (p.relu) store8<true>(p, f, pix, ch, full8);
   else store8<false>(p, f, pix, ch, full8);
+}
+
+// 8 accumulator columns of one pixel (channels ch..ch+7): + bias, + residual, ReLU, store.
+// Fast path: 16-bit output, cout % 8 == 0 (whole group in range).
+__device__ __forceinline__ void epilogue_group8(const EpiOut& p, const uint32_t* v8, const float* bias_s,
+                                                int64_t pix, int ch, const uint4* res_pre = nullptr) {
+  if (p.out_f32 || (p.cout & 7)) {
+    epilogue_group8_generic(p, v8[0], v8[1], v8[2], v8[3], v8[4], v8[5], v8[6], v8[7], bias_s, pix, ch);
+    return;
+  }
+  if (ch >= p.cout) return;
+  const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch);
+  const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch + 4);
+  float f0 = __uint_as_float(v8[0]) + b0.x, f1 = __uint_as_float(v8[1]) + b0.y;
+  float f2 = __uint_as_float(v8[2]) + b0.z, f3 = __uint_as_float(v8[3]) + b0.w;
+  float f4 = __uint_as_float(v8[4]) + b1.x, f5 = __uint_as_float(v8[5]) + b1.y;
+  float f6 = __uint_as_float(v8[6]) + b1.z, f7 = __uint_as_float(v8[7]) + b1.w;
+  const int64_t off = pix * p.cout + ch;
+  if (p.residual) {
+    const uint4 rv = res_pre ? *res_pre : __ldg(reinterpret_cast<const uint4*>(p.residual + off));
+    float2 r;
+    r = unpack_act2(rv.x); f0 += r.x; f1 += r.y;
+    r = unpack_act2(rv.y); f2 += r.x; f3 += r.y;
+    r = unpack_act2(rv.z); f4 += r.x; f5 += r.y;
+    r = unpack_act2(rv.w); f6 += r.x; f7 += r.y;
+  }
+  uint4 pk;
+  if (p.relu) {
+    pk.x = pack2<true>(f0, f1); pk.y = pack2<true>(f2, f3); pk.z = pack2<true>(f4, f5); pk.w = pack2<true>(f6, f7);
+  } else {
+    pk.x = pack2<false>(f0, f1); pk.y = pack2<false>(f2, f3); pk.z = pack2<false>(f4, f5); pk.w = pack2<false>(f6, f7);
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + off) = pk;
 }
 
 // 32 accumulator columns [c, c+32) of one pixel.

@@ -379,6 +379,18 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
     const int depth = p.a_stages / 2 > 1 ? p.a_stages / 2 : 1;
     int inflight = 0, oldest = 0;
     const uint32_t ring_addr = smem_u32(a_ring);
+    // Per-thread copy table: which halo pixel / 16-byte chunk this thread fetches in its
+    // it-th copy of every stage, and where it lands (identical for every stage and slab).
+    constexpr int CH8 = KC / 8;  // 16-byte chunks per pixel
+    constexpr int NITER = MODE == 0 ? (HW * HH * CH8 + 32 * HALO2_LOAD_WARPS - 1) / (32 * HALO2_LOAD_WARPS) : 1;
+    uint32_t ltab[NITER];
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) {
+      const int idx = it * 32 * HALO2_LOAD_WARPS + ptid;
+      const int j = idx % CH8, pix = idx / CH8;
+      const int hy = pix / HW, hx = pix - hy * HW;
+      ltab[it] = ((swz<P>((uint32_t)(pix * P + j * 16)) >> 4) << 16) | ((uint32_t)hy << 10) | ((uint32_t)hx << 4) | (uint32_t)j;
+    }
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n_tile, X0, Y0, n;
       decode(t, n_tile, X0, Y0, n);
@@ -420,19 +432,21 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
       for (int s = 0; s < p.nslabs; ++s) {
         const HaloSrc& sv = p.src[p.slab_src[s]];
         const int c0 = p.slab_c0[s];
-        constexpr int CH8 = KC / 8;  // 16-byte chunks per pixel
         mbar_wait(&ctl->a_empty[as], aph ^ 1);
         const uint32_t stage_addr = ring_addr + (uint32_t)as * p.a_stage_bytes;
         const uint16_t* img = sv.ptr + (int64_t)n * sv.Hs * sv.Ws * sv.C + c0;
-        for (int idx = ptid; idx < HW * HH * CH8; idx += 32 * HALO2_LOAD_WARPS) {
-          const int j = idx % CH8;
-          const int pix = idx / CH8;
-          const int hy = pix / HW, hx = pix - hy * HW;
-          const int y = Y0 - 1 + hy, x = X0 - 1 + hx;
-          const bool ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
-          const int sy = sv.up ? y >> 1 : y, sx = sv.up ? x >> 1 : x;
-          const uint16_t* g = img + ((int64_t)sy * sv.Ws + sx) * sv.C + j * 8;
-          cp_async_16(stage_addr + swz<P>((uint32_t)(pix * P + j * 16)), ok ? g : sv.ptr, ok ? 16u : 0u);
+        const int up = sv.up;
+        const uint32_t row_elems = (uint32_t)sv.Ws * sv.C, px_elems = (uint32_t)sv.C;
+#pragma unroll
+        for (int it = 0; it < NITER; ++it) {
+          const uint32_t e = ltab[it];  // [31:16] swizzled smem offset / 16, [15:10] hy, [9:4] hx, [3:0] chunk j
+          if (it * 32 * HALO2_LOAD_WARPS + ptid < HW * HH * CH8) {
+            const int y = Y0 - 1 + (int)((e >> 10) & 63), x = X0 - 1 + (int)((e >> 4) & 63);
+            const bool ok = (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W;
+            const uint32_t sy = (uint32_t)(up ? y >> 1 : y), sx = (uint32_t)(up ? x >> 1 : x);
+            const uint16_t* g = img + (sy * row_elems + sx * px_elems + (e & 15) * 8);
+            cp_async_16(stage_addr + ((e >> 16) << 4), ok ? g : sv.ptr, ok ? 16u : 0u);
+          }
         }
         cp_async_commit();
         if (++inflight > depth) {
@@ -578,6 +592,7 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
     const int xi = row & 7, yi = row >> 3;
     const EpiOut eo{p.out, p.residual, p.out_f32, p.relu, p.cout};
     const int ncols = MT * p.BN;
+    const int bn_log2 = 31 - __clz(p.BN);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n_tile, X0, Y0, n;
       decode(t, n_tile, X0, Y0, n);
@@ -596,8 +611,9 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
           for (int g8 = 0; g8 < 4; ++g8) {
             const int col = c + g8 * 8;
             if (col >= ncols) break;
-            const int mt = MT == 1 ? 0 : col / p.BN;
-            const int ch = MT == 1 ? col : col - mt * p.BN;
+            // BN is a power of two whenever MT > 1 (MT <= 256 / BN is only granted then)
+            const int mt = MT == 1 ? 0 : col >> bn_log2;
+            const int ch = MT == 1 ? col : col & (p.BN - 1);
             const int ox = X0 + mt * 8 + xi;
             if (ox < p.W) epilogue_group8(eo, &v[g8 * 8], bias_s, rowpix + ox, ch0 + ch);
           }

@@ -602,6 +602,7 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
       const int P = 2 * h.kc;
       int mt = std::min(h.kc == 64 ? 2 : 4, std::max(1, 256 / cp.BN));
       mt = mt >= 4 ? 4 : (mt >= 2 ? 2 : 1);
+      if (cp.BN & (cp.BN - 1)) mt = 1;  // the epilogue maps column -> (tile, channel) with shifts
       int tx = 0, ty = (ot.H + 15) / 16;
       double eff = 0;
       for (;; mt /= 2) {
