@@ -162,6 +162,11 @@ int vsb_set_batch(vsb_engine* e, int32_t slices_per_batch);
  * 1: CUDA-core convolutions everywhere (bring-up / cross-check);
  * 2: as 1 but also without the dedicated 7x7 stem kernel.                   */
 int vsb_set_conv_impl(vsb_engine* e, int32_t impl);
+/* Tuning / cross-check switches: "halo" (1: halo-tile conv kernels, default),
+ * "fuse_head" (1: softmax/argmax/merge inside the last conv's epilogue; default 0:
+ *   bit-identical, but measured slower than the separate head kernel),
+ * "sub_batch_mb" (L2 budget for depth-first sub-batches, 0 = off, default).      */
+int vsb_set_flag(vsb_engine* e, const char* name, int32_t value);
 
 /* ---- test hooks (bit-exact criteria of BASELINE.json) ---------------------
  * Slicer only: padded+normalised bf16 images [nb, Hp, Wp] of direction d,

@@ -169,6 +169,27 @@ def test_skip_duplicates_is_result_identical(engine, unet_r34, golden):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
+def test_kernel_variants_agree(engine, unet_r34, golden):
+    """Fused head == separate head kernel bit for bit (same logits, same arithmetic);
+    halo kernels vs per-tap TMA kernel vs CUDA-core kernel agree to accumulation order."""
+    _, model = unet_r34
+    engine.load_model(model)
+    engine.set_volume(golden["volume"])
+    results = {}
+    for name, flags in {"default": {}, "fused": {"fuse_head": 1}, "pertap": {"halo": 0}}.items():
+        for k, v in flags.items():
+            engine.set_flag(k, v)
+        engine.reset()
+        engine.predict(0b111, True)
+        results[name] = engine.fetch()
+        for k in flags:
+            engine.set_flag(k, {"fuse_head": 0, "halo": 1}[k])
+    assert np.array_equal(results["default"][0], results["fused"][0])
+    assert np.array_equal(results["default"][1], results["fused"][1])
+    dp = np.abs(results["default"][1].astype(np.float32) - results["pertap"][1].astype(np.float32)).max()
+    assert dp < 2e-3 and (results["default"][0] == results["pertap"][0]).mean() > 0.99
+
+
 def test_non_uint8_volumes_are_refused_loudly(predictor):
     with pytest.raises(NotImplementedError):
         predictor._predict_single_axis(np.random.rand(8, 32, 32))

@@ -89,6 +89,7 @@ SIGNATURES = {
     "vsb_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64), C.c_int32]),
     "vsb_set_batch": (C.c_int, [_P, C.c_int32]),
     "vsb_set_conv_impl": (C.c_int, [_P, C.c_int32]),
+    "vsb_set_flag": (C.c_int, [_P, C.c_char_p, C.c_int32]),
     "vsb_slice_batch": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int32, _P]),
     "vsb_merge_injected": (C.c_int, [_P, C.c_int32, _P, _P]),
     "vsb_forward_logits": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),

@@ -6,6 +6,7 @@
 #include "conv_halo.cuh"
 
 #include "conv_epilogue.cuh"
+#include "kernels.h"
 
 namespace vsb {
 
@@ -286,6 +287,41 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 //         one tap of four K-steps is issued per tile (KC = 64, MT = 1).
 // =====================================================================================
 namespace {
+// logits (accumulator columns 0..C-1 + bias) of one padded pixel -> merged key.
+// Arithmetic identical to head_kernel (kernels_simple.cu), so fused and unfused paths
+// produce the same keys.
+__device__ __forceinline__ void head_fused_pixel(const HeadFuse& hf, const uint32_t* v8, const float* bias_s,
+                                                 int n, int oy, int ox) {
+  const int r = oy - hf.crop_top, c = ox - hf.crop_left;
+  if ((unsigned)r >= (unsigned)hf.Hc || (unsigned)c >= (unsigned)hf.Wc) return;
+  float l[8];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    l[k] = k < hf.C ? __uint_as_float(v8[k]) + bias_s[k] : -INFINITY;
+    m = fmaxf(m, l[k]);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    l[k] = k < hf.C ? expf(l[k] - m) : 0.f;
+    sum += l[k];
+  }
+  float best = -1.f;
+  int lab = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float pk = __fdiv_rn(l[k], sum);
+    if (k < hf.C && pk > best) {
+      best = pk;
+      lab = k;
+    }
+  }
+  const int64_t vox = hf.base + (hf.s0 + n) * hf.stride_s + (int64_t)r * hf.stride_r + (int64_t)c * hf.stride_c;
+  const uint16_t h = __half_as_ushort(__float2half_rn(best));
+  atomicMax(hf.keys + vox, pack_key(h, hf.d, (uint32_t)lab, __float_as_uint(best)));
+}
+
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -615,7 +651,13 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
             const int mt = MT == 1 ? 0 : col >> bn_log2;
             const int ch = MT == 1 ? col : col & (p.BN - 1);
             const int ox = X0 + mt * 8 + xi;
-            if (ox < p.W) epilogue_group8(eo, &v[g8 * 8], bias_s, rowpix + ox, ch0 + ch);
+            if (ox < p.W) {
+              if (p.head.on) {
+                if (ch == 0) head_fused_pixel(p.head, &v[g8 * 8], bias_s, n - p.n_base, oy, ox);
+              } else {
+                epilogue_group8(eo, &v[g8 * 8], bias_s, rowpix + ox, ch0 + ch);
+              }
+            }
           }
         }
       }

@@ -53,6 +53,17 @@ struct HaloSrc {
   const uint16_t* ptr;  // NHWC
   int32_t C, Hs, Ws, up;
 };
+// Fused head (north-star kernel (c)): when the convolution is the segmentation head, the
+// epilogue turns the C logits of a pixel straight into softmax -> first-max label ->
+// fp16 p_max -> centre crop -> inverse rotation -> packed-key atomicMax, instead of
+// storing logits for a separate kernel (vol_seg_2d_predictor.py:45-64, 90-98).
+struct HeadFuse {
+  int32_t on, C, d;
+  int32_t Hc, Wc, crop_top, crop_left;  // cropped image size and torchvision crop offsets
+  int64_t s0;                           // slice index of image 0 of the batch
+  int64_t base, stride_s, stride_r, stride_c;
+  unsigned long long* keys;
+};
 constexpr int HALO2_MAX_SLABS = 64;
 struct ConvHalo2Params {
   HaloSrc src[6];
@@ -73,6 +84,7 @@ struct ConvHalo2Params {
   int32_t tiles_x, tiles_y;
   int32_t a_stages, a_stage_bytes;
   int32_t b_stages, b_bytes;
+  HeadFuse head;
 };
 constexpr int HALO2_LOAD_WARPS = 4;
 constexpr int HALO2_THREADS = 32 * (HALO2_LOAD_WARPS + 2 + 8);

@@ -141,6 +141,9 @@ struct vsb_engine {
   int batch_override = 0;
   int conv_impl = 0;
   bool no_halo = false;
+  bool no_fuse_head = true;   // fused head is bit-identical but measured slower (epilogue-bound); opt-in via vsb_set_flag
+  int fuse_op = -1;            // conv op whose epilogue performs the head (set per predict_range batch)
+  vsb::HeadFuse fuse{};
   int sub_batch_mb = 0;  // L2 budget (MB) per tensor for depth-first sub-batches; 0 = off (measured slower: per-launch prologue dominates)
   bool profiling = false;
   std::vector<float> op_ms;
@@ -767,7 +770,11 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
     vsb::ConvHalo2Params h = cp.h2params;
     h.NB = nb;
     h.n_base = n0;
-    ProfScope ps(e, PC_CONV_TC, oi);
+    if (e->fuse_op == oi) {
+      h.head = e->fuse;
+      h.head.s0 += n0;
+    }
+    ProfScope ps(e, e->fuse_op == oi ? PC_HEAD : PC_CONV_TC, oi);
     CK(vsb::launch_conv_halo2(h, e->num_sms, e->stream));
     return VSB_OK;
   }
@@ -929,10 +936,44 @@ int predict_range(vsb_engine* e, int d, int64_t s_begin, int64_t s_end) {
       vsb::launch_slicer(e->d_vol, g, s0, nb, (uint16_t*)e->tens[0].ptr, e->stream);
       CK(cudaGetLastError());
     }
+    // fused head: the conv that produces the logits merges them in its own epilogue
+    e->fuse_op = -1;
+    {
+      int hidx = -1;
+      for (int i = 0; i < (int)e->ops.size(); ++i)
+        if (e->ops[i].kind == VSB_OP_HEAD) hidx = i;
+      if (hidx >= 0 && !e->vote_mode && !e->no_fuse_head && !e->no_halo && e->conv_impl == 0 &&
+          e->num_classes <= 8 && (e->ops[hidx].factor <= 1)) {
+        const int lt = e->ops[hidx].src[0];
+        for (int i = 0; i < hidx; ++i)
+          if (e->ops[i].kind == VSB_OP_CONV && e->ops[i].out == lt && e->conv[i].tc && e->conv[i].use_halo2 &&
+              e->conv[i].n_tiles == 1 && e->conv[i].BN >= 8 && (e->conv[i].BN & (e->conv[i].BN - 1)) == 0)
+            e->fuse_op = i;
+      }
+      if (e->fuse_op >= 0) {
+        vsb::HeadFuse& f = e->fuse;
+        f.on = 1;
+        f.C = e->num_classes;
+        f.d = d;
+        f.Hc = (int)g.H;
+        f.Wc = (int)g.W;
+        f.crop_top = (int)g.crop_top;
+        f.crop_left = (int)g.crop_left;
+        f.s0 = s0;
+        f.base = g.base;
+        f.stride_s = g.stride_s;
+        f.stride_r = g.stride_r;
+        f.stride_c = g.stride_c;
+        f.keys = e->d_keys;
+      }
+    }
     int head = -1;
     rc = run_network(e, nb, &head);
+    const bool fused = e->fuse_op >= 0;
+    e->fuse_op = -1;
     if (rc) return rc;
     if (head < 0) return fail(VSB_ERR_INVALID, "plan has no HEAD op");
+    if (fused) continue;
     const vsb_op& hop = e->ops[head];
     vsb::HeadArgs h{};
     h.logits = (const float*)e->tens[hop.src[0]].ptr;
@@ -995,6 +1036,7 @@ int vsb_create(int device, vsb_engine** out) {
   CK(vsb::conv_tc_configure());
   CK(vsb::conv_halo_configure());
   e->no_halo = getenv("VSB_NO_HALO") != nullptr;
+  if (getenv("VSB_FUSE_HEAD")) e->no_fuse_head = false;
   if (const char* sb = getenv("VSB_SUB_BATCH_MB")) e->sub_batch_mb = atoi(sb);
   *out = e;
   return VSB_OK;
@@ -1238,6 +1280,18 @@ int vsb_launch_count(vsb_engine* e, int64_t* count, int32_t reset) {
 int vsb_set_batch(vsb_engine* e, int32_t n) {
   if (!e || n < 0 || n > 1024) return fail(VSB_ERR_INVALID, "bad batch");
   e->batch_override = n;
+  return VSB_OK;
+}
+
+int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
+  if (!e || !name) return fail(VSB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  const std::string n(name);
+  if (n == "halo") e->no_halo = value == 0;
+  else if (n == "fuse_head") e->no_fuse_head = value == 0;
+  else if (n == "sub_batch_mb") e->sub_batch_mb = value;
+  else return fail(VSB_ERR_INVALID, "unknown flag '%s'", name);
   return VSB_OK;
 }
 

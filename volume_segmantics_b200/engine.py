@@ -160,6 +160,9 @@ class Engine:
     def set_conv_impl(self, impl: str) -> None:
         _lib.check(self.lib.vsb_set_conv_impl(self.h, {"tc": 0, "simt": 1, "generic": 2}[impl]))
 
+    def set_flag(self, name: str, value: int) -> None:
+        _lib.check(self.lib.vsb_set_flag(self.h, name.encode(), int(value)))
+
     # -- test hooks ---------------------------------------------------------------
     def geometry(self, d: int) -> _lib.Direction:
         z, y, x = self.shape
