@@ -97,7 +97,9 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     }
     fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < p.n_tiles * p.BN; i += HALO_THREADS) bias_s[i] = p.bias[i];
+  // bias_s is indexed by absolute output channel; this launch covers [cout_off, cout_off + n_tiles*BN)
+  bias_s -= p.cout_off;
+  for (int i = threadIdx.x; i < p.n_tiles * p.BN; i += HALO_THREADS) bias_s[p.cout_off + i] = p.bias[p.cout_off + i];
   if (warp == 1) tmem_alloc<512>(&ctl->tmem_base);
   tc_fence_before_sync();
   __syncthreads();
@@ -116,7 +118,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         mbar_wait(&ctl->a_empty[as], aph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&ctl->a_full[as], a_box_bytes);
-          tma_load_5d(p.map, &ctl->a_full[as], a_ring + (size_t)as * p.a_stage_bytes, cs * 64, X0 - p.dil, 0,
+          tma_load_5d(p.map, &ctl->a_full[as], a_ring + (size_t)as * p.a_stage_bytes, p.cin_off + cs * 64, X0 - p.dil, 0,
                       Y0 - p.dil, n);
         }
         __syncwarp();
@@ -237,7 +239,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       const int ox = X0 + xi, oy = Y0 + yi;
       const bool valid = ox < p.W && oy < p.H;
       const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
-      const int ch0 = n_tile * p.BN;
+      const int ch0 = p.cout_off + n_tile * p.BN;
       uint4 rpre0[4], rpre1[4];
       bool have0 = false, have1 = false;
       if (valid) {

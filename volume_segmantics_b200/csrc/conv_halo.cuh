@@ -30,7 +30,8 @@ struct ConvHaloParams {
   int32_t BN, n_tiles;
   int32_t NB, H, W;
   int32_t n_base;            // first image of this launch
-  int32_t ncs;               // Cin / 64
+  int32_t cin_off, cout_off; // channel window of this launch (grouped conv = one 64-channel block per launch)
+  int32_t ncs;               // input channels of the launch / 64
   int32_t dil;
   int32_t tiles_x, tiles_y;
   int32_t a_stages, a_stage_bytes;

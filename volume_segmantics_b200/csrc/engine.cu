@@ -92,6 +92,9 @@ struct ConvPlan {
   bool use_halo = false;  // decided per workspace (tile efficiency)
   uint8_t* d_whalo = nullptr;
   vsb::ConvHaloParams hparams{};
+  bool depthwise = false;     // groups == cin == cout, 3x3 stride 1: vectorised depthwise kernel, weights [9][C]
+  bool grouped_halo = false;  // groups > 1, 3x3 stride 1: one resident-weight halo launch per 64-channel block
+  int n_blocks = 0;
   bool stem_tc = false;   // 7x7/2 single-channel stem on tensor cores (halo2 kernel, MODE 1)
   bool halo2_ok = false, use_halo2 = false;  // cp.async-assembled halo (concat / up-sampled / narrow sources)
   vsb::ConvHalo2Params h2params{};
@@ -249,6 +252,60 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
     CK(cudaMalloc(&cp.d_bias_pad, cp.BN * 4));
     CK(cudaMemcpy(cp.d_bias_pad, bias.data(), cp.BN * 4, cudaMemcpyHostToDevice));
     cp.stem_tc = true;
+    return VSB_OK;
+  }
+  cp.depthwise = false;
+  if (op.kind == VSB_OP_CONV && op.groups == op.cin && op.cin == op.cout && op.kh == 3 && op.kw == 3 &&
+      op.stride == 1 && op.pad == op.dil && op.res < 0 && e->tdesc[op.out].dtype == 0) {
+    bool ok = true;
+    for (int s = 0; s < op.n_src; ++s)
+      ok &= e->tdesc[op.src[s]].channels % 8 == 0 && !op.src_up[s] && e->tdesc[op.src[s]].dtype == 0;
+    if (ok) {
+      std::vector<uint16_t> w((size_t)9 * op.cout);
+      for (int c = 0; c < op.cout; ++c)
+        for (int tap = 0; tap < 9; ++tap)
+          memcpy(&w[(size_t)tap * op.cout + c], e->h_weights.data() + op.w_off + ((int64_t)c * 9 + tap) * 2, 2);
+      CK(cudaMalloc(&cp.d_whalo, w.size() * 2));
+      CK(cudaMemcpy(cp.d_whalo, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+      cp.depthwise = true;
+      return VSB_OK;
+    }
+  }
+  cp.grouped_halo = false;
+  if (op.kind == VSB_OP_CONV && op.groups > 1 && op.n_src == 1 && !op.src_up[0] && op.kh == 3 && op.kw == 3 &&
+      op.stride == 1 && op.pad == op.dil && (op.dil == 1 || op.dil == 2) && op.cin == op.cout && op.cin % 64 == 0 &&
+      64 % (op.cin / op.groups) == 0 && e->tdesc[op.src[0]].dtype == 0 && e->tdesc[op.out].dtype == 0 &&
+      e->tdesc[op.out].ds_log2 >= 0) {
+    // Block-diagonal packing: the 64 output channels of block b only see the 64 input
+    // channels of block b (groups never straddle a block); cross-group weights are zero.
+    const int cg = op.cin / op.groups;
+    cp.n_blocks = op.cin / 64;
+    cp.BN = 64;
+    cp.n_tiles = 1;
+    const size_t img = 64 * 128;
+    std::vector<uint8_t> hp((size_t)cp.n_blocks * 9 * img, 0);
+    for (int b = 0; b < cp.n_blocks; ++b)
+      for (int tap = 0; tap < 9; ++tap) {
+        uint8_t* dst = hp.data() + ((size_t)b * 9 + tap) * img;
+        for (int n = 0; n < 64; ++n) {
+          const int o = b * 64 + n;
+          const int g0 = (o / cg) * cg - b * 64;  // first input channel (block-local) of o's group
+          for (int j = 0; j < cg; ++j) {
+            const int k = g0 + j;  // block-local input channel
+            uint32_t off = (uint32_t)(n * 128 + k * 2);
+            off ^= ((off >> 7) & 7u) << 4;
+            memcpy(dst + off, e->h_weights.data() + op.w_off + ((((int64_t)o * 3 + tap / 3) * 3 + tap % 3) * cg + j) * 2, 2);
+          }
+        }
+      }
+    CK(cudaMalloc(&cp.d_whalo, hp.size()));
+    CK(cudaMemcpy(cp.d_whalo, hp.data(), hp.size(), cudaMemcpyHostToDevice));
+    std::vector<float> bias(op.cout, 0.f);
+    if (op.b_off >= 0) memcpy(bias.data(), e->h_weights.data() + op.b_off, (size_t)op.cout * 4);
+    CK(cudaMalloc(&cp.d_bias_pad, op.cout * 4));
+    CK(cudaMemcpy(cp.d_bias_pad, bias.data(), op.cout * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * VSB_MAX_SRC));
+    cp.grouped_halo = true;
     return VSB_OK;
   }
   if (!cp.tc) return VSB_OK;
@@ -549,6 +606,45 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
       h.b_bytes = cp.BN * 128;
       continue;
     }
+    if (cp.grouped_halo) {
+      const vsb_op& op = e->ops[i];
+      const TensorBuf& ot = e->tens[op.out];
+      const TensorBuf& st = e->tens[op.src[0]];
+      const int tx = (ot.W + 7) / 8, ty = (ot.H + 15) / 16;
+      const double eff = (double)ot.W * ot.H / ((double)tx * 8 * ty * 16);
+      cp.use_halo = false;
+      if (eff >= 0.5) {
+        vsb::ConvHaloParams& h = cp.hparams;
+        h = vsb::ConvHaloParams{};
+        const int HW = 8 + 2 * op.dil, HH = 16 + 2 * op.dil;
+        TmaDesc hm;
+        int rc = make_tensor_map(e, &hm, st, nb, false, 64, HW, HH, 1);
+        if (rc) return rc;
+        CK(cudaMemcpy(cp.d_maps, &hm, sizeof(hm), cudaMemcpyHostToDevice));
+        h.map = cp.d_maps;
+        h.bias = cp.d_bias_pad;
+        h.residual = op.res >= 0 ? (const uint16_t*)e->tens[op.res].ptr : nullptr;
+        h.out = ot.ptr;
+        h.out_f32 = 0;
+        h.relu = op.relu;
+        h.cout = op.cout;
+        h.BN = 64;
+        h.n_tiles = 1;
+        h.NB = nb;
+        h.H = ot.H;
+        h.W = ot.W;
+        h.ncs = 1;
+        h.dil = op.dil;
+        h.tiles_x = tx;
+        h.tiles_y = ty;
+        h.b_bytes = 64 * 128;
+        h.b_stages = 0;
+        h.a_stage_bytes = (int)align_up((size_t)HW * HH * 128, 1024);
+        h.a_stages = 4;
+        cp.use_halo = true;
+      }
+      continue;
+    }
     if (!cp.tc) continue;
     const vsb_op& op = e->ops[i];
     const TensorBuf& ot = e->tens[op.out];
@@ -766,6 +862,19 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
     CK(vsb::launch_conv_halo2(h, e->num_sms, e->stream));
     return VSB_OK;
   }
+  if (cp.grouped_halo && cp.use_halo && e->conv_impl == 0 && !e->no_halo) {
+    for (int b = 0; b < cp.n_blocks; ++b) {
+      vsb::ConvHaloParams h = cp.hparams;
+      h.NB = nb;
+      h.n_base = n0;
+      h.cin_off = b * 64;
+      h.cout_off = b * 64;
+      h.wpacked = cp.d_whalo + (size_t)b * 9 * 64 * 128;
+      ProfScope ps(e, PC_CONV_TC, oi);
+      CK(vsb::launch_conv_halo(h, e->num_sms, e->stream));
+    }
+    return VSB_OK;
+  }
   if (cp.tc && cp.use_halo2 && e->conv_impl == 0 && !e->no_halo) {
     vsb::ConvHalo2Params h = cp.h2params;
     h.NB = nb;
@@ -816,6 +925,13 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
   a.residual = op.res >= 0 ? (const uint8_t*)e->tens[op.res].ptr + out_off * 2 : nullptr;
   a.out = (uint8_t*)ot.ptr + out_off * (ot.dtype ? 4 : 2);
   a.out_f32 = ot.dtype;
+  if (cp.depthwise && e->conv_impl != 2) {
+    a.weights = cp.d_whalo;
+    ProfScope ps(e, PC_OTHER, oi);
+    vsb::launch_dwconv3x3(a, e->stream);
+    CK(cudaGetLastError());
+    return VSB_OK;
+  }
   ProfScope ps(e, PC_CONV_SIMT, oi);
   vsb::launch_conv_simt(a, e->stream);
   CK(cudaGetLastError());

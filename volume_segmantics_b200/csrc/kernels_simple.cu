@@ -324,6 +324,66 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Depthwise 3x3 (smp SeparableConv2d "0" of DeepLabV3+ [ext]): stride 1, pad = dil,
+// input = channel concat of NHWC sources (every C % 8 == 0).  Memory-bound: one thread =
+// one pixel x 8 channels, 16-byte loads; weights repacked by the engine to [tap][C].
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(ConvArgs a) {
+  const int C8 = a.cout >> 3;
+  const int64_t total = (int64_t)a.NB * a.H * a.W * C8;
+  const uint16_t* __restrict__ wt = (const uint16_t*)a.weights;  // [9][C]
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    const int ox = (int)((i / C8) % a.W);
+    const int oy = (int)((i / ((int64_t)C8 * a.W)) % a.H);
+    const int64_t n = i / ((int64_t)C8 * a.W * a.H);
+    int s = 0, cb = 0;
+    while (s + 1 < a.n_src && c >= cb + a.src[s].C) cb += a.src[s++].C;
+    const SrcView& sv = a.src[s];
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = a.bias ? a.bias[c + j] : 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy - a.pad + ky * a.dil;
+      if (iy < 0 || iy >= a.H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox - a.pad + kx * a.dil;
+        if (ix < 0 || ix >= a.W) continue;
+        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(
+            (const uint16_t*)sv.ptr + ((n * sv.H + iy) * (int64_t)sv.W + ix) * sv.C + (c - cb)));
+        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wt + (ky * 3 + kx) * a.cout + c));
+        const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, ws[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 xf = unpack_act2(xs[j]), wf = unpack_act2(ws[j]);
+          acc[2 * j] = fmaf(xf.x, wf.x, acc[2 * j]);
+          acc[2 * j + 1] = fmaf(xf.y, wf.y, acc[2 * j + 1]);
+        }
+      }
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    uint4 pk;
+    pk.x = pack_act2(acc[0], acc[1]);
+    pk.y = pack_act2(acc[2], acc[3]);
+    pk.z = pack_act2(acc[4], acc[5]);
+    pk.w = pack_act2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>((uint16_t*)a.out + i * 8) = pk;
+  }
+}
+
+void launch_dwconv3x3(const ConvArgs& a, cudaStream_t st) {
+  const int64_t total = (int64_t)a.NB * a.H * a.W * (a.cout / 8);
+  const int64_t blocks = (total + 255) / 256;
+  dwconv3x3_kernel<<<(int)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, st>>>(a);
+}
+
 void launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
   const int64_t total = (int64_t)a.NB * a.H * a.W * a.cout;
   const int64_t blocks = (total + 255) / 256;
@@ -421,6 +481,32 @@ __device__ __forceinline__ float logit_at(const HeadArgs& a, int64_t n, int py, 
   return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
 }
 
+// softmax -> first-max label and probability of one padded pixel (py, px) of image n
+__device__ __forceinline__ void head_pixel(const HeadArgs& a, int64_t n, int py, int px, int Hl, int Wl,
+                                           float& best, int& lab) {
+  float l[VSB_MAX_CLASSES];
+  float m = -INFINITY;
+  for (int k = 0; k < a.C; ++k) {
+    l[k] = logit_at(a, n, py, px, k, Hl, Wl);
+    m = fmaxf(m, l[k]);
+  }
+  float sum = 0.f;
+  for (int k = 0; k < a.C; ++k) {
+    l[k] = expf(l[k] - m);
+    sum += l[k];
+  }
+  // probs = exp/sum; label = first index of the max prob (torch.argmax)
+  best = -1.f;
+  lab = 0;
+  for (int k = 0; k < a.C; ++k) {
+    const float p = __fdiv_rn(l[k], sum);
+    if (p > best) {
+      best = p;
+      lab = k;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   const vsb_direction& g = a.g;
   const int64_t total = (int64_t)a.nb * g.H * g.W;
@@ -430,28 +516,9 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
     const int64_t c = i % g.W;
     const int64_t r = (i / g.W) % g.H;
     const int64_t s = i / (g.W * g.H);
-    const int py = (int)(r + g.crop_top), px = (int)(c + g.crop_left);
-    float l[VSB_MAX_CLASSES];
-    float m = -INFINITY;
-    for (int k = 0; k < a.C; ++k) {
-      l[k] = logit_at(a, s, py, px, k, Hl, Wl);
-      m = fmaxf(m, l[k]);
-    }
-    float sum = 0.f;
-    for (int k = 0; k < a.C; ++k) {
-      l[k] = expf(l[k] - m);
-      sum += l[k];
-    }
-    // probs = exp/sum; label = first index of the max prob (torch.argmax)
-    float best = -1.f;
-    int lab = 0;
-    for (int k = 0; k < a.C; ++k) {
-      const float p = __fdiv_rn(l[k], sum);
-      if (p > best) {
-        best = p;
-        lab = k;
-      }
-    }
+    float best;
+    int lab;
+    head_pixel(a, s, (int)(r + g.crop_top), (int)(c + g.crop_left), Hl, Wl, best, lab);
     const int64_t vox = g.base + (a.s0 + s) * g.stride_s + r * g.stride_r + c * g.stride_c;
     if (a.votes) {
       // one-hot vote (vol_seg_2d_predictor.py:118-136): uint8 counts, <= 12
@@ -465,7 +532,48 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   }
 }
 
+// x-plane directions (slices run along x, stride_s == 1): logits are read with the image
+// column fastest (coalesced), keys are transposed through shared memory and merged with
+// the slice index fastest, so a warp's 32 atomics hit 256 contiguous bytes of the key
+// volume instead of 32 different sectors.
+__global__ void __launch_bounds__(256) head_xplane_kernel(HeadArgs a) {
+  __shared__ unsigned long long tile[32][33];
+  const vsb_direction& g = a.g;
+  const int Hl = (int)(g.Hp / a.factor), Wl = (int)(g.Wp / a.factor);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t ctiles = (g.W + 31) >> 5, stiles = (a.nb + 31) >> 5;
+  const int64_t total = stiles * g.H * ctiles;
+  for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const int64_t ct = t % ctiles;
+    const int64_t r = (t / ctiles) % g.H;
+    const int64_t stile = t / (ctiles * g.H);
+    __syncthreads();
+    for (int si = ty; si < 32; si += 8) {
+      const int64_t s = stile * 32 + si, c = ct * 32 + tx;
+      unsigned long long key = 0ull;
+      if (s < a.nb && c < g.W) {
+        float best;
+        int lab;
+        head_pixel(a, s, (int)(r + g.crop_top), (int)(c + g.crop_left), Hl, Wl, best, lab);
+        key = pack_key(__half_as_ushort(__float2half_rn(best)), a.d, (uint32_t)lab, __float_as_uint(best));
+      }
+      tile[si][tx] = key;
+    }
+    __syncthreads();
+    for (int ci = ty; ci < 32; ci += 8) {
+      const int64_t s = stile * 32 + tx, c = ct * 32 + ci;
+      const unsigned long long key = tile[tx][ci];
+      if (key) atomicMax(a.keys + (g.base + (a.s0 + s) * g.stride_s + r * g.stride_r + c * g.stride_c), key);
+    }
+  }
+}
+
 void launch_head(const HeadArgs& a, cudaStream_t st) {
+  if (!a.votes && a.g.stride_s == 1 && a.g.stride_c != 1 && a.nb >= 8) {
+    const int64_t tiles = ((a.nb + 31) / 32) * a.g.H * ((a.g.W + 31) / 32);
+    head_xplane_kernel<<<(int)(tiles < 148 * 16 ? tiles : 148 * 16), 256, 0, st>>>(a);
+    return;
+  }
   const int64_t total = (int64_t)a.nb * a.g.H * a.g.W;
   const int64_t blocks = (total + 255) / 256;
   const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
