@@ -84,7 +84,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     }
     fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < p.n_tiles * p.BN; i += TC_THREADS) bias_s[i] = p.bias[i];
+  bias_s -= p.cout_off;  // indexed by absolute output channel
+  for (int i = threadIdx.x; i < p.n_tiles * p.BN; i += TC_THREADS) bias_s[p.cout_off + i] = p.bias[p.cout_off + i];
   {
     const int4* src = reinterpret_cast<const int4*>(p.runs);
     int4* dst = reinterpret_cast<int4*>(runs_s);
@@ -122,7 +123,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
             mbar_arrive_expect_tx(&ctl->full[stage], tx_bytes);
             for (int q = 0; q < ncls; ++q)
               tma_load_5d(map, &ctl->full[stage], a_dst + q * cls_bytes,
-                          run.cls[q][0] + b * (RB / 2), X0 + run.cls[q][1], run.cls[q][2],
+                          p.cin_off + run.cls[q][0] + b * (RB / 2), X0 + run.cls[q][1], run.cls[q][2],
                           Y0 + run.cls[q][3], N0 + p.n_base);
             bulk_load_1d(a_dst + p.a_bytes, wsrc + b * wstep, b_bytes, &ctl->full[stage]);
           }
@@ -199,7 +200,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
       const int on = N0 + ni;
       const bool valid = on < p.NB && oy < p.H && ox < p.W;
       const int64_t pix = ((int64_t)(on + p.n_base) * p.H + oy) * p.W + ox;
-      const int ch0 = n_tile * p.BN;
+      const int ch0 = p.cout_off + n_tile * p.BN;
 
       mbar_wait(&ctl->acc_full[acc], acc_phase);
       tc_fence_after_sync();

@@ -49,6 +49,7 @@ struct ConvTcParams {
   int32_t BN, n_tiles;        // N tile and number of N tiles
   int32_t NB, H, W;           // output dims (NB images starting at image n_base)
   int32_t n_base;
+  int32_t cin_off, cout_off;  // channel window (grouped conv: one 64-channel block per launch)
   int32_t ncls_log2;          // 0: one pixel class, 2: four parity classes
   int32_t bw_log2, bh_log2, nt_log2;  // box (per class), bw*bh*nt*ncls == 128
   int32_t tiles_x, tiles_y, tiles_n;  // box-grid tile counts
