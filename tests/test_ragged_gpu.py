@@ -1,0 +1,82 @@
+"""Ragged / tiny volumes in the reference's own test regime (random sizes 10..255 per
+axis, reference tests/conftest.py:67-69) through the public API, against the oracle run
+live on the same trained weights: every kernel path that depends on the spatial size
+(halo tiles vs per-tap tiles packing several images, pad > image, crop shift for
+pad = 3 mod 4, 1x1 maps at 1/32 resolution) must agree."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import predict_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 2e-2
+SETTINGS = dict(quality="medium", output_probs=False, clip_data=False, st_dev_factor=2.575,
+                data_hdf5_path="/data", cuda_device=0, downsample=False, one_hot=False, prediction_axis="Z")
+SHAPES = [(10, 17, 255), (33, 12, 64), (11, 61, 29), (5, 96, 160), (40, 10, 10), (1, 32, 32)]
+
+
+@pytest.fixture(scope="module")
+def pair(tmp_path_factory, trained_unet_r34):
+    import volume_segmantics.utilities.base_data_utils as utils
+    from volume_segmantics.model.operations.vol_seg_2d_predictor import VolSeg2dPredictor
+
+    oracle, _ = trained_unet_r34
+    path = tmp_path_factory.mktemp("ragged") / "m.pytorch"
+    struc = {"type": utils.ModelType.U_NET, "encoder_name": "resnet34", "encoder_weights": None,
+             "in_channels": 1, "classes": 4}
+    torch.save({"model_state_dict": oracle.state_dict(), "model_struc_dict": struc, "label_codes": {}}, path)
+    return VolSeg2dPredictor(str(path), SimpleNamespace(**SETTINGS)), po.OraclePredictor(oracle, 4)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_three_ways_on_ragged_shapes(pair, shape):
+    pred, oracle = pair
+    rng = np.random.default_rng(sum(shape))
+    # smooth field + noise, as the training data of the parity network
+    z, y, x = np.meshgrid(*[np.arange(s, dtype=np.float32) for s in shape], indexing="ij")
+    vol = np.clip(128 + 50 * np.sin(z / 4.0) + 40 * np.sin(y / 6.0 + 1) + 30 * np.sin(x / 8.0 + 2)
+                  + rng.normal(0, 20, shape), 0, 255).astype(np.uint8)
+    labels, probs = pred._predict_3_ways_max_probs(vol)
+    want_l, want_p = oracle.predict_3_ways_max_probs(vol)
+    assert labels.shape == shape and labels.dtype == np.uint8 and probs.dtype == np.float16
+    perr = np.abs(probs.astype(np.float32) - want_p.astype(np.float32)).max()
+    agree = (labels == want_l).mean()
+    print(f"[ragged {shape}] agreement {agree:.5f} max prob err {perr:.5f}")
+    assert perr < PROB_TOL
+    assert agree >= 0.995  # tiny volumes: a handful of boundary voxels weigh more than at scale
+
+
+def test_single_axis_each_direction_on_a_ragged_shape(pair):
+    pred, oracle = pair
+    shape = (13, 37, 70)
+    vol = np.random.default_rng(3).integers(0, 256, shape, dtype=np.uint8)
+    eng = pred.engine
+    pred._prepare(vol)
+    for d in range(12):
+        eng.reset()
+        eng.predict(1 << d, skip_duplicates=False)
+        lab, prb = eng.fetch()
+        sl = np.ascontiguousarray(po.direction_slices(vol, d))
+        l_s, p_s = oracle.predict_single_axis(sl, True, po.AXIS_Z)  # slice space of direction d
+        want_l = po.direction_to_volume(l_s, d)
+        want_p = po.direction_to_volume(p_s, d)
+        perr = np.abs(prb.astype(np.float32) - want_p.astype(np.float32)).max()
+        assert perr < PROB_TOL, f"direction {d}: prob error {perr}"
+        assert (lab == want_l).mean() >= 0.99, f"direction {d}"
+
+
+def test_one_hot_votes_all_qualities(pair):
+    pred, oracle = pair
+    vol = np.random.default_rng(5).integers(0, 256, (12, 33, 20), dtype=np.uint8)
+    for fn_b, fn_o, n in [(pred._predict_single_axis_to_one_hot, oracle.predict_single_axis_to_one_hot, 1),
+                          (pred._predict_3_ways_one_hot, oracle.predict_3_ways_one_hot, 3),
+                          (pred._predict_12_ways_one_hot, oracle.predict_12_ways_one_hot, 12)]:
+        votes, want = fn_b(vol), fn_o(vol)
+        assert votes.dtype == np.uint8 and votes.shape == want.shape == (4,) + vol.shape
+        assert (votes.sum(0) == n).all()
+        moved = np.abs(votes.astype(int) - want).sum() / 2
+        assert moved <= 0.01 * n * vol.size
