@@ -193,8 +193,14 @@ int vsb_set_profiling(vsb_engine* e, int32_t on);
 /* Same, per op index of the loaded plan (conv / pool ops).                   */
 int vsb_op_ms(vsb_engine* e, int32_t op, float* ms, int64_t* launches);
 
-/* ---- clip_to_uint8 (base_data_utils.py:243-287), SURVEY 8f-1 -------------- */
-/* (declared when implemented) */
+/* ---- clip_to_uint8 (base_data_utils.py:243-287), SURVEY 8f-1 --------------
+ * Elementwise part of the reference's pre-processing: NaN -> mean, clip to
+ * [lower, upper], rescale to 0..255, truncate to uint8 -- the same IEEE double
+ * operations in the same order as numpy (bit-exact given the same statistics, which
+ * the host computes with numpy like the reference).  `data` and `out` are HOST
+ * pointers; dtype: 0 f32, 1 f64, 2 u8, 3 i8, 4 u16, 5 i16, 6 u32, 7 i32, 8 i64.     */
+int vsb_clip_to_uint8(vsb_engine* e, const void* data, int32_t dtype, int64_t n, double mean,
+                      double lower, double upper, uint8_t* out);
 
 #ifdef __cplusplus
 }

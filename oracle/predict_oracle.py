@@ -251,3 +251,22 @@ def merge_injected_oracle(shape_zyx, dirs, probs_by_dir, labels_by_dir):
             label_c[1], prob_c[1] = lab, prb
             merge_vols_in_mem(prob_c, label_c)
     return label_c[0].copy(), prob_c[0].copy()
+
+
+def clip_to_uint8_oracle(data: np.ndarray, data_mean: float, st_dev_factor: float) -> np.ndarray:
+    """base_data_utils.py:243-287 restated (numpy, float64): clip to mean +- k*sigma, rescale,
+    truncate.  Works on a copy; the reference mutates float input in place."""
+    data = np.array(data, copy=True)
+    data_st_dev = np.nanstd(data)
+    lower_bound = data_mean - (data_st_dev * st_dev_factor)
+    upper_bound = data_mean + (data_st_dev * st_dev_factor)
+    if np.isnan(data).any():
+        data = np.nan_to_num(data, copy=False, nan=data_mean)
+    if np.issubdtype(data.dtype, np.integer):
+        data = data.astype(float)
+    data = np.clip(data, lower_bound, upper_bound, out=data)
+    data = np.subtract(data, lower_bound, out=data)
+    data = np.divide(data, (upper_bound - lower_bound), out=data)
+    data = np.clip(data, 0.0, 1.0, out=data)
+    data = np.multiply(data, 255, out=data)
+    return data.astype(np.uint8)

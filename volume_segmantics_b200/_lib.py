@@ -95,6 +95,7 @@ SIGNATURES = {
     "vsb_forward_logits": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vsb_debug_tensor": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "vsb_stage_ms": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    "vsb_clip_to_uint8": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_double, C.c_double, C.c_double, _P]),
     "vsb_set_profiling": (C.c_int, [_P, C.c_int32]),
     "vsb_op_ms": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
 }

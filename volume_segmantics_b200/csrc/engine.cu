@@ -1590,6 +1590,34 @@ int vsb_debug_tensor(vsb_engine* e, int32_t t, float* out, int64_t capacity, int
   return VSB_OK;
 }
 
+int vsb_clip_to_uint8(vsb_engine* e, const void* data, int32_t dtype, int64_t n, double mean, double lower,
+                      double upper, uint8_t* out) {
+  if (!e || !data || !out || n <= 0 || dtype < 0 || dtype > 8) return fail(VSB_ERR_INVALID, "bad clip arguments");
+  if (!(upper > lower)) return fail(VSB_ERR_INVALID, "clip range is empty (upper <= lower)");
+  CK(cudaSetDevice(e->device));
+  static const int esz[9] = {4, 8, 1, 1, 2, 2, 4, 4, 8};
+  // stream the volume through the GPU in chunks so a float64 1024^3 volume never needs 8 GiB at once
+  const int64_t chunk = 256ll << 20;
+  void* din = nullptr;
+  uint8_t* dout = nullptr;
+  CK(cudaMalloc(&din, (size_t)std::min(chunk, n) * esz[dtype]));
+  cudaError_t err = cudaMalloc(&dout, (size_t)std::min(chunk, n));
+  for (int64_t off = 0; err == cudaSuccess && off < n; off += chunk) {
+    const int64_t m = std::min(chunk, n - off);
+    err = cudaMemcpyAsync(din, (const uint8_t*)data + off * esz[dtype], (size_t)m * esz[dtype], cudaMemcpyHostToDevice,
+                          e->stream);
+    if (err != cudaSuccess) break;
+    vsb::launch_clip_u8(din, dtype, m, mean, lower, upper, dout, e->stream);
+    err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaMemcpyAsync(out + off, dout, (size_t)m, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  }
+  cudaFree(din);
+  cudaFree(dout);
+  CK(err);
+  return VSB_OK;
+}
+
 int vsb_set_profiling(vsb_engine* e, int32_t on) {
   if (!e) return fail(VSB_ERR_INVALID, "null engine");
   CK(cudaSetDevice(e->device));

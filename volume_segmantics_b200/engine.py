@@ -160,6 +160,20 @@ class Engine:
     def set_conv_impl(self, impl: str) -> None:
         _lib.check(self.lib.vsb_set_conv_impl(self.h, {"tc": 0, "simt": 1, "generic": 2}[impl]))
 
+    CLIP_DTYPES = {"float32": 0, "float64": 1, "uint8": 2, "int8": 3, "uint16": 4, "int16": 5,
+                   "uint32": 6, "int32": 7, "int64": 8}
+
+    def clip_to_uint8(self, data: np.ndarray, mean: float, lower: float, upper: float) -> np.ndarray:
+        """Elementwise part of base_data_utils.clip_to_uint8 on the GPU (bit-exact to numpy)."""
+        data = np.ascontiguousarray(data)
+        code = self.CLIP_DTYPES.get(data.dtype.name)
+        if code is None:
+            raise NotImplementedError(f"clip_to_uint8: dtype {data.dtype} not supported on the GPU path")
+        out = np.empty(data.shape, np.uint8)
+        _lib.check(self.lib.vsb_clip_to_uint8(self.h, _ptr(data), code, data.size, float(mean), float(lower),
+                                              float(upper), _ptr(out)))
+        return out
+
     def set_flag(self, name: str, value: int) -> None:
         _lib.check(self.lib.vsb_set_flag(self.h, name.encode(), int(value)))
 
@@ -219,3 +233,15 @@ class Engine:
             _lib.check(self.lib.vsb_stage_ms(self.h, i, C.byref(ms), C.byref(n)))
             out[name] = (ms.value, n.value)
         return out
+
+
+_ENGINES: Dict[int, Engine] = {}
+
+
+def get_engine(device: int = 0) -> Engine:
+    """One engine per GPU per process (the C-ABI handle is not thread-safe)."""
+    device = int(device)
+    eng = _ENGINES.get(device)
+    if eng is None or not eng.h:
+        eng = _ENGINES[device] = Engine(device)
+    return eng

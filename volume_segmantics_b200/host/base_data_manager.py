@@ -10,6 +10,15 @@ import numpy as np
 from . import utils
 
 
+def _cuda_available() -> bool:
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        return False
+
+
 class BaseDataManager:
     def __init__(self, data_vol: Union[Path, str, np.ndarray], settings: SimpleNamespace) -> None:
         self.data_vol_shape = None
@@ -35,7 +44,9 @@ class BaseDataManager:
         self.data_mean = np.nanmean(self.data_vol)
         logging.info(f"Mean value: {self.data_mean}")
         if self.settings.clip_data:
-            self.data_vol = utils.clip_to_uint8(self.data_vol, self.data_mean, self.st_dev_factor)
+            # elementwise part on the GPU the prediction will use (None -> numpy, as the reference)
+            device = getattr(self.settings, "cuda_device", None) if _cuda_available() else None
+            self.data_vol = utils.clip_to_uint8(self.data_vol, self.data_mean, self.st_dev_factor, cuda_device=device)
         if np.isnan(self.data_vol).any():
             logging.info("Replacing NaN values.")
             self.data_vol = np.nan_to_num(self.data_vol, copy=False)

@@ -15,7 +15,7 @@ from types import SimpleNamespace
 
 import numpy as np
 
-from ..engine import Engine
+from ..engine import Engine, get_engine
 from ..plan import B200SegmentationModel
 from .enums import Axis
 from .model_2d import create_model_from_file
@@ -65,7 +65,7 @@ class VolSeg2dPredictor:
     @property
     def engine(self) -> Engine:
         if self._engine is None:
-            self._engine = Engine(self.model_device_num)
+            self._engine = get_engine(self.model_device_num)
         return self._engine
 
     def _prepare(self, data_vol) -> np.ndarray:

@@ -145,24 +145,42 @@ def get_numpy_from_path(path: Path, internal_path: str = "/data"):
         return numpy_from_hdf5(path, hdf5_path=internal_path, nexus=path.suffix == ".nxs")
 
 
-def clip_to_uint8(data: np.ndarray, data_mean: float, st_dev_factor: float) -> np.ndarray:
+def clip_to_uint8(data: np.ndarray, data_mean: float, st_dev_factor: float, cuda_device=None) -> np.ndarray:
     """:243-287 -- clip to mean +- k sigma, rescale to 0..255, truncate to uint8.
-    Runs once before the hot path; numpy, float64 like the
-    reference."""
+    The statistics (`np.nanstd`, clipped-voxel counts for the log) are numpy exactly as in
+    the reference; the six elementwise float64 passes (:272-287) run as ONE kernel of the
+    B200 engine when `cuda_device` names a GPU (bit-exact to numpy, tests/test_clip_gpu.py).
+    Without a device argument this is the reference's numpy code path."""
     logging.info("Clipping data and converting to uint8.")
+    logging.info("Calculating standard deviation.")
     data_st_dev = np.nanstd(data)
+    logging.info(f"Std dev: {data_st_dev}. Calculating stats.")
+    num_vox = data.size
     lower = data_mean - data_st_dev * st_dev_factor
     upper = data_mean + data_st_dev * st_dev_factor
+    with np.errstate(invalid="ignore"):
+        gt_ub = (data > upper).sum()
+        lt_lb = (data < lower).sum()
     logging.info(f"Lower bound: {lower}, upper bound: {upper}")
+    logging.info(f"Number of voxels above upper bound to be clipped {gt_ub} - percentage {gt_ub / num_vox * 100:.3f}%")
+    logging.info(f"Number of voxels below lower bound to be clipped {lt_lb} - percentage {lt_lb / num_vox * 100:.3f}%")
+    if cuda_device is not None:
+        from ..engine import Engine, get_engine
+
+        if data.dtype.name in Engine.CLIP_DTYPES and upper > lower:
+            logging.info("Rescaling intensities and converting to uint8 on the GPU.")
+            return get_engine(int(cuda_device)).clip_to_uint8(data, float(data_mean), float(lower), float(upper))
     if np.isnan(data).any():
         logging.info("Replacing NaN values.")
         data = np.nan_to_num(data, copy=False, nan=data_mean)
+    logging.info("Rescaling intensities.")
     if np.issubdtype(data.dtype, np.integer):
         data = data.astype(float)
     data = np.clip(data, lower, upper, out=data)
     data = np.subtract(data, lower, out=data)
     data = np.divide(data, (upper - lower), out=data)
     data = np.clip(data, 0.0, 1.0, out=data)
+    logging.info("Converting to uint8.")
     data = np.multiply(data, 255, out=data)
     return data.astype(np.uint8)
 
