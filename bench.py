@@ -194,22 +194,57 @@ def run_ours(args):
     vol_dev = vol_host.to(dev)
     torch.cuda.synchronize()
     eng.set_volume_device(vol_dev.data_ptr(), (size, size, size))
-    keys = torch.zeros(nvox, dtype=torch.int64, device=dev)
-    eng.bind_keys(keys.data_ptr())
-    labels_dev = torch.empty(nvox, dtype=torch.uint8, device=dev)
-    probs_dev = torch.empty(nvox, dtype=torch.float16, device=dev)
-
     dirs = sharding.direction_list(DIR_MASK, skip_duplicates=True)
     items = sharding.partition((size, size, size), dirs, world, granule=8)[rank]
 
+    # ---- the one exchange step --------------------------------------------
+    # "peer": fused max-reduce + unpack of this rank's voxel shard, reading the other ranks'
+    #         key volumes over NVLink through CUDA-IPC mappings (one kernel, no NCCL payload);
+    #         two 4-byte all-reduces act as stream-ordered barriers around it.
+    # "nccl": ncclAllReduce(max) over the whole 8 B/voxel key volume, then rank 0 unpacks.
+    exchange = args.exchange if world > 1 else "none"
+    keys = None
+    if exchange == "peer":
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.keys_ipc_handle())
+        ok = 1
+        try:
+            eng.open_peers(handles, rank)
+        except _lib.VsbError as ex:
+            print(f"[rank {rank}] peer mapping unavailable ({ex}); falling back to the NCCL all-reduce", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            eng.close_peers()
+            exchange = "nccl"
+    if exchange == "nccl":
+        keys = torch.zeros(nvox, dtype=torch.int64, device=dev)
+        eng.bind_keys(keys.data_ptr())
+    shards = sharding.voxel_shards(nvox, world)
+    v0, v1 = shards[rank]
+    out_n = nvox if exchange != "peer" else shards[0][1] - shards[0][0]
+    labels_dev = torch.empty(out_n, dtype=torch.uint8, device=dev)
+    probs_dev = torch.empty(out_n, dtype=torch.float16, device=dev)
+    tick = torch.zeros(1, dtype=torch.int32, device=dev)
+
     def step():
         with torch.cuda.stream(stream):
-            keys.zero_()
+            if exchange == "nccl":
+                keys.zero_()
+            else:
+                eng.reset()
             for it in items:
                 eng.predict_range(it.d, it.s0, it.s1)
-            if world > 1:
+            if exchange == "nccl":
                 dist.all_reduce(keys, op=dist.ReduceOp.MAX)
-            if rank == 0:
+                if rank == 0:
+                    eng.unpack_device(labels_dev.data_ptr(), probs_dev.data_ptr())
+            elif exchange == "peer":
+                dist.all_reduce(tick)  # every rank has finished merging into its own keys
+                eng.reduce_unpack_shard(v0, v1, labels_dev.data_ptr(), probs_dev.data_ptr())
+                dist.all_reduce(tick)  # every rank has finished reading its peers' keys
+            else:
                 eng.unpack_device(labels_dev.data_ptr(), probs_dev.data_ptr())
 
     def barrier():
@@ -240,7 +275,7 @@ def run_ours(args):
     # kernel launch bracketed by CUDA events, for the roofline of the conv kernels.
     sampler = ClockSampler(local) if rank == 0 else None
     ms = timed_pass(False)
-    launches = eng.launch_count() + (1 if world > 1 else 0) * args.steps
+    launches = eng.launch_count()  # own kernels only (NCCL kernels are not counted)
     ms_prof = ms if args.no_profile else timed_pass(True)
     clocks = sampler.stop() if sampler else None
     stages = eng.stage_times()
@@ -253,7 +288,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (tcgen05 conv), this rank's launches ----
     peak_tf, peak_gbs, peak_src = measured_peaks()
-    macs_px = conv_macs_per_pixel(model.spec) - 49 * 64 / 4.0  # the 7x7 stem runs on CUDA cores
+    macs_px = conv_macs_per_pixel(model.spec) - 49 * 64 / 4.0  # the 7x7 stem is timed in its own class
     padded_px = sum(it.cost for it in items)
     conv_ms, conv_n = stages["conv_tc"]
     conv_flops = 2.0 * macs_px * padded_px * args.steps
@@ -272,7 +307,7 @@ def run_ours(args):
     # ---- e2e through the public API with host buffers ------------------------------
     e2e = None
     if rank == 0 or world > 1:
-        e2e = run_e2e(args, eng, model, vol_host, stream, world, rank, items, keys, dev)
+        e2e = run_e2e(args, eng, model, vol_host, stream, world, rank, items, keys, dev, exchange, shards)
 
     # ---- CPU baseline: bounded sample on rank 0, N = 1 only -------------------------
     cpu = None
@@ -295,7 +330,10 @@ def run_ours(args):
                        "note": "directions 3,6,9,10 duplicate 1,4,7,0 image-for-image and can never win the first-max merge "
                                "(SURVEY.md 3.3); they are skipped and NOT counted in the roofline FLOPs",
                        "l2": "inputs larger than L2 (1 GiB volume + 8 GiB keys per step)",
-                       "accumulate": "fp32", "parallelism": f"slice-range sharding over {world} GPU(s) + 1 NCCL max-reduce"},
+                       "accumulate": "fp32", "parallelism": f"slice-range sharding over {world} GPU(s)",
+                       "exchange": {"none": "single GPU: unpack only",
+                                    "peer": "fused max-reduce + unpack of each rank's voxel shard over NVLink peer memory (CUDA IPC); result sharded over ranks",
+                                    "nccl": "ncclAllReduce(max) of the 8 B/voxel key volume, rank 0 unpacks"}[exchange]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -303,7 +341,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, eng, model, vol_host, stream, world, rank, items, keys, dev):
+def run_e2e(args, eng, model, vol_host, stream, world, rank, items, keys, dev, exchange, shards):
     """Host ndarray in -> host ndarrays out, copies inside the timed region."""
     import torch
     import torch.distributed as dist
@@ -338,23 +376,49 @@ def run_e2e(args, eng, model, vol_host, stream, world, rank, items, keys, dev):
     labels_h = torch.empty(nvox, dtype=torch.uint8).pin_memory() if rank == 0 else None
     probs_h = torch.empty(nvox, dtype=torch.float16).pin_memory() if rank == 0 else None
     vol_dev = torch.empty(nvox, dtype=torch.uint8, device=dev)
-    labels_dev = torch.empty(nvox, dtype=torch.uint8, device=dev)
-    probs_dev = torch.empty(nvox, dtype=torch.float16, device=dev)
+    per = shards[0][1] - shards[0][0]
+    v0, v1 = shards[rank]
+    n_out = nvox if exchange == "nccl" else per
+    labels_dev = torch.empty(n_out, dtype=torch.uint8, device=dev)
+    probs_dev = torch.empty(n_out, dtype=torch.float16, device=dev)
+    lab_all = torch.empty(per * world, dtype=torch.uint8, device=dev) if (exchange == "peer" and rank == 0) else None
+    prb_all = torch.empty(per * world, dtype=torch.float16, device=dev) if (exchange == "peer" and rank == 0) else None
+    tick = torch.zeros(1, dtype=torch.int32, device=dev)
     eng.set_stream(stream.cuda_stream)
+    if exchange == "peer":
+        eng.close_peers()  # set_volume_device re-creates nothing (same size), but remap to be safe
     eng.set_volume_device(vol_dev.data_ptr(), (size, size, size))
-    eng.bind_keys(keys.data_ptr())
+    if exchange == "nccl":
+        eng.bind_keys(keys.data_ptr())
+    else:
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.keys_ipc_handle())
+        eng.open_peers(handles, rank)
 
     def one():
         with torch.cuda.stream(stream):
             vol_dev.copy_(vol_host.view(-1), non_blocking=True)
-            keys.zero_()
+            if exchange == "nccl":
+                keys.zero_()
+            else:
+                eng.reset()
             for it in items:
                 eng.predict_range(it.d, it.s0, it.s1)
-            dist.all_reduce(keys, op=dist.ReduceOp.MAX)
-            if rank == 0:
-                eng.unpack_device(labels_dev.data_ptr(), probs_dev.data_ptr())
-                labels_h.copy_(labels_dev, non_blocking=True)
-                probs_h.copy_(probs_dev, non_blocking=True)
+            if exchange == "nccl":
+                dist.all_reduce(keys, op=dist.ReduceOp.MAX)
+                if rank == 0:
+                    eng.unpack_device(labels_dev.data_ptr(), probs_dev.data_ptr())
+                    labels_h.copy_(labels_dev, non_blocking=True)
+                    probs_h.copy_(probs_dev, non_blocking=True)
+            else:
+                dist.all_reduce(tick)
+                eng.reduce_unpack_shard(v0, v1, labels_dev.data_ptr(), probs_dev.data_ptr())
+                dist.all_reduce(tick)
+                dist.gather(labels_dev, list(lab_all.split(per)) if rank == 0 else None, dst=0)
+                dist.gather(probs_dev, list(prb_all.split(per)) if rank == 0 else None, dst=0)
+                if rank == 0:
+                    labels_h.copy_(lab_all[:nvox], non_blocking=True)
+                    probs_h.copy_(prb_all[:nvox], non_blocking=True)
         torch.cuda.synchronize()
 
     one()
@@ -365,8 +429,11 @@ def run_e2e(args, eng, model, vol_host, stream, world, rank, items, keys, dev):
     dist.barrier()
     t = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if exchange == "peer":
+        eng.close_peers()
     return {"value": nvox / float(t.item()), "unit": "voxels/s", "h2d_bytes_per_step": nvox * world,
-            "d2h_bytes_per_step": 3 * nvox, "api": "Engine.predict_range per rank + NCCL max-reduce, host ndarray in/out"}
+            "d2h_bytes_per_step": 3 * nvox,
+            "api": f"Engine.predict_range per rank + {exchange} exchange, host ndarray in/out"}
 
 
 def main():
@@ -378,6 +445,8 @@ def main():
     ap.add_argument("--size", type=int, default=1024, help="edge of the cubic synthetic volume (BASELINE: 1024)")
     ap.add_argument("--batch", type=int, default=0, help="slices per launch (0 = engine default)")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with CUDA events")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU key exchange: fused NVLink peer reduce+unpack (default) or NCCL all-reduce")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":

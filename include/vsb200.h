@@ -134,6 +134,18 @@ int vsb_predict(vsb_engine* e, uint32_t dir_mask, int32_t skip_duplicates);
 int vsb_keys(vsb_engine* e, void** dev_ptr, int64_t* count);
 int vsb_bind_keys(vsb_engine* e, void* dev_ptr);
 
+/* Fused multi-GPU exchange over NVLink peer memory: every rank exports a
+ * CUDA-IPC handle of its key volume, opens the others', and then max-reduces + unpacks
+ * its own voxel shard [v_begin, v_end) with ONE kernel that loads the peers' keys
+ * directly (no NCCL all-reduce, no second pass over the keys).  The caller orders the
+ * ranks with a stream-ordered barrier before (all ranks finished predicting) and after
+ * (all ranks finished reading) the call.  handles64: n_ranks x 64 bytes, rank-major.   */
+int vsb_keys_ipc_export(vsb_engine* e, uint8_t* handle64);
+int vsb_peers_open(vsb_engine* e, int32_t n_ranks, int32_t my_rank, const uint8_t* handles64);
+int vsb_peers_close(vsb_engine* e);
+int vsb_reduce_unpack_shard(vsb_engine* e, int64_t v_begin, int64_t v_end, uint8_t* labels_dev,
+                            uint16_t* probs_fp16_dev);
+
 /* Unpack keys -> labels uint8 (Z,Y,X) [+ probs fp16 bits] and copy to host
  * (the `return labels, probs` of vol_seg_2d_predictor.py:65,88,116).
  * probs may be NULL.  Synchronises the stream.                              */

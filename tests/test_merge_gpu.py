@@ -56,3 +56,27 @@ def test_merge_idempotent_and_reset(engine):
     engine.reset()
     lab, prb = engine.fetch()
     assert not lab.any() and not prb.view(np.uint16).any()
+
+
+def test_reduce_unpack_shard_single_rank_equals_fetch(engine):
+    """The fused reduce+unpack kernel with one rank (no peers) is the plain unpack."""
+    import torch
+
+    shape = (9, 21, 35)  # odd voxel count: exercises the scalar tail
+    rng = np.random.default_rng(4)
+    engine.set_volume(np.zeros(shape, np.uint8))
+    for d in (0, 5, 7):
+        engine.merge_injected(d, rng.random(direction_dims(shape, d)).astype(np.float32),
+                              rng.integers(0, 200, direction_dims(shape, d)).astype(np.uint8))
+    want_l, want_p = engine.fetch()
+    n = int(np.prod(shape))
+    lab = torch.zeros(n, dtype=torch.uint8, device="cuda:0")
+    prb = torch.zeros(n, dtype=torch.float16, device="cuda:0")
+    engine.reduce_unpack_shard(0, n, lab.data_ptr(), prb.data_ptr())
+    engine.synchronize()
+    assert np.array_equal(lab.cpu().numpy(), want_l.ravel())
+    assert np.array_equal(prb.cpu().numpy().view(np.uint16), want_p.ravel().view(np.uint16))
+    # a sub-shard
+    engine.reduce_unpack_shard(8, 1000, lab.data_ptr(), prb.data_ptr())
+    engine.synchronize()
+    assert np.array_equal(lab.cpu().numpy()[:992], want_l.ravel()[8:1000])

@@ -80,6 +80,10 @@ SIGNATURES = {
     "vsb_predict": (C.c_int, [_P, C.c_uint32, C.c_int32]),
     "vsb_keys": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "vsb_bind_keys": (C.c_int, [_P, _P]),
+    "vsb_keys_ipc_export": (C.c_int, [_P, _P]),
+    "vsb_peers_open": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "vsb_peers_close": (C.c_int, [_P]),
+    "vsb_reduce_unpack_shard": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "vsb_fetch": (C.c_int, [_P, _P, _P]),
     "vsb_unpack_device": (C.c_int, [_P, _P, _P]),
     "vsb_set_vote_mode": (C.c_int, [_P, C.c_int32]),

@@ -134,6 +134,9 @@ struct vsb_engine {
   int vote_mode = 0;
   uint8_t* d_labels = nullptr;
   uint16_t* d_probs = nullptr;
+  // multi-GPU peers (CUDA IPC mappings of the other ranks' key volumes)
+  int n_ranks = 1, my_rank = 0;
+  unsigned long long* peer_keys[8] = {nullptr};
 
   // workspace
   int ws_Hp = 0, ws_Wp = 0, ws_nb = 0;
@@ -1242,12 +1245,15 @@ static void free_plan(vsb_engine* e) {
   e->has_plan = false;
 }
 
+static void close_peers(vsb_engine* e);
+
 void vsb_destroy(vsb_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   free_workspace(e);
   free_plan(e);
+  close_peers(e);
   cudaFree(e->d_vol_owned);
   cudaFree(e->d_keys_owned);
   cudaFree(e->d_votes);
@@ -1615,6 +1621,79 @@ int vsb_clip_to_uint8(vsb_engine* e, const void* data, int32_t dtype, int64_t n,
   cudaFree(din);
   cudaFree(dout);
   CK(err);
+  return VSB_OK;
+}
+
+int vsb_keys_ipc_export(vsb_engine* e, uint8_t* handle64) {
+  if (!e || !handle64) return fail(VSB_ERR_INVALID, "null argument");
+  if (!e->d_keys_owned || e->d_keys != e->d_keys_owned)
+    return fail(VSB_ERR_STATE, "IPC export needs the engine-owned key volume (no vsb_bind_keys)");
+  CK(cudaSetDevice(e->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, e->d_keys_owned));
+  memcpy(handle64, &h, 64);
+  return VSB_OK;
+}
+
+static void close_peers(vsb_engine* e) {
+  for (int r = 0; r < 8; ++r) {
+    if (e->peer_keys[r] && r != e->my_rank) cudaIpcCloseMemHandle(e->peer_keys[r]);
+    e->peer_keys[r] = nullptr;
+  }
+  e->n_ranks = 1;
+  e->my_rank = 0;
+}
+
+int vsb_peers_open(vsb_engine* e, int32_t n_ranks, int32_t my_rank, const uint8_t* handles64) {
+  if (!e || !handles64 || n_ranks < 1 || n_ranks > 8 || my_rank < 0 || my_rank >= n_ranks)
+    return fail(VSB_ERR_INVALID, "bad peer arguments (1..8 ranks)");
+  if (!e->d_keys_owned) return fail(VSB_ERR_STATE, "no volume set");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  close_peers(e);
+  e->n_ranks = n_ranks;
+  e->my_rank = my_rank;
+  for (int r = 0; r < n_ranks; ++r) {
+    if (r == my_rank) {
+      e->peer_keys[r] = e->d_keys_owned;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles64 + (size_t)r * 64, 64);
+    void* p = nullptr;
+    cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+      close_peers(e);
+      return fail(VSB_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(err));
+    }
+    e->peer_keys[r] = (unsigned long long*)p;
+  }
+  return VSB_OK;
+}
+
+int vsb_peers_close(vsb_engine* e) {
+  if (!e) return fail(VSB_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  close_peers(e);
+  return VSB_OK;
+}
+
+int vsb_reduce_unpack_shard(vsb_engine* e, int64_t v_begin, int64_t v_end, uint8_t* labels_dev, uint16_t* probs_dev) {
+  if (!e || !e->d_keys_owned || !labels_dev) return fail(VSB_ERR_STATE, "no volume set / null output");
+  const int64_t n = e->Z * e->Y * e->X;
+  if (v_begin < 0 || v_end > n || v_begin > v_end || (v_begin & 1))
+    return fail(VSB_ERR_INVALID, "bad shard [%lld, %lld) (begin must be even)", (long long)v_begin, (long long)v_end);
+  for (int r = 0; r < e->n_ranks; ++r)
+    if (!e->peer_keys[r] && !(e->n_ranks == 1)) return fail(VSB_ERR_STATE, "peer %d not opened", r);
+  CK(cudaSetDevice(e->device));
+  const unsigned long long* ks[8];
+  if (e->n_ranks == 1) ks[0] = e->d_keys;
+  else for (int r = 0; r < e->n_ranks; ++r) ks[r] = e->peer_keys[r];
+  e->launches += 1;
+  vsb::launch_reduce_unpack(ks, e->n_ranks, v_begin, v_end - v_begin, labels_dev, probs_dev, e->stream);
+  CK(cudaGetLastError());
   return VSB_OK;
 }
 

@@ -67,6 +67,8 @@ void launch_unpack(const unsigned long long* keys, int64_t n, uint8_t* labels, u
                    cudaStream_t st);
 void launch_clip_u8(const void* in, int dtype, int64_t n, double mean, double lower, double upper, uint8_t* out,
                     cudaStream_t st);
+void launch_reduce_unpack(const unsigned long long* const* keys, int n_ranks, int64_t v0, int64_t n, uint8_t* labels,
+                          uint16_t* probs, cudaStream_t st);
 void launch_f32_to_act(const float* in, uint16_t* out, int64_t n, cudaStream_t st);
 void launch_to_f32(const void* in, int is_f32, float* out, int64_t n, cudaStream_t st);
 

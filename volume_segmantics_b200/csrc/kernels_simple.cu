@@ -682,6 +682,54 @@ void launch_clip_u8(const void* in, int dtype, int64_t n, double mean, double lo
   clip_u8_kernel<<<(int)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, st>>>(in, dtype, n, mean, lower, upper, out);
 }
 
+// ---------------------------------------------------------------------------
+// Fused multi-GPU exchange: max-reduce of the packed keys over all ranks + unpack, for
+// the voxel shard [v0, v0 + n) owned by this rank.  keys[r] are the ranks' key volumes
+// (this rank's own buffer and CUDA-IPC mappings of the peers' buffers, read directly
+// over NVLink with 16-byte loads).  Replaces ncclAllReduce(uint64, max) + unpack:
+// each rank pulls (N-1)/N * 8 B per shard voxel instead of the ring's 2(N-1)/N * 8 B per
+// voxel of the whole volume, and the result never round-trips through the key buffer.
+// ---------------------------------------------------------------------------
+struct PeerKeys {
+  const unsigned long long* k[8];
+  int n;
+};
+__global__ void __launch_bounds__(256) reduce_unpack_kernel(PeerKeys pk, int64_t v0, int64_t n,
+                                                            uint8_t* __restrict__ labels,
+                                                            uint16_t* __restrict__ probs) {
+  const int64_t n2 = n >> 1;  // v0 is even (shards are cut on multiples of 8 voxels)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    ulonglong2 m = make_ulonglong2(0ull, 0ull);
+#pragma unroll 8
+    for (int r = 0; r < pk.n; ++r) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(pk.k[r] + v0 + 2 * i);
+      m.x = v.x > m.x ? v.x : m.x;
+      m.y = v.y > m.y ? v.y : m.y;
+    }
+    reinterpret_cast<uint16_t*>(labels)[i] =
+        (uint16_t)(((m.x >> 36) & 0xff) | (((m.y >> 36) & 0xff) << 8));
+    if (probs) reinterpret_cast<uint32_t*>(probs)[i] = (uint32_t)(m.x >> 48) | ((uint32_t)(m.y >> 48) << 16);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail voxel
+    unsigned long long m = 0ull;
+    for (int r = 0; r < pk.n; ++r) {
+      const unsigned long long v = pk.k[r][v0 + n - 1];
+      m = v > m ? v : m;
+    }
+    labels[n - 1] = (uint8_t)((m >> 36) & 0xff);
+    if (probs) probs[n - 1] = (uint16_t)(m >> 48);
+  }
+}
+void launch_reduce_unpack(const unsigned long long* const* keys, int n_ranks, int64_t v0, int64_t n, uint8_t* labels,
+                          uint16_t* probs, cudaStream_t st) {
+  PeerKeys pk{};
+  pk.n = n_ranks;
+  for (int r = 0; r < n_ranks; ++r) pk.k[r] = keys[r];
+  const int64_t blocks = ((n >> 1) + 255) / 256 + 1;
+  reduce_unpack_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(pk, v0, n, labels, probs);
+}
+
 __global__ void f32_to_act_kernel(const float* in, uint16_t* out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)

@@ -137,6 +137,23 @@ class Engine:
         _lib.check(self.lib.vsb_unpack_device(self.h, C.c_void_p(labels_ptr),
                                               C.c_void_p(probs_ptr) if probs_ptr else None))
 
+    # -- multi-GPU peer exchange ---------------------------------------------------
+    def keys_ipc_handle(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        _lib.check(self.lib.vsb_keys_ipc_export(self.h, buf))
+        return bytes(buf)
+
+    def open_peers(self, handles: "list[bytes]", my_rank: int) -> None:
+        blob = (C.c_uint8 * (64 * len(handles))).from_buffer_copy(b"".join(handles))
+        _lib.check(self.lib.vsb_peers_open(self.h, len(handles), my_rank, blob))
+
+    def close_peers(self) -> None:
+        _lib.check(self.lib.vsb_peers_close(self.h))
+
+    def reduce_unpack_shard(self, v0: int, v1: int, labels_ptr: int, probs_ptr: int = 0) -> None:
+        _lib.check(self.lib.vsb_reduce_unpack_shard(self.h, v0, v1, C.c_void_p(labels_ptr),
+                                                    C.c_void_p(probs_ptr) if probs_ptr else None))
+
     def set_vote_mode(self, on: bool) -> None:
         _lib.check(self.lib.vsb_set_vote_mode(self.h, int(on)))
 

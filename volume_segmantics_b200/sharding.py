@@ -84,6 +84,14 @@ def partition(shape_zyx: Sequence[int], dirs: Sequence[int], world: int, granule
     return shares
 
 
+def voxel_shards(nvox: int, world: int, align: int = 8) -> List[Tuple[int, int]]:
+    """Contiguous voxel ranges, one per rank, for the fused peer reduce + unpack
+    (cut on multiples of `align` voxels so 16-byte key loads stay aligned)."""
+    per = -(-nvox // world)
+    per = -(-per // align) * align
+    return [(min(r * per, nvox), min((r + 1) * per, nvox)) for r in range(world)]
+
+
 # ---- packed keys on the host (tests, diagnostics) -----------------------------
 def pack_keys_np(prob_f32: np.ndarray, labels: np.ndarray, d: int) -> np.ndarray:
     """Host restatement of the device key layout (csrc/kernels.h pack_key)."""
