@@ -62,6 +62,25 @@ __device__ __forceinline__ void issue_slab_resident(uint32_t d_tmem, uint64_t a_
   }
 }
 
+// Same, skipping the K-steps whose weights are all zero (bit tap*KSTEPS+k of `mask` clear).
+template <int NTAPS, int KSTEPS>
+__device__ __forceinline__ void issue_slab_masked(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t b_step,
+                                                  uint32_t row_units, uint32_t col_units, uint32_t idesc,
+                                                  bool accumulate_first, uint64_t mask) {
+  uint32_t acc = accumulate_first ? 1u : 0u;
+#pragma unroll
+  for (int tap = 0; tap < NTAPS; ++tap) {
+    const uint64_t at = desc_add(a_desc, (tap / 3) * row_units + (tap % 3) * col_units);
+    const uint64_t bt = desc_add(b_desc, tap * b_step);
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k)
+      if ((mask >> (tap * KSTEPS + k)) & 1ull) {
+        umma_bf16_ss(d_tmem, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc, acc);
+        acc = 1u;
+      }
+  }
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(HALO_THREADS, 1)
@@ -183,8 +202,12 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         const uint64_t a_stage_desc = desc_add(a_desc0, as * a_step);
         if (resident) {
           if (elect_one()) {
-            issue_slab_resident<9, 4>(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), b_step, row_units,
-                                      col_units, idesc, cs != 0);
+            if (p.use_kmask)
+              issue_slab_masked<9, 4>(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), b_step, row_units,
+                                      col_units, idesc, cs != 0, p.kmask[cs]);
+            else
+              issue_slab_resident<9, 4>(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), b_step, row_units,
+                                        col_units, idesc, cs != 0);
             umma_commit(&ctl->a_empty[as]);
             if (cs == p.ncs - 1) umma_commit(&ctl->acc_full[acc]);
           }

@@ -20,6 +20,7 @@
 
 namespace vsb {
 
+constexpr int HALO_KMASK_SLABS = 4;
 struct ConvHaloParams {
   const TmaDesc* map;        // plain 5-D map (c, x, 1, y, n), box {64, 8+2d, 1, 16+2d, 1}
   const uint8_t* wpacked;    // [n_tile][slab][tap] images of [BN][64] pre-swizzled rows
@@ -37,6 +38,10 @@ struct ConvHaloParams {
   int32_t a_stages, a_stage_bytes;
   int32_t b_stages;          // 0: all weights resident in shared memory
   int32_t b_bytes;           // BN * 128
+  // Resident-weight launches only: bit tap*4+k of kmask[slab] = the K-step (tap, channels
+  // 16k..16k+15) has non-zero weights; the others are not issued (space-to-depth convs).
+  int32_t use_kmask;
+  uint64_t kmask[HALO_KMASK_SLABS];
 };
 
 // ---- generalised variant: the halo tile is assembled by four cp.async producer warps

@@ -467,6 +467,30 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
         }
     CK(cudaMalloc(&cp.d_whalo, hp.size()));
     CK(cudaMemcpy(cp.d_whalo, hp.data(), hp.size(), cudaMemcpyHostToDevice));
+    // K-steps (tap, 16-channel block) whose weights are all zero need no MMA (structured
+    // sparsity of the space-to-depth convolutions, plan.py): bit tap*4+k of kmask[slab].
+    cp.hparams.use_kmask = 0;
+    if (cp.n_tiles == 1 && ncs <= vsb::HALO_KMASK_SLABS) {
+      bool any_zero = false;
+      for (int cs = 0; cs < ncs; ++cs) {
+        uint64_t m = 0;
+        for (int tap = 0; tap < 9; ++tap)
+          for (int k = 0; k < 4; ++k) {
+            bool nz = false;
+            const uint8_t* im = hp.data() + ((size_t)cs * 9 + tap) * img;
+            for (int n = 0; n < cp.BN && !nz; ++n)
+              for (int ch = 2 * k; ch < 2 * k + 2 && !nz; ++ch) {
+                const uint64_t* q = reinterpret_cast<const uint64_t*>(im + (size_t)n * 128 + ((ch ^ (n & 7)) * 16));
+                nz = (q[0] | q[1]) != 0;
+              }
+            if (nz) m |= 1ull << (tap * 4 + k);
+            else any_zero = true;
+          }
+        cp.hparams.kmask[cs] = m;
+      }
+      cp.hparams.kmask[0] |= 1ull;  // the first MMA of a tile initialises the accumulator
+      cp.hparams.use_kmask = any_zero ? 1 : 0;
+    }
   }
   cp.halo2_ok = false;
   if (!cp.halo_ok && !cp.s2 && op.kh == 3 && op.kw == 3 && op.pad == 1 && op.dil == 1) {
@@ -1132,7 +1156,7 @@ int predict_range(vsb_engine* e, int d, int64_t s_begin, int64_t s_end) {
       for (int i = 0; i < (int)e->ops.size(); ++i)
         if (e->ops[i].kind == VSB_OP_HEAD) hidx = i;
       if (hidx >= 0 && !e->vote_mode && !e->no_fuse_head && !e->no_halo && e->conv_impl == 0 &&
-          e->num_classes <= 8 && (e->ops[hidx].factor <= 1)) {
+          e->num_classes <= 8 && (e->ops[hidx].factor <= 1) && e->ops[hidx].mode == 0) {
         const int lt = e->ops[hidx].src[0];
         for (int i = 0; i < hidx; ++i)
           if (e->ops[i].kind == VSB_OP_CONV && e->ops[i].out == lt && e->conv[i].tc && e->conv[i].use_halo2 &&
@@ -1168,6 +1192,7 @@ int predict_range(vsb_engine* e, int d, int64_t s_begin, int64_t s_end) {
     h.logits = (const float*)e->tens[hop.src[0]].ptr;
     h.C = e->num_classes;
     h.factor = hop.factor > 0 ? hop.factor : 1;
+    h.s2d = hop.mode == 1;
     h.nb = nb;
     h.g = g;
     h.d = d;
@@ -1286,6 +1311,11 @@ int vsb_load_plan(vsb_engine* e, const vsb_tensor_desc* tensors, int32_t n_tenso
       if (op.src[s] < 0 || op.src[s] >= n_tensors) return fail(VSB_ERR_INVALID, "op %d: src id", i);
     if (op.kind != VSB_OP_HEAD && (op.out <= 0 || op.out >= n_tensors)) return fail(VSB_ERR_INVALID, "op %d: out id", i);
     if (op.res >= n_tensors) return fail(VSB_ERR_INVALID, "op %d: res id", i);
+    if (op.kind == VSB_OP_HEAD && op.mode == 1) {
+      const vsb_tensor_desc& lt = e->tdesc[op.src[0]];
+      if (num_classes > 8 || op.factor > 1 || lt.dtype != 1 || lt.ds_log2 != 1 || lt.channels != 4 * num_classes)
+        return fail(VSB_ERR_INVALID, "op %d: space-to-depth head needs f32 logits [Hp/2, Wp/2, 4*classes], classes <= 8", i);
+    }
     if (op.kind == VSB_OP_CONV) {
       if (op.groups < 1 || op.cin % op.groups || op.cout % op.groups) return fail(VSB_ERR_INVALID, "op %d: groups", i);
       const size_t wb = (size_t)op.cout * op.kh * op.kw * (op.cin / op.groups) * 2;
@@ -1561,14 +1591,31 @@ int vsb_forward_logits(vsb_engine* e, const float* images, int32_t nb, int32_t H
       return rc;
     }
   }
+  std::vector<float> s2d;  // space-to-depth logits are un-shuffled on the host (test hook, not the hot path)
   if (err == cudaSuccess && head >= 0) {
     const vsb_op& hop = e->ops[head];
     const TensorBuf& lt = e->tens[hop.src[0]];
-    err = cudaMemcpyAsync(logits, lt.ptr, (size_t)nb * lt.H * lt.W * lt.C * 4, cudaMemcpyDeviceToHost, e->stream);
+    const size_t cnt = (size_t)nb * lt.H * lt.W * lt.C;
+    float* dst = logits;
+    if (hop.mode == 1) {
+      s2d.resize(cnt);
+      dst = s2d.data();
+    }
+    err = cudaMemcpyAsync(dst, lt.ptr, cnt * 4, cudaMemcpyDeviceToHost, e->stream);
   }
   if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
   cudaFree(dimg);
   CK(err);
+  if (!s2d.empty()) {
+    const int C = e->num_classes, Hh = Hp / 2, Wh = Wp / 2;
+    for (int64_t n = 0; n < nb; ++n)
+      for (int i = 0; i < Hh; ++i)
+        for (int j = 0; j < Wh; ++j) {
+          const float* src = s2d.data() + ((n * Hh + i) * Wh + j) * 4 * C;
+          for (int q = 0; q < 4; ++q)
+            memcpy(logits + ((n * Hp + 2 * i + (q >> 1)) * Wp + 2 * j + (q & 1)) * C, src + q * C, (size_t)C * 4);
+        }
+  }
   prof_collect(e);
   if (head < 0) return fail(VSB_ERR_INVALID, "plan has no HEAD op");
   return VSB_OK;

@@ -38,8 +38,9 @@ struct ConvArgs {
 };
 
 struct HeadArgs {
-  const float* logits;  // f32 [nb, Hl, Wl, C]   (Hl = Hp/factor)
+  const float* logits;  // f32 [nb, Hl, Wl, C]   (Hl = Hp/factor); s2d: [nb, Hp/2, Wp/2, 4*C]
   int C, factor;        // factor > 1: bilinear align_corners=True upsampling
+  int s2d;              // 1: space-to-depth logits, channel (2a+b)*C + k = class k of pixel (2i+a, 2j+b)
   int nb;
   vsb_direction g;
   int d;
@@ -61,6 +62,7 @@ void launch_gap(const uint16_t* in, int NB, int H, int W, int C, uint16_t* out, 
 void launch_upsample(const uint16_t* in, int NB, int Hin, int Win, int C, int Hout, int Wout,
                      int mode, uint16_t* out, cudaStream_t st);
 void launch_head(const HeadArgs& a, cudaStream_t st);
+bool launch_head_s2d(const HeadArgs& a, cudaStream_t st);  // kernels_head.cu; false: class count not instantiated
 void launch_merge_injected(const float* probs, const uint8_t* labels, const vsb_direction& g, int d,
                            unsigned long long* keys, cudaStream_t st);
 void launch_unpack(const unsigned long long* keys, int64_t n, uint8_t* labels, uint16_t* probs,

@@ -32,89 +32,130 @@ __device__ __forceinline__ uint16_t normalise_u8(int v) {
 }
 
 // ---------------------------------------------------------------------------
-// Slicer, case A: image columns run along a unit-or-arbitrary stride; one
-// thread emits 8 consecutive padded pixels (one 16-byte store).
-// Replaces datasets.py:122 (vol[i] on the rotate_array_to_axis / np.rot90 view),
-// :125-127 (PadIfNeeded) and :129-135 (normalise).
+// Slicer.  Replaces datasets.py:122 (vol[i] on the rotate_array_to_axis / np.rot90 view),
+// :125-127 (PadIfNeeded) and :129-135 (normalise).  HBM-bound: 1 B read + 2 B written per
+// padded pixel.  The 256-entry normalisation table is replicated 32 times in shared memory
+// (entry [v][lane]) so the per-pixel lookups of a warp never collide on a bank.
 // ---------------------------------------------------------------------------
+struct SlicerLut {
+  uint16_t t[256][32];
+};
+__device__ __forceinline__ void slicer_lut_fill(SlicerLut& lut) {
+  // 256 threads: thread v computes entry v and writes its 32 copies
+  const uint32_t val = normalise_u8(threadIdx.x);
+  uint4 q;
+  q.x = q.y = q.z = q.w = val | (val << 16);
+  uint4* dst = reinterpret_cast<uint4*>(&lut.t[threadIdx.x][0]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dst[i] = q;
+}
+// 8 source bytes (two little-endian words) -> 8 normalised 16-bit pixels
+__device__ __forceinline__ uint4 slicer_lookup8(const SlicerLut& lut, uint32_t lo, uint32_t hi, int lane) {
+  uint4 o;
+  o.x = lut.t[lo & 0xff][lane] | ((uint32_t)lut.t[(lo >> 8) & 0xff][lane] << 16);
+  o.y = lut.t[(lo >> 16) & 0xff][lane] | ((uint32_t)lut.t[lo >> 24][lane] << 16);
+  o.z = lut.t[hi & 0xff][lane] | ((uint32_t)lut.t[(hi >> 8) & 0xff][lane] << 16);
+  o.w = lut.t[(hi >> 16) & 0xff][lane] | ((uint32_t)lut.t[hi >> 24][lane] << 16);
+  return o;
+}
+
+// Case A: image columns are contiguous voxels (or any stride when the batch is small).
+// One warp = one padded image row; a lane emits 16 consecutive padded pixels per step
+// (one 16-byte load when the span is interior and aligned, two 16-byte stores).
 __global__ void __launch_bounds__(256) slicer_rows_kernel(const uint8_t* __restrict__ vol,
                                                           vsb_direction g, int64_t s0, int nb,
                                                           uint16_t* __restrict__ out) {
-  __shared__ uint16_t lut[256];
-  if (threadIdx.x < 256) lut[threadIdx.x] = normalise_u8(threadIdx.x);
+  __shared__ __align__(16) SlicerLut lut;
+  slicer_lut_fill(lut);
   __syncthreads();
-  const int64_t w8 = g.Wp >> 3;
-  const int64_t total = (int64_t)nb * g.Hp * w8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t pc0 = (i % w8) << 3;
-    const int64_t pr = (i / w8) % g.Hp;
-    const int64_t s = i / (w8 * g.Hp);
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)nb * g.Hp;
+  const int chunks = (int)(g.Wp >> 4);
+  for (int64_t rowid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); rowid < rows; rowid += (int64_t)gridDim.x * 8) {
+    const int64_t s = rowid / g.Hp, pr = rowid - s * g.Hp;
     const int64_t r = reflect101(pr - g.pad_top, g.H);
-    const int64_t rowbase = g.base + (s0 + s) * g.stride_s + r * g.stride_r;
-    const int64_t c0 = pc0 - g.pad_left;
-    uint32_t px[8];
-    const uint8_t* p = vol + rowbase + c0;
-    if (g.stride_c == 1 && c0 >= 0 && c0 + 7 < g.W && ((uintptr_t)p & 7) == 0) {
-      const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    const uint8_t* rowp = vol + g.base + (s0 + s) * g.stride_s + r * g.stride_r;
+    uint16_t* orow = out + rowid * g.Wp;
+    for (int ch = lane; ch < chunks; ch += 32) {
+      const int64_t c0 = (int64_t)ch * 16 - g.pad_left;
+      uint32_t w[4];
+      const uint8_t* p = rowp + c0;
+      if (g.stride_c == 1 && c0 >= 0 && c0 + 15 < g.W && ((uintptr_t)p & 15) == 0) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        px[j] = (v.x >> (8 * j)) & 0xff;
-        px[4 + j] = (v.y >> (8 * j)) & 0xff;
-      }
-    } else {
+        for (int q = 0; q < 4; ++q) {
+          uint32_t acc = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int64_t c = reflect101(c0 + j, g.W);
-        px[j] = __ldg(vol + rowbase + c * g.stride_c);
+          for (int j = 0; j < 4; ++j) {
+            const int64_t c = reflect101(c0 + 4 * q + j, g.W);
+            acc |= (uint32_t)__ldg(rowp + c * g.stride_c) << (8 * j);
+          }
+          w[q] = acc;
+        }
       }
+      uint4* o = reinterpret_cast<uint4*>(orow + ch * 16);
+      o[0] = slicer_lookup8(lut, w[0], w[1], lane);
+      o[1] = slicer_lookup8(lut, w[2], w[3], lane);
     }
-    uint4 o;
-    o.x = lut[px[0]] | ((uint32_t)lut[px[1]] << 16);
-    o.y = lut[px[2]] | ((uint32_t)lut[px[3]] << 16);
-    o.z = lut[px[4]] | ((uint32_t)lut[px[5]] << 16);
-    o.w = lut[px[6]] | ((uint32_t)lut[px[7]] << 16);
-    *reinterpret_cast<uint4*>(out + ((s * g.Hp + pr) * g.Wp + pc0)) = o;
   }
 }
 
-// Slicer, case B: the slice index runs along x (unit stride; directions
-// 2,5,8,11).  A 64-column x 32-slice tile is read with the slice index fastest
-// (32 contiguous bytes per column), transposed through shared memory and
-// written with the column index fastest (128 contiguous bytes per slice).
+// Case B: the slice index runs along x (unit stride; directions 2,5,8,11).  A tile of
+// 128 image columns x 32 slices is read with the slice index fastest (4 slices per 32-bit
+// load, 32 contiguous bytes per column), transposed through shared memory and written
+// with the column index fastest (16 bytes per lane, 256 contiguous bytes per slice row).
+constexpr int XP_COLS = 128;
+constexpr int XP_PITCH = XP_COLS + 4;  // bytes per slice row of the tile: conflict-free both ways
 __global__ void __launch_bounds__(256) slicer_xplane_kernel(const uint8_t* __restrict__ vol,
                                                             vsb_direction g, int64_t s0, int nb,
                                                             uint16_t* __restrict__ out) {
-  __shared__ uint16_t lut[256];
-  __shared__ uint8_t tile[64][36];
-  lut[threadIdx.x] = normalise_u8(threadIdx.x);
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const int64_t ctiles = (g.Wp + 63) >> 6;
+  __shared__ __align__(16) SlicerLut lut;
+  __shared__ __align__(16) uint8_t tile[32 * XP_PITCH];
+  slicer_lut_fill(lut);
+  const int lane = threadIdx.x & 31;
+  const int64_t ctiles = (g.Wp + XP_COLS - 1) / XP_COLS;
   const int64_t stiles = (nb + 31) >> 5;
   const int64_t total = g.Hp * ctiles * stiles;
+  const bool fast = ((s0 | g.base | g.stride_r | g.stride_c) & 3) == 0 && ((uintptr_t)vol & 3) == 0;
   for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
     const int64_t ct = t % ctiles;
     const int64_t pr = (t / ctiles) % g.Hp;
     const int64_t stile = t / (ctiles * g.Hp);
     const int64_t r = reflect101(pr - g.pad_top, g.H);
-    const int64_t sl = stile * 32 + tx;
+    const uint8_t* rowp = vol + g.base + (s0 + stile * 32) * g.stride_s + r * g.stride_r;
+    const int sl_left = (int)(nb - stile * 32 < 32 ? nb - stile * 32 : 32);
     __syncthreads();
-    for (int cc = ty; cc < 64; cc += 8) {
-      const int64_t pc = ct * 64 + cc;
-      uint8_t v = 0;
-      if (pc < g.Wp && sl < nb) {
+    // load: 8 lanes cover the 32 slices of one column, a warp covers 4 columns
+#pragma unroll
+    for (int it = 0; it < XP_COLS / 32; ++it) {
+      const int cc = it * 32 + (threadIdx.x >> 3), sg = threadIdx.x & 7;
+      const int64_t pc = ct * XP_COLS + cc;
+      uint32_t v = 0;
+      if (pc < g.Wp) {
         const int64_t c = reflect101(pc - g.pad_left, g.W);
-        v = __ldg(vol + g.base + (s0 + sl) * g.stride_s + r * g.stride_r + c * g.stride_c);
+        const uint8_t* p = rowp + c * g.stride_c + 4 * sg;
+        if (fast && 4 * sg + 3 < sl_left) {
+          v = __ldg(reinterpret_cast<const uint32_t*>(p));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (4 * sg + j < sl_left) v |= (uint32_t)__ldg(p + j) << (8 * j);
+        }
       }
-      tile[cc][tx] = v;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tile[(4 * sg + j) * XP_PITCH + cc] = (uint8_t)(v >> (8 * j));
     }
     __syncthreads();
-    for (int ss = ty; ss < 32; ss += 8) {
-      const int64_t s = stile * 32 + ss;
-      const int64_t pc = ct * 64 + 2 * tx;
-      if (s < nb && pc < g.Wp) {  // Wp is even
-        const uint32_t o = lut[tile[2 * tx][ss]] | ((uint32_t)lut[tile[2 * tx + 1][ss]] << 16);
-        *reinterpret_cast<uint32_t*>(out + ((s * g.Hp + pr) * g.Wp + pc)) = o;
+    // store: 16 lanes cover the 128 columns of one slice row, a warp covers 2 slices
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int ss = it * 16 + (threadIdx.x >> 4), k = threadIdx.x & 15;
+      const int64_t s = stile * 32 + ss, pc = ct * XP_COLS + 8 * k;
+      if (s < nb && pc < g.Wp) {  // Wp is a multiple of 32, so a chunk of 8 is all in or all out
+        const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile + ss * XP_PITCH + 8 * k);
+        *reinterpret_cast<uint4*>(out + ((s * g.Hp + pr) * g.Wp + pc)) = slicer_lookup8(lut, tw[0], tw[1], lane);
       }
     }
   }
@@ -123,13 +164,12 @@ __global__ void __launch_bounds__(256) slicer_xplane_kernel(const uint8_t* __res
 void launch_slicer(const uint8_t* vol, const vsb_direction& g, int64_t s0, int nb, uint16_t* out,
                    cudaStream_t st) {
   if (g.stride_s == 1 && nb >= 8) {
-    const int64_t total = g.Hp * ((g.Wp + 63) / 64) * ((nb + 31) / 32);
-    const int grid = (int)(total < 148 * 16 ? total : 148 * 16);
+    const int64_t total = g.Hp * ((g.Wp + XP_COLS - 1) / XP_COLS) * ((nb + 31) / 32);
+    const int grid = (int)(total < 148 * 8 ? total : 148 * 8);
     slicer_xplane_kernel<<<grid, 256, 0, st>>>(vol, g, s0, nb, out);
   } else {
-    const int64_t total = (int64_t)nb * g.Hp * (g.Wp / 8);
-    const int64_t blocks = (total + 255) / 256;
-    const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+    const int64_t blocks = ((int64_t)nb * g.Hp + 7) / 8;
+    const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
     slicer_rows_kernel<<<grid, 256, 0, st>>>(vol, g, s0, nb, out);
   }
 }
@@ -569,6 +609,10 @@ __global__ void __launch_bounds__(256) head_xplane_kernel(HeadArgs a) {
 }
 
 void launch_head(const HeadArgs& a, cudaStream_t st) {
+  if (a.s2d) {
+    launch_head_s2d(a, st);  // class counts are validated when the plan is loaded
+    return;
+  }
   if (!a.votes && a.g.stride_s == 1 && a.g.stride_c != 1 && a.nb >= 8) {
     const int64_t tiles = ((a.nb + 31) / 32) * a.g.H * ((a.g.W + 31) / 32);
     head_xplane_kernel<<<(int)(tiles < 148 * 16 ? tiles : 148 * 16), 256, 0, st>>>(a);

@@ -86,7 +86,8 @@ class B200SegmentationModel(nn.Module):
         return torch.from_numpy(logits).permute(0, 3, 1, 2).contiguous()
 
 
-def _fold(sd: Dict[str, torch.Tensor], L: Layer) -> Tuple[np.ndarray, np.ndarray]:
+def _fold_f32(sd: Dict[str, torch.Tensor], L: Layer) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Conv weight [O,I,kh,kw] and bias with the eval-mode BatchNorm folded in (fp32)."""
     w = sd[f"{L.name}.weight"].detach().to("cpu", torch.float32)
     b = sd[f"{L.name}.bias"].detach().to("cpu", torch.float32) if L.has_bias else torch.zeros(L.cout)
     if L.bn:
@@ -97,11 +98,108 @@ def _fold(sd: Dict[str, torch.Tensor], L: Layer) -> Tuple[np.ndarray, np.ndarray
         scale = g / torch.sqrt(var + BN_EPS)
         w = w * scale[:, None, None, None]
         b = (b - mean) * scale + beta
+    return w, b
+
+
+def _pack(w: torch.Tensor, b: torch.Tensor) -> Tuple[np.ndarray, np.ndarray]:
+    """fp32 OIHW weights -> the library's 16-bit format in OHWI order; bias stays fp32."""
     w_ohwi = w.permute(0, 2, 3, 1).contiguous()
     if _lib.act_dtype() == torch.float16:
         w_ohwi = w_ohwi.clamp(-65504.0, 65504.0)
     w_ohwi = w_ohwi.to(_lib.act_dtype())
     return w_ohwi.view(torch.int16).numpy().view(np.uint16), b.numpy().astype(np.float32)
+
+
+def _fold(sd: Dict[str, torch.Tensor], L: Layer) -> Tuple[np.ndarray, np.ndarray]:
+    return _pack(*_fold_f32(sd, L))
+
+
+# ---------------------------------------------------------------------------
+# Space-to-depth ("S2D") tail.
+#
+# The last decoder block of smp's Unet / UnetPlusPlus is  nearest-x2 upsample ->
+# conv3x3(Cin->16)+BN+ReLU -> conv3x3(16->16)+BN+ReLU, followed by the 3x3 segmentation
+# head (16->classes), all at full resolution with GEMM N = 16: the tensor pipe idles
+# while the shared-memory A operand streams.  The three convolutions are rewritten, with
+# identical arithmetic up to summation order, as 3x3 convolutions at HALF resolution whose
+# channels carry the 2x2 sub-pixels (channel = (2*a + b) * C + c for output pixel
+# (2i+a, 2j+b)), so N becomes 4*16 = 64:
+#   * upsample -> conv: every output sub-pixel sees the 3x3 low-resolution
+#     neighbourhood; taps that land on the same source pixel are summed (in fp32, before
+#     the one rounding to 16 bit) -- the same multiply-accumulate count as the original;
+#   * conv on an S2D tensor: the 4x4 input patch of a 2x2 output block, spread over
+#     the 3x3 S2D neighbourhood; 20 of the 36 (tap, sub-pixel) K-blocks are zero and the
+#     engine skips them (it scans the packed weights for all-zero K-steps).
+# The logits tensor is [Hp/2, Wp/2, 4*classes]; the HEAD op carries mode = 1 and the
+# head kernel reads four voxels per thread.
+# ---------------------------------------------------------------------------
+def s2d_upconv_weights(w: torch.Tensor) -> torch.Tensor:
+    """[O,I,3,3] of `nearest-x2 upsample -> conv3x3 pad 1`  ->  [4*O,I,3,3] conv3x3 pad 1 on the
+    low-resolution source producing the S2D output."""
+    o, i = w.shape[:2]
+    out = torch.zeros(4, o, i, 3, 3, dtype=torch.float32)
+    for a in (0, 1):
+        for b in (0, 1):
+            for ky in range(3):
+                dy = (a + ky - 1) // 2  # source row offset of up-sampled row 2i+a+ky-1
+                for kx in range(3):
+                    dx = (b + kx - 1) // 2
+                    out[a * 2 + b, :, :, dy + 1, dx + 1] += w[:, :, ky, kx]
+    return out.reshape(4 * o, i, 3, 3)
+
+
+def s2d_conv_weights(w: torch.Tensor) -> torch.Tensor:
+    """[O,I,3,3] conv3x3 pad 1 at full resolution -> [4*O,4*I,3,3] conv3x3 pad 1 between S2D tensors."""
+    o, i = w.shape[:2]
+    out = torch.zeros(4, o, 4, i, 3, 3, dtype=torch.float32)
+    for a in (0, 1):
+        for b in (0, 1):
+            for ky in range(3):
+                r = a + ky - 1
+                dy, a2 = r // 2, r % 2
+                for kx in range(3):
+                    c = b + kx - 1
+                    dx, b2 = c // 2, c % 2
+                    out[a * 2 + b, :, a2 * 2 + b2, :, dy + 1, dx + 1] = w[:, :, ky, kx]
+    return out.reshape(4 * o, 4 * i, 3, 3)
+
+
+def find_s2d_tail(spec: NetSpec):
+    """Indices (A, B, H, head) of the layers the S2D rewrite applies to, or None."""
+    import os
+
+    if os.environ.get("VSB200_S2D_TAIL", "1") == "0":
+        return None
+    layers = spec.layers
+    if not layers or layers[-1].kind != "head" or layers[-1].factor != 1 or spec.classes > 8:
+        return None
+    producer = {L.out: i for i, L in enumerate(layers) if L.out >= 0}
+    uses: Dict[int, int] = {}
+    for L in layers:
+        for t, _ in L.srcs:
+            uses[t] = uses.get(t, 0) + 1
+        if L.res >= 0:
+            uses[L.res] = uses.get(L.res, 0) + 1
+
+    def plain3x3(L: Layer) -> bool:
+        return (L.kind == "conv" and L.k == 3 and L.pad == 1 and L.stride == 1 and L.dil == 1 and L.groups == 1
+                and L.res < 0 and len(L.srcs) == 1)
+
+    hi = producer.get(layers[-1].srcs[0][0])
+    if hi is None or not plain3x3(layers[hi]) or layers[hi].srcs[0][1] or uses.get(layers[hi].out) != 1:
+        return None
+    bi = producer.get(layers[hi].srcs[0][0])
+    if bi is None or not plain3x3(layers[bi]) or layers[bi].srcs[0][1] or uses.get(layers[bi].out) != 1:
+        return None
+    ai = producer.get(layers[bi].srcs[0][0])
+    if ai is None or not plain3x3(layers[ai]) or not layers[ai].srcs[0][1] or uses.get(layers[ai].out) != 1:
+        return None
+    A, B = layers[ai], layers[bi]
+    if A.cin % 16 or A.cout % 16 or B.cout % 16 or spec.tensors[A.out].ds_log2 != 0:
+        return None
+    if spec.tensors[A.out].dtype or spec.tensors[B.out].dtype or not spec.tensors[layers[hi].out].dtype:
+        return None
+    return ai, bi, hi, len(layers) - 1
 
 
 class Plan:
@@ -114,9 +212,14 @@ class Plan:
 def lower_to_plan(model: B200SegmentationModel) -> Plan:
     spec = model.spec
     sd = model.state_dict()
+    tail = find_s2d_tail(spec)
     tensors = (_lib.TensorDesc * len(spec.tensors))()
     for i, t in enumerate(spec.tensors):
         tensors[i] = _lib.TensorDesc(t.channels, t.ds_log2, t.dtype, 0)
+    if tail:
+        for li in tail[:3]:  # S2D tensors: 4x the channels at half the resolution
+            t = spec.tensors[spec.layers[li].out]
+            tensors[spec.layers[li].out] = _lib.TensorDesc(4 * t.channels, t.ds_log2 + 1, t.dtype, 0)
     ops = (_lib.Op * len(spec.layers))()
     chunks, off = [], 0
 
@@ -146,11 +249,22 @@ def lower_to_plan(model: B200SegmentationModel) -> Plan:
         op.w_off = op.b_off = -1
         op.mode, op.factor = L.mode, L.factor
         if L.kind == "conv":
-            w, b = _fold(sd, L)
-            op.cin, op.cout, op.kh, op.kw = L.cin, L.cout, L.k, L.k
+            wf, bf = _fold_f32(sd, L)
+            cin, cout = L.cin, L.cout
+            if tail and i == tail[0]:
+                wf, bf = s2d_upconv_weights(wf), bf.repeat(4)
+                cout = 4 * cout
+                op.src_up[0] = 0
+            elif tail and i in tail[1:3]:
+                wf, bf = s2d_conv_weights(wf), bf.repeat(4)
+                cin, cout = 4 * cin, 4 * cout
+            w, b = _pack(wf, bf)
+            op.cin, op.cout, op.kh, op.kw = cin, cout, L.k, L.k
             op.stride, op.pad, op.dil, op.groups, op.relu = L.stride, L.pad, L.dil, L.groups, int(L.relu)
             op.w_off = add(w)
             op.b_off = add(b)
+        elif tail and i == tail[3]:
+            op.mode = 1  # logits are S2D: [Hp/2, Wp/2, 4*classes]
         ops[i] = op
     blob = np.concatenate(chunks) if chunks else np.zeros(1, np.uint8)
     return Plan(tensors, ops, blob, spec.classes)
