@@ -177,7 +177,9 @@ int vsb_set_conv_impl(vsb_engine* e, int32_t impl);
 /* Tuning / cross-check switches: "halo" (1: halo-tile conv kernels, default),
  * "fuse_head" (1: softmax/argmax/merge inside the last conv's epilogue; default 0:
  *   bit-identical, but measured slower than the separate head kernel),
- * "sub_batch_mb" (L2 budget for depth-first sub-batches, 0 = off, default).      */
+ * "sub_batch_mb" (L2 budget for depth-first sub-batches, 0 = off, default),
+ * "tma_epilogue" (1: halo-kernel epilogue through shared memory + TMA store, default),
+ * "halo_a_stages" (maximum depth of the halo ring, 2..8, default 8).              */
 int vsb_set_flag(vsb_engine* e, const char* name, int32_t value);
 
 /* ---- test hooks (bit-exact criteria of BASELINE.json) ---------------------

@@ -19,6 +19,10 @@ eng = Engine(0)
 eng.load_model(model)
 if batch:
     eng.set_batch(batch)
+import os  # noqa: E402
+for kv in filter(None, os.environ.get("VSB_FLAGS", "").split(",")):  # e.g. VSB_FLAGS=tma_epilogue=0,halo_a_stages=4
+    k, v = kv.split("=")
+    eng.set_flag(k, int(v))
 vol = np.random.default_rng(0).integers(0, 256, (nslices, size, size), dtype=np.uint8)
 eng.set_volume(vol)
 eng.predict_range(0, 0, nslices)

@@ -82,19 +82,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must never hang the GPU box (that is a strike).
-// After ~4 s of wall clock the CTA traps and the launch reports an error.
-__device__ __forceinline__ uint64_t global_timer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
+// Bounded wait: a protocol bug must never hang the GPU box (that is a strike).  The poll
+// loop itself stays minimal (try_wait suspends in hardware); the clock is read only every
+// 4096 polls and the CTA traps after ~2^33 cycles (seconds) without progress.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
+  uint32_t polls = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (global_timer_ns() - t0 > 4000000000ull) {
-      asm volatile("trap;");
+    if ((++polls & 4095u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > (1ll << 33)) asm volatile("trap;");
     }
   }
 }

@@ -18,22 +18,58 @@ struct HaloCtl {
   uint64_t b_full[HALO_MAX_B_STAGES];
   uint64_t b_empty[HALO_MAX_B_STAGES];
   uint64_t w_full;
-  uint64_t acc_full[2];
-  uint64_t acc_empty[2];
+  uint64_t acc_full[8];
+  uint64_t acc_empty[8];
+  uint64_t res_full[2];
+  uint64_t res_empty[2];
   uint32_t tmem_base;
   uint32_t pad[3];
 };
+// Cycle accounting slots (CTA 0, one lane per role): producer 0..3 = {total, wait a_empty, tiles, -};
+// MMA 4..7 = {total, wait acc_empty, wait a_full, issue}; epilogue group 0 issuer 8..15 =
+// {total, wait store-read, wait acc_full, tmem_ld+bar1, math+sts, arrive+fence+bar2, store issue, tiles}.
+__device__ __forceinline__ long long dev_clock() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+  return t;
+}
+struct ProfClock {
+  unsigned long long* out;
+  long long t;
+  __device__ __forceinline__ ProfClock(unsigned long long* o) : out(o), t(o ? dev_clock() : 0) {}
+  __device__ __forceinline__ void lap(int slot) {
+    if (out) {
+      const long long n = dev_clock();
+      out[slot] += (unsigned long long)(n - t);
+      t = n;
+    }
+  }
+};
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 constexpr int kHaloCtlBytes = 1024;
 constexpr int kHaloBiasBytes = 2048 * 4;
 
 __device__ __forceinline__ void halo_decode(const ConvHaloParams& p, int t, int& n_tile, int& X0, int& Y0,
                                             int& n) {
-  n_tile = t % p.n_tiles;
-  int sp = t / p.n_tiles;
-  const int tx = sp % p.tiles_x;
-  sp /= p.tiles_x;
-  const int ty = sp % p.tiles_y;
-  n = sp / p.tiles_y + p.n_base;
+  auto fdiv = [](uint32_t v, const FastDiv& f) { return f.m ? __umulhi(v, f.m) : v; };
+  uint32_t sp = fdiv((uint32_t)t, p.div_n_tiles);
+  n_tile = t - (int)(sp * p.div_n_tiles.d);
+  uint32_t q = fdiv(sp, p.div_tx);
+  const int tx = (int)(sp - q * p.div_tx.d);
+  sp = q;
+  q = fdiv(sp, p.div_ty);
+  const int ty = (int)(sp - q * p.div_ty.d);
+  n = (int)q + p.n_base;
   X0 = tx * 8;
   Y0 = ty * 16;
 }
@@ -91,14 +127,18 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   uint8_t* a_ring = smem;
   uint8_t* b_area = smem + (size_t)p.a_stages * p.a_stage_bytes;
   const size_t b_area_bytes = p.b_stages ? (size_t)p.b_stages * p.b_bytes : (size_t)p.ncs * 9 * p.b_bytes;
-  HaloCtl* ctl = reinterpret_cast<HaloCtl*>(b_area + b_area_bytes);
+  uint8_t* out_stage = b_area + b_area_bytes;
+  uint8_t* res_stage = out_stage + (size_t)p.out_bufs * p.out_buf_bytes;
+  HaloCtl* ctl = reinterpret_cast<HaloCtl*>(res_stage + (size_t)p.res_bufs * p.out_buf_bytes);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + kHaloCtlBytes);
+  float* const bias_l = bias_s;  // launch-relative index (tile-local channel)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.n_tiles * p.tiles_x * p.tiles_y * p.NB;
   const int HW = 8 + 2 * p.dil, HH = 16 + 2 * p.dil;
   const bool resident = p.b_stages == 0;
+  const uint32_t acc_cols = 512u / (uint32_t)p.acc_stages;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_stages; ++i) {
@@ -110,9 +150,14 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       mbar_init(&ctl->b_empty[i], 1);
     }
     mbar_init(&ctl->w_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    const int epi_threads = 32 * HALO_EPI_WARPS / (p.epi_groups == 2 ? 2 : 1);
+    for (int i = 0; i < 8; ++i) {
       mbar_init(&ctl->acc_full[i], 1);
-      mbar_init(&ctl->acc_empty[i], 32 * HALO_EPI_WARPS);
+      mbar_init(&ctl->acc_empty[i], epi_threads);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->res_full[i], 1);
+      mbar_init(&ctl->res_empty[i], epi_threads);
     }
     fence_mbar_init();
   }
@@ -130,15 +175,44 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     int as = 0;
     uint32_t aph = 0;
     const uint32_t a_box_bytes = (uint32_t)(HW * HH * 128);
+    int rb = 0;
+    uint32_t rph = 0;
+    unsigned long long* pr = (p.prof && blockIdx.x == 0 && lane == 0) ? p.prof : nullptr;
+    const long long pstart = pr ? dev_clock() : 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n_tile, X0, Y0, n;
       halo_decode(p, t, n_tile, X0, Y0, n);
-      for (int cs = 0; cs < p.ncs; ++cs) {
-        mbar_wait(&ctl->a_empty[as], aph ^ 1);
+      if (pr) pr[2] += 1;
+      if (p.res_map) {
+        // residual tile of this output tile, in the epilogue's staging layout
+        mbar_wait(&ctl->res_empty[rb], rph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&ctl->a_full[as], a_box_bytes);
-          tma_load_5d(p.map, &ctl->a_full[as], a_ring + (size_t)as * p.a_stage_bytes, p.cin_off + cs * 64, X0 - p.dil, 0,
-                      Y0 - p.dil, n);
+          const int groups = p.BN >> 6;
+          mbar_arrive_expect_tx(&ctl->res_full[rb], (uint32_t)(groups * 16384));
+          for (int g = 0; g < groups; ++g)
+            tma_load_5d(p.res_map, &ctl->res_full[rb], res_stage + (size_t)rb * p.out_buf_bytes + g * 16384,
+                        p.cout_off + n_tile * p.BN + g * 64, X0, 0, Y0, n);
+        }
+        __syncwarp();
+        if (++rb == p.res_bufs) {
+          rb = 0;
+          rph ^= 1;
+        }
+      }
+      for (int cs = 0; cs < p.ncs; ++cs) {
+        {
+          ProfClock pc(pr);
+          mbar_wait(&ctl->a_empty[as], aph ^ 1);
+          pc.lap(1);
+        }
+        if (elect_one()) {
+          if (p.dbg & 1) {
+            mbar_arrive(&ctl->a_full[as]);
+          } else {
+            mbar_arrive_expect_tx(&ctl->a_full[as], a_box_bytes);
+            tma_load_5d(p.map, &ctl->a_full[as], a_ring + (size_t)as * p.a_stage_bytes, p.cin_off + cs * 64, X0 - p.dil, 0,
+                        Y0 - p.dil, n);
+          }
         }
         __syncwarp();
         if (++as == p.a_stages) {
@@ -147,6 +221,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         }
       }
     }
+    if (pr) pr[0] += (unsigned long long)(dev_clock() - pstart);
   } else if (warp == 2) {
     // ===================== B producer: weight images =====================
     if (resident) {
@@ -192,17 +267,26 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     const uint32_t row_units = (uint32_t)(p.dil * HW * 8);  // one dilated halo row, in 16-byte units
     const uint32_t col_units = (uint32_t)(p.dil * 8);
     if (resident) mbar_wait(&ctl->w_full, 0);
+    unsigned long long* pr = (p.prof && blockIdx.x == 0 && lane == 0) ? p.prof : nullptr;
+    const long long mstart = pr ? dev_clock() : 0;
+    ProfClock pc(pr);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      pc.lap(7);
       mbar_wait(&ctl->acc_empty[acc], acc_phase ^ 1);
+      pc.lap(5);
       tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
       for (int cs = 0; cs < p.ncs; ++cs) {
+        pc.lap(7);
         mbar_wait(&ctl->a_full[as], aph);
+        pc.lap(6);
         tc_fence_after_sync();
         const uint64_t a_stage_desc = desc_add(a_desc0, as * a_step);
         if (resident) {
           if (elect_one()) {
-            if (p.use_kmask)
+            if (p.dbg & 2)
+              umma_bf16_ss(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), idesc, cs != 0 ? 1u : 0u);
+            else if (p.use_kmask)
               issue_slab_masked<9, 4>(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), b_step, row_units,
                                       col_units, idesc, cs != 0, p.kmask[cs]);
             else
@@ -242,11 +326,147 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           aph ^= 1;
         }
       }
-      if (++acc == 2) {
+      if (++acc == p.acc_stages) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    if (pr) pr[4] += (unsigned long long)(dev_clock() - mstart);
+  } else if (p.out_map) {
+    // ===================== epilogue through shared memory + TMA store =====================
+    // One group of eight warps (columns split in halves) or, for BN <= 64, two groups of four
+    // warps on alternate tiles (a thread owns all BN columns of its row).  Tile `it` (CTA-local
+    // count) uses accumulator stage it % acc_stages, residual buffer it % res_bufs and, with two
+    // groups, staging buffer = group; all three are even-periodic, so a group always meets the
+    // same stages and buffers.
+    const int G = p.epi_groups == 2 ? 2 : 1;
+    const int quarter = warp & 3;
+    const int half = (warp - 3) >> 2;
+    const int grp = G == 2 ? half : 0;
+    const int row = quarter * 32 + lane;
+    const int gthreads = 32 * HALO_EPI_WARPS / G;
+    const bool issuer = threadIdx.x == 96 + grp * 128;
+    const bool has_res = p.res_map != nullptr;
+    const uint32_t out_addr0 = smem_u32(out_stage), res_addr0 = smem_u32(res_stage);
+    const uint32_t f32_pitch = (uint32_t)p.cout * 4u;
+    const int c_begin = G == 2 ? 0 : half * 32, c_step = G == 2 ? 32 : 64;
+    const float* bt = bias_l;  // n_tiles == 1 on this path
+    int it = grp;
+    unsigned long long* pr = (p.prof && blockIdx.x == 0 && threadIdx.x == 96) ? p.prof : nullptr;
+    const long long estart = pr ? dev_clock() : 0;
+    ProfClock pc(pr);
+    for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles; t += G * gridDim.x, it += G) {
+      if (pr) pr[15] += 1;
+      pc.lap(14);
+      const int acc = it % p.acc_stages;
+      const uint32_t acc_phase = (uint32_t)(it / p.acc_stages) & 1u;
+      const int ob = G == 2 ? grp : it % p.out_bufs;
+      const int rb = has_res ? it % p.res_bufs : 0;
+      const uint32_t rph = has_res ? (uint32_t)(it / p.res_bufs) & 1u : 0u;
+      const uint32_t ost = out_addr0 + (uint32_t)ob * p.out_buf_bytes;
+      const uint32_t rst = res_addr0 + (uint32_t)rb * p.out_buf_bytes;
+      // the staging buffer is free once the TMA store issued from it has read it
+      if (issuer) {
+        if (G == 1 && p.out_bufs == 2) tma_store_wait_read<1>();
+        else tma_store_wait_read<0>();
+      }
+      pc.lap(9);
+      mbar_wait(&ctl->acc_full[acc], acc_phase);
+      pc.lap(10);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(quarter * 32) << 16);
+      if (!p.out_f32) {
+        for (int c = c_begin; c < p.BN; c += c_step) {
+          uint32_t v[32];
+          if (p.dbg & 8) {
+#pragma unroll
+            for (int z = 0; z < 32; ++z) v[z] = (uint32_t)row;
+          } else {
+            tmem_ld_32x32b_x32(taddr + c, v);
+            tmem_ld_wait();
+          }
+          if (c == c_begin) {
+            if (has_res) mbar_wait(&ctl->res_full[rb], rph);
+            if (!(p.dbg & 16)) named_bar_sync(1 + 2 * grp, gthreads);
+            pc.lap(11);
+          }
+          const uint32_t row_off = (uint32_t)(c >> 6) * 16384u + (uint32_t)row * 128u;
+          const int j0 = (c & 63) >> 3;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t off = row_off + ((uint32_t)((j0 + q) ^ (row & 7)) << 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(bt + c + q * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bt + c + q * 8 + 4);
+            float f0 = __uint_as_float(v[q * 8 + 0]) + b0.x, f1 = __uint_as_float(v[q * 8 + 1]) + b0.y;
+            float f2 = __uint_as_float(v[q * 8 + 2]) + b0.z, f3 = __uint_as_float(v[q * 8 + 3]) + b0.w;
+            float f4 = __uint_as_float(v[q * 8 + 4]) + b1.x, f5 = __uint_as_float(v[q * 8 + 5]) + b1.y;
+            float f6 = __uint_as_float(v[q * 8 + 6]) + b1.z, f7 = __uint_as_float(v[q * 8 + 7]) + b1.w;
+            if (has_res) {
+              const uint4 rv = lds128(rst + off);
+              float2 r;
+              r = unpack_act2(rv.x); f0 += r.x; f1 += r.y;
+              r = unpack_act2(rv.y); f2 += r.x; f3 += r.y;
+              r = unpack_act2(rv.z); f4 += r.x; f5 += r.y;
+              r = unpack_act2(rv.w); f6 += r.x; f7 += r.y;
+            }
+            uint4 pk;
+            if (p.relu) {
+              pk.x = pack2<true>(f0, f1); pk.y = pack2<true>(f2, f3); pk.z = pack2<true>(f4, f5); pk.w = pack2<true>(f6, f7);
+            } else {
+              pk.x = pack2<false>(f0, f1); pk.y = pack2<false>(f2, f3); pk.z = pack2<false>(f4, f5); pk.w = pack2<false>(f6, f7);
+            }
+            if (!(p.dbg & 32)) sts128(ost + off, pk);
+            else if (pk.x == 0x12345678u) sts128(ost + off, pk);
+          }
+        }
+      } else {
+        // f32 logits (cout <= 32): dense rows of cout floats, no swizzle
+        uint32_t v[32];
+        if (G == 2 || half == 0) {
+          tmem_ld_32x32b_x32(taddr, v);
+          tmem_ld_wait();
+        }
+        named_bar_sync(1 + 2 * grp, gthreads);
+        if (G == 2 || half == 0) {
+          const uint32_t row_off = (uint32_t)row * f32_pitch;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (q * 4 < p.cout) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bt + q * 4);
+              uint4 o;
+              float f0 = __uint_as_float(v[q * 4 + 0]) + b0.x, f1 = __uint_as_float(v[q * 4 + 1]) + b0.y;
+              float f2 = __uint_as_float(v[q * 4 + 2]) + b0.z, f3 = __uint_as_float(v[q * 4 + 3]) + b0.w;
+              if (p.relu) {
+                f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f);
+              }
+              o.x = __float_as_uint(f0); o.y = __float_as_uint(f1); o.z = __float_as_uint(f2); o.w = __float_as_uint(f3);
+              sts128(ost + row_off + q * 16, o);
+            }
+          }
+        }
+      }
+      pc.lap(12);
+      tc_fence_before_sync();
+      mbar_arrive(&ctl->acc_empty[acc]);
+      if (has_res) mbar_arrive(&ctl->res_empty[rb]);
+      if (!(p.dbg & 32)) fence_proxy_async_smem();
+      if (!(p.dbg & 16)) named_bar_sync(2 + 2 * grp, gthreads);
+      pc.lap(13);
+      if (issuer && !(p.dbg & 4)) {
+        int n_tile, X0, Y0, n;
+        halo_decode(p, t, n_tile, X0, Y0, n);
+        if (p.out_f32) {
+          tma_store_5d(p.out_map, out_stage + (size_t)ob * p.out_buf_bytes, 0, X0, 0, Y0, n);
+        } else {
+          for (int g = 0; g < (p.BN >> 6); ++g)
+            tma_store_5d(p.out_map, out_stage + (size_t)ob * p.out_buf_bytes + g * 16384, p.cout_off + g * 64, X0, 0, Y0,
+                         n);
+        }
+        tma_store_commit();
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+    if (pr) pr[8] += (unsigned long long)(dev_clock() - estart);
   } else {
     // ===================== epilogue =====================
     int acc = 0;
@@ -271,7 +491,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       }
       mbar_wait(&ctl->acc_full[acc], acc_phase);
       tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(quarter * 32) << 16);
       for (int c = half * 32; c < p.BN; c += 64) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c, v);
@@ -283,7 +503,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       }
       tc_fence_before_sync();
       mbar_arrive(&ctl->acc_empty[acc]);
-      if (++acc == 2) {
+      if (++acc == p.acc_stages) {
         acc = 0;
         acc_phase ^= 1;
       }
@@ -742,7 +962,8 @@ cudaError_t launch_conv_halo2(const ConvHalo2Params& p, int num_sms, cudaStream_
 
 size_t conv_halo_smem_bytes(const ConvHaloParams& p) {
   const size_t b = p.b_stages ? (size_t)p.b_stages * p.b_bytes : (size_t)p.ncs * 9 * p.b_bytes;
-  return (size_t)p.a_stages * p.a_stage_bytes + b + kHaloCtlBytes + kHaloBiasBytes + 1024;
+  return (size_t)p.a_stages * p.a_stage_bytes + b + (size_t)(p.out_bufs + p.res_bufs) * p.out_buf_bytes +
+         kHaloCtlBytes + kHaloBiasBytes + 1024;
 }
 
 cudaError_t conv_halo_configure() {
@@ -761,9 +982,16 @@ cudaError_t conv_halo_configure() {
   return e;
 }
 
-cudaError_t launch_conv_halo(const ConvHaloParams& p, int num_sms, cudaStream_t st) {
-  const int total_tiles = p.n_tiles * p.tiles_x * p.tiles_y * p.NB;
-  const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+cudaError_t launch_conv_halo(const ConvHaloParams& p0, int num_sms, cudaStream_t st) {
+  ConvHaloParams p = p0;
+  const int64_t total_tiles = (int64_t)p.n_tiles * p.tiles_x * p.tiles_y * p.NB;
+  const int64_t dmax = p.n_tiles > p.tiles_x ? (p.n_tiles > p.tiles_y ? p.n_tiles : p.tiles_y)
+                                             : (p.tiles_x > p.tiles_y ? p.tiles_x : p.tiles_y);
+  if (total_tiles * dmax >= (1ll << 32)) return cudaErrorInvalidValue;  // FastDiv exactness bound
+  p.div_n_tiles = make_fastdiv((uint32_t)p.n_tiles);
+  p.div_tx = make_fastdiv((uint32_t)p.tiles_x);
+  p.div_ty = make_fastdiv((uint32_t)p.tiles_y);
+  const int grid = total_tiles < num_sms ? (int)total_tiles : num_sms;
   conv_halo_kernel<<<grid, HALO_THREADS, conv_halo_smem_bytes(p), st>>>(p);
   return cudaGetLastError();
 }

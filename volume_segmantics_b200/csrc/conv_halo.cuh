@@ -21,6 +21,17 @@
 namespace vsb {
 
 constexpr int HALO_KMASK_SLABS = 4;
+// Division by a launch constant: q = umulhi(t, m) with m = ceil(2^32 / d), exact while
+// t * d < 2^32 (checked by the launcher); m == 0 encodes d == 1.
+struct FastDiv {
+  uint32_t d, m;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  f.m = d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d);
+  return f;
+}
 struct ConvHaloParams {
   const TmaDesc* map;        // plain 5-D map (c, x, 1, y, n), box {64, 8+2d, 1, 16+2d, 1}
   const uint8_t* wpacked;    // [n_tile][slab][tap] images of [BN][64] pre-swizzled rows
@@ -42,6 +53,32 @@ struct ConvHaloParams {
   // 16k..16k+15) has non-zero weights; the others are not issued (space-to-depth convs).
   int32_t use_kmask;
   uint64_t kmask[HALO_KMASK_SLABS];
+  // TMEM accumulator stages: 2, 4 or 8 stages of 512 / acc_stages columns (>= BN).  Narrow
+  // layers have so little MMA work per tile that two stages leave the MMA warp waiting for
+  // the epilogue's round trip; more stages hide it.
+  int32_t acc_stages;
+  // Shared-memory epilogue (out_map != null): the epilogue warps write the finished tile
+  // (bias, residual, ReLU, 16-bit pack) into a swizzled staging buffer and ONE thread hands
+  // it to TMA (cp.async.bulk.tensor store), which also clips tiles that overhang the image.
+  // The residual tile arrives the same way (res_map, fetched by the A producer warp).
+  // Per-thread 16-byte global stores at a pixel stride cost one L1 wavefront per lane --
+  // measured as the limiter of every <= 128-channel layer (profiles/r01_ncu_l1conv*).
+  const TmaDesc* out_map;   // box {64 ch (16 bit) | cout (f32), 8, 1, 16, 1}
+  const TmaDesc* res_map;   // same box over the residual tensor, or null
+  int32_t out_bufs, res_bufs;  // staging buffers (1 or 2 / 0, 1 or 2)
+  int32_t out_buf_bytes;       // bytes per staging buffer (multiple of 1024)
+  // epi_groups == 2 (BN <= 64, out_bufs == 2): the eight epilogue warps form two groups of
+  // four that take alternate tiles, each with its own staging buffer -- the per-tile latency
+  // chain (accumulator wait, TMEM load, pack, fences, barriers; about 1 us, measured) is the
+  // throughput limit of the small-K layers, and two chains run concurrently.
+  int32_t epi_groups;
+  FastDiv div_n_tiles, div_tx, div_ty;  // set by the launcher
+  // Timing experiments only (results are wrong when set): bit 0 = no halo TMA loads,
+  // bit 1 = one MMA per slab, bit 2 = no output stores.
+  int32_t dbg;
+  // Optional cycle accounting of CTA 0 (vsb_set_flag("halo_prof", 1)): 32 x uint64, see
+  // conv_halo.cu HaloProf; null in production.
+  unsigned long long* prof;
 };
 
 // ---- generalised variant: the halo tile is assembled by four cp.async producer warps

@@ -148,6 +148,11 @@ struct vsb_engine {
   int batch_override = 0;
   int conv_impl = 0;
   bool no_halo = false;
+  bool no_tma_epilogue = false;  // vsb_set_flag("tma_epilogue", 0): per-thread global stores in the halo epilogue
+  int halo_a_stages_max = 8;     // vsb_set_flag("halo_a_stages", n)
+  bool no_epi_groups = false;    // vsb_set_flag("epi_groups", 0): one epilogue group even for BN <= 64
+  unsigned long long* d_halo_prof = nullptr;  // vsb_set_flag("halo_prof", 1): per-launch cycle accounting to stderr
+  int halo_dbg = 0;              // vsb_set_flag("halo_dbg", bits): timing experiments, see ConvHaloParams::dbg
   bool no_fuse_head = true;   // fused head is bit-identical but measured slower (epilogue-bound); opt-in via vsb_set_flag
   int fuse_op = -1;            // conv op whose epilogue performs the head (set per predict_range batch)
   vsb::HeadFuse fuse{};
@@ -561,23 +566,28 @@ void free_workspace(vsb_engine* e) {
   e->ws_Hp = e->ws_Wp = e->ws_nb = 0;
 }
 
+// f32_plain: the tensor holds f32 and the box is stored densely (no swizzle) -- the logits
+// tile of the shared-memory epilogue; otherwise 16-bit elements, swizzle by KB.
 int make_tensor_map(vsb_engine* e, TmaDesc* out_host, const TensorBuf& t, int nb, bool folded, int KB,
-                    int bw, int bh, int nt) {
+                    int bw, int bh, int nt, bool f32_plain = false) {
   CUtensorMap m;
-  const cuuint64_t C = t.C, W = t.W, H = t.H;
+  const cuuint64_t C = t.C, W = t.W, H = t.H, eb = f32_plain ? 4 : 2;
   cuuint64_t dims[5], strides[4];
   if (!folded) {
     dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = nb;
-    strides[0] = C * 2; strides[1] = W * C * 2; strides[2] = W * C * 2; strides[3] = H * W * C * 2;
+    strides[0] = C * eb; strides[1] = W * C * eb; strides[2] = W * C * eb; strides[3] = H * W * C * eb;
   } else {
     dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = nb;
-    strides[0] = 2 * C * 2; strides[1] = W * C * 2; strides[2] = 2 * W * C * 2; strides[3] = H * W * C * 2;
+    strides[0] = 2 * C * eb; strides[1] = W * C * eb; strides[2] = 2 * W * C * eb; strides[3] = H * W * C * eb;
   }
   cuuint32_t box[5] = {(cuuint32_t)KB, (cuuint32_t)bw, 1u, (cuuint32_t)bh, (cuuint32_t)nt};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const CUtensorMapSwizzle sw = KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                         : (KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  const CUresult r = e->encode(&m, (VSB_ACT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 5, t.ptr, dims, strides, box, estr,
+  const CUtensorMapSwizzle sw = f32_plain ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                          : (KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                      : (KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B));
+  const CUtensorMapDataType dt = f32_plain ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                           : (VSB_ACT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  const CUresult r = e->encode(&m, dt, 5, t.ptr, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -586,6 +596,57 @@ int make_tensor_map(vsb_engine* e, TmaDesc* out_host, const TensorBuf& t, int nb
                 t.C, t.W, t.H, nb, (int)folded, KB, bw, bh, nt);
   static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "tensor map size");
   memcpy(out_host, &m, sizeof(m));
+  return VSB_OK;
+}
+
+// Shared-memory epilogue + pipeline depth of one conv_halo launch.  `h` holds BN, n_tiles,
+// ncs, b_bytes, a_stage_bytes; decides out/res staging, accumulator stages, resident vs
+// streamed weights and the A / B ring depths inside the 227 KB of one SM.
+int configure_halo_pipeline(vsb_engine* e, ConvPlan& cp, vsb::ConvHaloParams& h, const vsb_op& op, const TensorBuf& ot,
+                            int nb) {
+  h.acc_stages = h.BN <= 64 ? 8 : (h.BN <= 128 ? 4 : 2);
+  h.out_map = h.res_map = nullptr;
+  h.out_bufs = h.res_bufs = 0;
+  h.out_buf_bytes = 0;
+  const bool has_res = op.res >= 0;
+  bool tma_epi = !e->no_tma_epilogue && h.n_tiles == 1;
+  if (ot.dtype == 0) tma_epi = tma_epi && h.BN % 64 == 0 && h.BN <= 128 && op.cout % 64 == 0;
+  else tma_epi = tma_epi && !has_res && op.cout % 4 == 0 && op.cout <= 32 && op.cout <= h.BN;
+  if (tma_epi) {
+    h.out_buf_bytes = ot.dtype == 0 ? (h.BN / 64) * 16384 : (int)align_up((size_t)128 * op.cout * 4, 1024);
+    h.out_bufs = h.out_buf_bytes <= 16384 ? 2 : 1;
+    h.res_bufs = has_res ? h.out_bufs : 0;
+  }
+  h.epi_groups = (tma_epi && h.out_bufs == 2 && h.BN <= 64 && !e->no_epi_groups) ? 2 : 1;
+  const size_t usable = 227 * 1024 - 1024 - 1024 - 2048 * 4 - (size_t)(h.out_bufs + h.res_bufs) * h.out_buf_bytes;
+  const size_t res_bytes = (size_t)h.ncs * 9 * h.b_bytes;
+  if (h.n_tiles == 1 && res_bytes + 2 * (size_t)h.a_stage_bytes <= usable) {
+    h.b_stages = 0;
+    h.a_stages = (int)std::min<size_t>(e->halo_a_stages_max, (usable - res_bytes) / h.a_stage_bytes);
+  } else {
+    h.a_stages = 2;
+    if (usable < 2 * (size_t)h.a_stage_bytes + 2 * (size_t)h.b_bytes) return 1;  // does not fit
+    h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, (usable - 2 * (size_t)h.a_stage_bytes) / h.b_bytes);
+    if (h.b_stages >= 6 && usable >= 3 * (size_t)h.a_stage_bytes + 4 * (size_t)h.b_bytes) {
+      h.a_stages = 3;
+      h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, (usable - 3 * (size_t)h.a_stage_bytes) / h.b_bytes);
+    }
+  }
+  if (tma_epi) {
+    TmaDesc m;
+    int rc;
+    if (ot.dtype == 0) rc = make_tensor_map(e, &m, ot, nb, false, 64, 8, 16, 1);
+    else rc = make_tensor_map(e, &m, ot, nb, false, op.cout, 8, 16, 1, true);
+    if (rc) return rc;
+    CK(cudaMemcpy(cp.d_maps + (VSB_MAX_SRC - 2), &m, sizeof(m), cudaMemcpyHostToDevice));
+    h.out_map = cp.d_maps + (VSB_MAX_SRC - 2);
+    if (has_res) {
+      rc = make_tensor_map(e, &m, e->tens[op.res], nb, false, 64, 8, 16, 1);
+      if (rc) return rc;
+      CK(cudaMemcpy(cp.d_maps + (VSB_MAX_SRC - 3), &m, sizeof(m), cudaMemcpyHostToDevice));
+      h.res_map = cp.d_maps + (VSB_MAX_SRC - 3);
+    }
+  }
   return VSB_OK;
 }
 
@@ -721,9 +782,12 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
         h.tiles_x = tx;
         h.tiles_y = ty;
         h.b_bytes = 64 * 128;
-        h.b_stages = 0;
         h.a_stage_bytes = (int)align_up((size_t)HW * HH * 128, 1024);
-        h.a_stages = 4;
+        {
+          int rc2 = configure_halo_pipeline(e, cp, h, op, ot, nb);
+          if (rc2 < 0) return rc2;
+          if (rc2 > 0 || h.b_stages != 0) return fail(VSB_ERR_UNSUPPORTED, "op %d: grouped halo launch does not fit", i);
+        }
         cp.use_halo = true;
       }
       continue;
@@ -841,16 +905,9 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
       h.n_tiles = cp.n_tiles;
       h.b_bytes = cp.BN * 128;
       h.a_stage_bytes = (int)align_up((size_t)HW * HH * 128, 1024);
-      const size_t budget = 200 * 1024;
-      const size_t res_bytes = (size_t)h.ncs * 9 * h.b_bytes;
-      if (cp.n_tiles == 1 && res_bytes + 2 * (size_t)h.a_stage_bytes <= budget) {
-        h.b_stages = 0;
-        h.a_stages = (int)std::min<size_t>(4, (budget - res_bytes) / h.a_stage_bytes);
-      } else {
-        h.a_stages = 2;
-        h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, (budget - 2 * (size_t)h.a_stage_bytes) / h.b_bytes);
-      }
-      if (eff >= 0.6 && (h.b_stages == 0 || h.b_stages >= 2)) {
+      int fit = configure_halo_pipeline(e, cp, h, op, ot, nb);
+      if (fit < 0) return fit;
+      if (eff >= 0.6 && fit == 0 && (h.b_stages == 0 || h.b_stages >= 2)) {
         TmaDesc hm;
         const TensorBuf& st = e->tens[op.src[0]];
         int rc = make_tensor_map(e, &hm, st, nb, false, 64, HW, HH, 1);
@@ -933,8 +990,24 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
     vsb::ConvHaloParams h = cp.hparams;
     h.NB = nb;
     h.n_base = n0;
-    ProfScope ps(e, PC_CONV_TC, oi);
-    CK(vsb::launch_conv_halo(h, e->num_sms, e->stream));
+    h.dbg = e->halo_dbg;
+    h.prof = e->d_halo_prof;
+    if (e->d_halo_prof) CK(cudaMemsetAsync(e->d_halo_prof, 0, 32 * 8, e->stream));
+    {
+      ProfScope ps(e, PC_CONV_TC, oi);
+      CK(vsb::launch_conv_halo(h, e->num_sms, e->stream));
+    }
+    if (e->d_halo_prof) {
+      unsigned long long v[32];
+      CK(cudaMemcpyAsync(v, e->d_halo_prof, sizeof(v), cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      fprintf(stderr,
+              "[halo_prof] op %d BN %d ncs %d a_stages %d b_stages %d acc %d groups %d | producer: total %llu wait_a_empty %llu tiles %llu"
+              " | mma: total %llu wait_acc_empty %llu wait_a_full %llu issue %llu | epi: total %llu store_rd %llu acc_full %llu"
+              " ld+bar1 %llu math %llu arrive+bar2 %llu store %llu tiles %llu\n",
+              oi, h.BN, h.ncs, h.a_stages, h.b_stages, h.acc_stages, h.epi_groups, v[0], v[1], v[2], v[4], v[5], v[6], v[7], v[8],
+              v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+    }
     return VSB_OK;
   }
   if (cp.stem_tc && e->conv_impl == 0 && !e->no_halo) {
@@ -1513,6 +1586,14 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
   if (n == "halo") e->no_halo = value == 0;
   else if (n == "fuse_head") e->no_fuse_head = value == 0;
   else if (n == "sub_batch_mb") e->sub_batch_mb = value;
+  else if (n == "halo_dbg") e->halo_dbg = value;
+  else if (n == "halo_prof") {
+    if (value && !e->d_halo_prof) CK(cudaMalloc(&e->d_halo_prof, 32 * 8));
+    if (!value && e->d_halo_prof) { cudaFree(e->d_halo_prof); e->d_halo_prof = nullptr; }
+  }
+  else if (n == "epi_groups") { e->no_epi_groups = value == 0; free_workspace(e); }
+  else if (n == "tma_epilogue") { e->no_tma_epilogue = value == 0; free_workspace(e); }
+  else if (n == "halo_a_stages") { e->halo_a_stages_max = std::max(2, std::min(value, (int)vsb::HALO_MAX_A_STAGES)); free_workspace(e); }
   else return fail(VSB_ERR_INVALID, "unknown flag '%s'", name);
   return VSB_OK;
 }
