@@ -22,6 +22,8 @@ struct HaloCtl {
   uint64_t acc_empty[8];
   uint64_t res_full[2];
   uint64_t res_empty[2];
+  uint64_t out_full[2];
+  uint64_t out_empty[2];
   uint32_t tmem_base;
   uint32_t pad[3];
 };
@@ -53,11 +55,33 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
+// elementwise max of two packed 16-bit activation pairs / 16-byte max-reduction to global
+__device__ __forceinline__ uint32_t act_max2(uint32_t a, uint32_t b) {
+  uint32_t r;
+#if VSB_ACT_F16
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+#else
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+#endif
+  return r;
+}
+__device__ __forceinline__ void red_max_act8(uint16_t* dst, uint4 v) {
+#if VSB_ACT_F16
+  asm volatile("red.global.max.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+#else
+  asm volatile("red.global.max.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+#endif
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 constexpr int kHaloCtlBytes = 1024;
 constexpr int kHaloBiasBytes = 2048 * 4;
+// Stem (MODE 1): raw input window of one tile = 37 rows x 24 pixels (48 B), fetched with
+// 8-byte cp.async two tiles ahead of the im2col build.
+constexpr int kStemRawRows = 37, kStemRawPitch = 48, kStemRawBytes = 2048, kStemRawRing = 4;
 
 __device__ __forceinline__ void halo_decode(const ConvHaloParams& p, int t, int& n_tile, int& X0, int& Y0,
                                             int& n) {
@@ -139,6 +163,9 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   const int HW = 8 + 2 * p.dil, HH = 16 + 2 * p.dil;
   const bool resident = p.b_stages == 0;
   const uint32_t acc_cols = 512u / (uint32_t)p.acc_stages;
+  const int G = p.epi_groups == 2 ? 2 : 1;     // epilogue groups (alternate tiles)
+  const int MW = p.mma_warps == 2 ? 2 : 1;     // MMA issuing warps (alternate tiles)
+  const bool smem_epi = p.out_map != nullptr;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_stages; ++i) {
@@ -150,14 +177,17 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       mbar_init(&ctl->b_empty[i], 1);
     }
     mbar_init(&ctl->w_full, 1);
-    const int epi_threads = 32 * HALO_EPI_WARPS / (p.epi_groups == 2 ? 2 : 1);
+    // shared-memory epilogue: one arrival per epilogue warp; direct epilogue: one per thread
+    const int epi_arrivals = smem_epi ? HALO_EPI_WARPS / G : 32 * HALO_EPI_WARPS;
     for (int i = 0; i < 8; ++i) {
       mbar_init(&ctl->acc_full[i], 1);
-      mbar_init(&ctl->acc_empty[i], epi_threads);
+      mbar_init(&ctl->acc_empty[i], epi_arrivals);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->res_full[i], 1);
-      mbar_init(&ctl->res_empty[i], epi_threads);
+      mbar_init(&ctl->res_empty[i], epi_arrivals);
+      mbar_init(&ctl->out_full[i], epi_arrivals);
+      mbar_init(&ctl->out_empty[i], 1);
     }
     fence_mbar_init();
   }
@@ -171,7 +201,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp == 0) {
-    // ===================== A producer: halo boxes =====================
+    // ===================== A producer: halo boxes (+ residual tiles) =====================
     int as = 0;
     uint32_t aph = 0;
     const uint32_t a_box_bytes = (uint32_t)(HW * HH * 128);
@@ -254,142 +284,176 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    int as = 0, bs = 0, acc = 0;
-    uint32_t aph = 0, bph = 0, acc_phase = 0;
-    const uint32_t idesc = umma_idesc_act(128, p.BN);
-    const uint32_t sbo = (uint32_t)HW * 128;
-    const uint64_t a_desc0 = umma_smem_desc_sw128(smem_u32(a_ring), sbo);
-    const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(b_area), 1024);
-    const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4;
-    const uint32_t b_step = (uint32_t)p.b_bytes >> 4;
-    const uint32_t row_units = (uint32_t)(p.dil * HW * 8);  // one dilated halo row, in 16-byte units
-    const uint32_t col_units = (uint32_t)(p.dil * 8);
-    if (resident) mbar_wait(&ctl->w_full, 0);
-    unsigned long long* pr = (p.prof && blockIdx.x == 0 && lane == 0) ? p.prof : nullptr;
-    const long long mstart = pr ? dev_clock() : 0;
-    ProfClock pc(pr);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      pc.lap(7);
-      mbar_wait(&ctl->acc_empty[acc], acc_phase ^ 1);
-      pc.lap(5);
-      tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
-      for (int cs = 0; cs < p.ncs; ++cs) {
+  } else if (warp == 1 || warp == HALO_MMA2_WARP) {
+    // ===================== MMA issuer(s) =====================
+    // Issuing one tcgen05.mma costs a single warp ~50 cycles of dependent instruction latency
+    // and every tile ~1000 more (waits, fences, commits) -- measured with p.prof -- which exceeds
+    // the 32-cycle execution of an N <= 64 MMA.  With mma_warps == 2 (resident weights, one
+    // slab per tile) two warps issue alternate tiles into alternate accumulator stages.
+    const int mw = warp == 1 ? 0 : 1;
+    if (mw < MW) {
+      int as = mw, bs = 0, acc = mw;
+      uint32_t aph = 0, bph = 0, acc_phase = 0;
+      const uint32_t idesc = umma_idesc_act(128, p.BN);
+      const uint32_t sbo = (uint32_t)HW * 128;
+      const uint64_t a_desc0 = umma_smem_desc_sw128(smem_u32(a_ring), sbo);
+      const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(b_area), 1024);
+      const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4;
+      const uint32_t b_step = (uint32_t)p.b_bytes >> 4;
+      const uint32_t row_units = (uint32_t)(p.dil * HW * 8);  // one dilated halo row, in 16-byte units
+      const uint32_t col_units = (uint32_t)(p.dil * 8);
+      if (resident) mbar_wait(&ctl->w_full, 0);
+      unsigned long long* pr = (p.prof && blockIdx.x == 0 && lane == 0 && mw == 0) ? p.prof : nullptr;
+      const long long mstart = pr ? dev_clock() : 0;
+      ProfClock pc(pr);
+      for (int t = blockIdx.x + mw * gridDim.x; t < total_tiles; t += MW * gridDim.x) {
         pc.lap(7);
-        mbar_wait(&ctl->a_full[as], aph);
-        pc.lap(6);
+        mbar_wait(&ctl->acc_empty[acc], acc_phase ^ 1);
+        pc.lap(5);
         tc_fence_after_sync();
-        const uint64_t a_stage_desc = desc_add(a_desc0, as * a_step);
-        if (resident) {
-          if (elect_one()) {
-            if (p.dbg & 2)
-              umma_bf16_ss(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), idesc, cs != 0 ? 1u : 0u);
-            else if (p.use_kmask)
-              issue_slab_masked<9, 4>(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), b_step, row_units,
-                                      col_units, idesc, cs != 0, p.kmask[cs]);
-            else
-              issue_slab_resident<9, 4>(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), b_step, row_units,
-                                        col_units, idesc, cs != 0);
-            umma_commit(&ctl->a_empty[as]);
-            if (cs == p.ncs - 1) umma_commit(&ctl->acc_full[acc]);
-          }
-          __syncwarp();
-        } else {
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&ctl->b_full[bs], bph);
-            tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
+        for (int cs = 0; cs < p.ncs; ++cs) {
+          pc.lap(7);
+          mbar_wait(&ctl->a_full[as], aph);
+          pc.lap(6);
+          tc_fence_after_sync();
+          const uint64_t a_stage_desc = desc_add(a_desc0, as * a_step);
+          if (resident) {
             if (elect_one()) {
-              const uint64_t at = desc_add(a_stage_desc, (tap / 3) * row_units + (tap % 3) * col_units);
-              const uint64_t bt = desc_add(b_desc0, bs * b_step);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_ss(d_tmem, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc,
-                             (tap | k) != 0 ? 1u : (cs != 0 ? 1u : 0u));
-              umma_commit(&ctl->b_empty[bs]);
-              if (tap == 8) {
-                umma_commit(&ctl->a_empty[as]);
-                if (cs == p.ncs - 1) umma_commit(&ctl->acc_full[acc]);
-              }
+              if (p.dbg & 2)
+                umma_bf16_ss(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), idesc, cs != 0 ? 1u : 0u);
+              else if (p.use_kmask)
+                issue_slab_masked<9, 4>(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), b_step, row_units,
+                                        col_units, idesc, cs != 0, p.kmask[cs]);
+              else
+                issue_slab_resident<9, 4>(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), b_step, row_units,
+                                          col_units, idesc, cs != 0);
+              umma_commit(&ctl->a_empty[as]);
+              if (cs == p.ncs - 1) umma_commit(&ctl->acc_full[acc]);
             }
             __syncwarp();
-            if (++bs == p.b_stages) {
-              bs = 0;
-              bph ^= 1;
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&ctl->b_full[bs], bph);
+              tc_fence_after_sync();
+              if (elect_one()) {
+                const uint64_t at = desc_add(a_stage_desc, (tap / 3) * row_units + (tap % 3) * col_units);
+                const uint64_t bt = desc_add(b_desc0, bs * b_step);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_ss(d_tmem, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc,
+                               (tap | k) != 0 ? 1u : (cs != 0 ? 1u : 0u));
+                umma_commit(&ctl->b_empty[bs]);
+                if (tap == 8) {
+                  umma_commit(&ctl->a_empty[as]);
+                  if (cs == p.ncs - 1) umma_commit(&ctl->acc_full[acc]);
+                }
+              }
+              __syncwarp();
+              if (++bs == p.b_stages) {
+                bs = 0;
+                bph ^= 1;
+              }
             }
           }
+          as += MW;  // MW == 2 only with ncs == 1: the slab sequence is the tile sequence
+          if (as >= p.a_stages) {
+            as -= p.a_stages;
+            aph ^= 1;
+          }
         }
-        if (++as == p.a_stages) {
-          as = 0;
-          aph ^= 1;
+        acc += MW;
+        if (acc >= p.acc_stages) {
+          acc -= p.acc_stages;
+          acc_phase ^= 1;
         }
       }
-      if (++acc == p.acc_stages) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
+      if (pr) pr[4] += (unsigned long long)(dev_clock() - mstart);
     }
-    if (pr) pr[4] += (unsigned long long)(dev_clock() - mstart);
-  } else if (p.out_map) {
-    // ===================== epilogue through shared memory + TMA store =====================
+  } else if (warp == HALO_STORE_WARP) {
+    // ===================== TMA store issuer (shared-memory epilogue) =====================
+    // Waits until an epilogue group has filled a staging buffer, hands it to TMA and gives the
+    // buffer back once TMA has read it (one store behind, so the wait is normally already over).
+    if (smem_epi && lane == 0) {
+      int ob = 0;
+      uint32_t oph = 0;
+      int prev_ob = -1;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&ctl->out_full[ob], oph);
+        if (!(p.dbg & 4)) {
+          int n_tile, X0, Y0, n;
+          halo_decode(p, t, n_tile, X0, Y0, n);
+          if (p.out_f32) {
+            tma_store_5d(p.out_map, out_stage + (size_t)ob * p.out_buf_bytes, 0, X0, 0, Y0, n);
+          } else {
+            for (int g = 0; g < (p.BN >> 6); ++g)
+              tma_store_5d(p.out_map, out_stage + (size_t)ob * p.out_buf_bytes + g * 16384, p.cout_off + g * 64, X0, 0,
+                           Y0, n);
+          }
+        }
+        tma_store_commit();
+        if (p.out_bufs == 2) {
+          if (prev_ob >= 0) {
+            tma_store_wait_read<1>();
+            mbar_arrive(&ctl->out_empty[prev_ob]);
+          }
+          prev_ob = ob;
+        } else {
+          tma_store_wait_read<0>();
+          mbar_arrive(&ctl->out_empty[ob]);
+        }
+        if (++ob == p.out_bufs) {
+          ob = 0;
+          oph ^= 1;
+        }
+      }
+      tma_store_wait_read<0>();
+      if (prev_ob >= 0) mbar_arrive(&ctl->out_empty[prev_ob]);
+      tma_store_wait_all<0>();
+    }
+  } else if (smem_epi) {
+    // ===================== epilogue through shared memory (stores by the store warp) =====================
     // One group of eight warps (columns split in halves) or, for BN <= 64, two groups of four
-    // warps on alternate tiles (a thread owns all BN columns of its row).  Tile `it` (CTA-local
-    // count) uses accumulator stage it % acc_stages, residual buffer it % res_bufs and, with two
-    // groups, staging buffer = group; all three are even-periodic, so a group always meets the
-    // same stages and buffers.
-    const int G = p.epi_groups == 2 ? 2 : 1;
+    // warps on alternate tiles (a thread owns all BN columns of its row).  With two groups the
+    // accumulator stage, residual buffer and staging buffer of a tile all have its group's parity.
     const int quarter = warp & 3;
     const int half = (warp - 3) >> 2;
     const int grp = G == 2 ? half : 0;
     const int row = quarter * 32 + lane;
-    const int gthreads = 32 * HALO_EPI_WARPS / G;
-    const bool issuer = threadIdx.x == 96 + grp * 128;
     const bool has_res = p.res_map != nullptr;
     const uint32_t out_addr0 = smem_u32(out_stage), res_addr0 = smem_u32(res_stage);
     const uint32_t f32_pitch = (uint32_t)p.cout * 4u;
     const int c_begin = G == 2 ? 0 : half * 32, c_step = G == 2 ? 32 : 64;
     const float* bt = bias_l;  // n_tiles == 1 on this path
-    int it = grp;
+    int acc = grp, ob = grp, rb = grp;
+    uint32_t acc_phase = 0, oph = 0, rph = 0;
     unsigned long long* pr = (p.prof && blockIdx.x == 0 && threadIdx.x == 96) ? p.prof : nullptr;
     const long long estart = pr ? dev_clock() : 0;
     ProfClock pc(pr);
-    for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles; t += G * gridDim.x, it += G) {
+    for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles; t += G * gridDim.x) {
       if (pr) pr[15] += 1;
-      pc.lap(14);
-      const int acc = it % p.acc_stages;
-      const uint32_t acc_phase = (uint32_t)(it / p.acc_stages) & 1u;
-      const int ob = G == 2 ? grp : it % p.out_bufs;
-      const int rb = has_res ? it % p.res_bufs : 0;
-      const uint32_t rph = has_res ? (uint32_t)(it / p.res_bufs) & 1u : 0u;
       const uint32_t ost = out_addr0 + (uint32_t)ob * p.out_buf_bytes;
       const uint32_t rst = res_addr0 + (uint32_t)rb * p.out_buf_bytes;
-      // the staging buffer is free once the TMA store issued from it has read it
-      if (issuer) {
-        if (G == 1 && p.out_bufs == 2) tma_store_wait_read<1>();
-        else tma_store_wait_read<0>();
-      }
-      pc.lap(9);
+      pc.lap(14);
       mbar_wait(&ctl->acc_full[acc], acc_phase);
       pc.lap(10);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(quarter * 32) << 16);
       if (!p.out_f32) {
-        for (int c = c_begin; c < p.BN; c += c_step) {
-          uint32_t v[32];
-          if (p.dbg & 8) {
+        // both 32-column chunks of a BN = 64 tile are requested before the one wait
+        uint32_t v[2][32];
+        const int c1 = c_begin + c_step;
+        tmem_ld_32x32b_x32(taddr + c_begin, v[0]);
+        if (c1 < p.BN) tmem_ld_32x32b_x32(taddr + c1, v[1]);
+        tmem_ld_wait();
+        if (has_res) mbar_wait(&ctl->res_full[rb], rph);
+        mbar_wait(&ctl->out_empty[ob], oph ^ 1);  // TMA has read the previous tile out of this buffer
+        pc.lap(11);
 #pragma unroll
-            for (int z = 0; z < 32; ++z) v[z] = (uint32_t)row;
-          } else {
-            tmem_ld_32x32b_x32(taddr + c, v);
-            tmem_ld_wait();
-          }
-          if (c == c_begin) {
-            if (has_res) mbar_wait(&ctl->res_full[rb], rph);
-            if (!(p.dbg & 16)) named_bar_sync(1 + 2 * grp, gthreads);
-            pc.lap(11);
-          }
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c = c_begin + ci * c_step;
+          if (c >= p.BN) break;
           const uint32_t row_off = (uint32_t)(c >> 6) * 16384u + (uint32_t)row * 128u;
           const int j0 = (c & 63) >> 3;
 #pragma unroll
@@ -397,10 +461,10 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
             const uint32_t off = row_off + ((uint32_t)((j0 + q) ^ (row & 7)) << 4);
             const float4 b0 = *reinterpret_cast<const float4*>(bt + c + q * 8);
             const float4 b1 = *reinterpret_cast<const float4*>(bt + c + q * 8 + 4);
-            float f0 = __uint_as_float(v[q * 8 + 0]) + b0.x, f1 = __uint_as_float(v[q * 8 + 1]) + b0.y;
-            float f2 = __uint_as_float(v[q * 8 + 2]) + b0.z, f3 = __uint_as_float(v[q * 8 + 3]) + b0.w;
-            float f4 = __uint_as_float(v[q * 8 + 4]) + b1.x, f5 = __uint_as_float(v[q * 8 + 5]) + b1.y;
-            float f6 = __uint_as_float(v[q * 8 + 6]) + b1.z, f7 = __uint_as_float(v[q * 8 + 7]) + b1.w;
+            float f0 = __uint_as_float(v[ci][q * 8 + 0]) + b0.x, f1 = __uint_as_float(v[ci][q * 8 + 1]) + b0.y;
+            float f2 = __uint_as_float(v[ci][q * 8 + 2]) + b0.z, f3 = __uint_as_float(v[ci][q * 8 + 3]) + b0.w;
+            float f4 = __uint_as_float(v[ci][q * 8 + 4]) + b1.x, f5 = __uint_as_float(v[ci][q * 8 + 5]) + b1.y;
+            float f6 = __uint_as_float(v[ci][q * 8 + 6]) + b1.z, f7 = __uint_as_float(v[ci][q * 8 + 7]) + b1.w;
             if (has_res) {
               const uint4 rv = lds128(rst + off);
               float2 r;
@@ -415,19 +479,20 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
             } else {
               pk.x = pack2<false>(f0, f1); pk.y = pack2<false>(f2, f3); pk.z = pack2<false>(f4, f5); pk.w = pack2<false>(f6, f7);
             }
-            if (!(p.dbg & 32)) sts128(ost + off, pk);
-            else if (pk.x == 0x12345678u) sts128(ost + off, pk);
+            sts128(ost + off, pk);
           }
         }
       } else {
         // f32 logits (cout <= 32): dense rows of cout floats, no swizzle
+        const bool active = G == 2 || half == 0;
         uint32_t v[32];
-        if (G == 2 || half == 0) {
+        if (active) {
           tmem_ld_32x32b_x32(taddr, v);
           tmem_ld_wait();
         }
-        named_bar_sync(1 + 2 * grp, gthreads);
-        if (G == 2 || half == 0) {
+        mbar_wait(&ctl->out_empty[ob], oph ^ 1);
+        pc.lap(11);
+        if (active) {
           const uint32_t row_off = (uint32_t)row * f32_pitch;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -446,29 +511,39 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         }
       }
       pc.lap(12);
+      // publish: staging buffer to the async proxy / store warp, accumulator stage and
+      // residual buffer back to their producers -- one arrival per warp
       tc_fence_before_sync();
-      mbar_arrive(&ctl->acc_empty[acc]);
-      if (has_res) mbar_arrive(&ctl->res_empty[rb]);
-      if (!(p.dbg & 32)) fence_proxy_async_smem();
-      if (!(p.dbg & 16)) named_bar_sync(2 + 2 * grp, gthreads);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&ctl->out_full[ob]);
+        mbar_arrive(&ctl->acc_empty[acc]);
+        if (has_res) mbar_arrive(&ctl->res_empty[rb]);
+      }
       pc.lap(13);
-      if (issuer && !(p.dbg & 4)) {
-        int n_tile, X0, Y0, n;
-        halo_decode(p, t, n_tile, X0, Y0, n);
-        if (p.out_f32) {
-          tma_store_5d(p.out_map, out_stage + (size_t)ob * p.out_buf_bytes, 0, X0, 0, Y0, n);
-        } else {
-          for (int g = 0; g < (p.BN >> 6); ++g)
-            tma_store_5d(p.out_map, out_stage + (size_t)ob * p.out_buf_bytes + g * 16384, p.cout_off + g * 64, X0, 0, Y0,
-                         n);
+      acc += G;
+      if (acc >= p.acc_stages) {
+        acc -= p.acc_stages;
+        acc_phase ^= 1;
+      }
+      if (G == 2) {
+        oph ^= 1;  // own buffer, every tile
+      } else if (++ob == p.out_bufs) {
+        ob = 0;
+        oph ^= 1;
+      }
+      if (has_res) {
+        rb += G;
+        if (rb >= p.res_bufs) {
+          rb -= p.res_bufs;
+          rph ^= 1;
         }
-        tma_store_commit();
       }
     }
-    if (issuer) tma_store_wait_all<0>();
     if (pr) pr[8] += (unsigned long long)(dev_clock() - estart);
   } else {
-    // ===================== epilogue =====================
+    // ===================== direct epilogue (per-thread global stores) =====================
     int acc = 0;
     uint32_t acc_phase = 0;
     const int quarter = warp & 3;
@@ -607,6 +682,8 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
       p.b_stages ? (size_t)p.b_stages * p.b_bytes : (size_t)p.nslabs * NTAPS * p.b_bytes;
   HaloCtl* ctl = reinterpret_cast<HaloCtl*>(b_area + b_area_bytes);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + kHaloCtlBytes);
+  uint8_t* stem_raw = reinterpret_cast<uint8_t*>(bias_s) + kHaloBiasBytes;     // MODE 1: raw input ring
+  uint8_t* pool_stage = stem_raw + kStemRawRing * kStemRawBytes;               // MODE 1 + pool: 2 x 16 KB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -625,7 +702,7 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
     mbar_init(&ctl->w_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->acc_full[i], 1);
-      mbar_init(&ctl->acc_empty[i], 32 * 8);
+      mbar_init(&ctl->acc_empty[i], (MODE == 1 && p.pool_out) ? 32 * 4 : 32 * 8);
     }
     fence_mbar_init();
   }
@@ -638,12 +715,15 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
 
   // tile index -> (n_tile, X0, Y0, image)
   auto decode = [&](int t, int& n_tile, int& X0, int& Y0, int& n) {
-    n_tile = t % p.n_tiles;
-    int sp = t / p.n_tiles;
-    const int tx = sp % p.tiles_x;
-    sp /= p.tiles_x;
-    const int ty = sp % p.tiles_y;
-    n = sp / p.tiles_y + p.n_base;
+    auto fdiv = [](uint32_t v, const FastDiv& f) { return f.m ? __umulhi(v, f.m) : v; };
+    uint32_t sp = fdiv((uint32_t)t, p.div_n_tiles);
+    n_tile = t - (int)(sp * p.div_n_tiles.d);
+    uint32_t q = fdiv(sp, p.div_tx);
+    const int tx = (int)(sp - q * p.div_tx.d);
+    sp = q;
+    q = fdiv(sp, p.div_ty);
+    const int ty = (int)(sp - q * p.div_ty.d);
+    n = (int)q + p.n_base;
     X0 = tx * (8 * MT);
     Y0 = ty * 16;
   };
@@ -672,26 +752,51 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
       const int hy = pix / HW, hx = pix - hy * HW;
       ltab[it] = ((swz<P>((uint32_t)(pix * P + j * 16)) >> 4) << 16) | ((uint32_t)hy << 10) | ((uint32_t)hx << 4) | (uint32_t)j;
     }
+    int stem_k = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n_tile, X0, Y0, n;
       decode(t, n_tile, X0, Y0, n);
       if (MODE == 1) {
+        // Raw input windows run kStemRawRing - 2 tiles ahead (8-byte cp.async, zero-filled outside
+        // the image); the im2col row of each output pixel is then assembled from shared memory:
+        // K chunk ky (16 bytes) = input columns 2*ox-4 .. 2*ox+3 of row 2*oy+ky-3, i.e. four
+        // aligned 32-bit words; column 2*ox-4 is outside the 7x7 window and meets a zero weight.
         const HaloSrc& sv = p.src[0];
-        const uint16_t* img = sv.ptr + (int64_t)n * sv.Hs * sv.Ws;
-        const int m = ptid, ox = X0 + (m & 7), oy = Y0 + (m >> 3);
-        // K layout: chunk ky (16 bytes) = input columns 2*ox-4 .. 2*ox+3 of row 2*oy+ky-3, i.e.
-        // four aligned 32-bit words; column 2*ox-4 is outside the 7x7 window and meets a zero weight.
+        auto fetch_raw = [&](int tt, int slot) {
+          if (tt < total_tiles) {
+            int nt2, X2, Y2, n2;
+            decode(tt, nt2, X2, Y2, n2);
+            const uint16_t* img2 = sv.ptr + (int64_t)n2 * sv.Hs * sv.Ws;
+            const uint32_t dst0 = smem_u32(stem_raw) + (uint32_t)slot * kStemRawBytes;
+            for (int i = ptid; i < kStemRawRows * 6; i += 32 * HALO2_LOAD_WARPS) {
+              const int rr = i / 6, cc = i - rr * 6;
+              const int iy = 2 * Y2 - 3 + rr, ix = 2 * X2 - 4 + 4 * cc;
+              const bool ok = iy >= 0 && iy < sv.Hs && ix >= 0 && ix < sv.Ws;
+              const uint16_t* g = ok ? img2 + (int64_t)iy * sv.Ws + ix : sv.ptr;
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst0 + rr * kStemRawPitch + cc * 8), "l"(g),
+                           "r"(ok ? 8u : 0u)
+                           : "memory");
+            }
+          }
+          cp_async_commit();
+        };
+        if (t == (int)blockIdx.x) {  // prologue: windows of the first two tiles
+          fetch_raw(t, 0);
+          fetch_raw(t + (int)gridDim.x, 1);
+        }
+        const int k = stem_k++;  // CTA-local tile count
+        fetch_raw(t + 2 * (int)gridDim.x, (k + 2) % kStemRawRing);
+        cp_async_wait<2>();  // this tile's window has landed (two newer groups may be in flight)
+        named_bar_sync(5, 32 * HALO2_LOAD_WARPS);  // ... for every loader thread
+        const int m = ptid, oxl = m & 7, oyl = m >> 3;
+        const uint32_t raw = smem_u32(stem_raw) + (uint32_t)(k % kStemRawRing) * kStemRawBytes;
         uint32_t vals[32];
 #pragma unroll
         for (int ky = 0; ky < 7; ++ky) {
-          const int iy = 2 * oy + ky - 3;
-          const bool oky = iy >= 0 && iy < sv.Hs;
-          const uint32_t* rowp = reinterpret_cast<const uint32_t*>(img + (int64_t)iy * sv.Ws);
+          const uint32_t rowa = raw + (uint32_t)(2 * oyl + ky) * kStemRawPitch + (uint32_t)oxl * 4;
 #pragma unroll
-          for (int wq = 0; wq < 4; ++wq) {
-            const int col = 2 * ox - 4 + 2 * wq;  // even; the pair (col, col+1) is inside or outside together
-            vals[ky * 4 + wq] = (oky && col >= 0 && col < sv.Ws) ? __ldg(rowp + (col >> 1)) : 0u;
-          }
+          for (int wq = 0; wq < 4; ++wq)
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(vals[ky * 4 + wq]) : "r"(rowa + wq * 4));
         }
 #pragma unroll
         for (int i = 28; i < 32; ++i) vals[i] = 0;
@@ -874,6 +979,79 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
     const EpiOut eo{p.out, p.residual, p.out_f32, p.relu, p.cout};
     const int ncols = MT * p.BN;
     const int bn_log2 = 31 - __clz(p.BN);
+    if (MODE == 1 && p.pool_out) {
+      // ---- stem + fused max-pool: BN == 64, full tiles (H % 16 == 0, W % 8 == 0), ReLU ----
+      // Two groups of four warps take alternate tiles (accumulator stage = group), each with
+      // its own 16 KB staging tile; a thread owns all 64 channels of its pixel.
+      const int grp = half;
+      const uint32_t stage = smem_u32(pool_stage) + (uint32_t)grp * 16384u;
+      const int et = (quarter << 5) | lane;  // 0..127 within the group
+      const int Hq = p.H >> 1, Wq = p.W >> 1;
+      uint32_t gphase = 0;
+      for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles; t += 2 * gridDim.x) {
+        int n_tile, X0, Y0, n;
+        decode(t, n_tile, X0, Y0, n);
+        mbar_wait(&ctl->acc_full[grp], gphase);
+        gphase ^= 1;
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + (uint32_t)grp * 256u + ((uint32_t)(quarter * 32) << 16);
+        uint32_t v[2][32];
+        tmem_ld_32x32b_x32(taddr, v[0]);
+        tmem_ld_32x32b_x32(taddr + 32, v[1]);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&ctl->acc_empty[grp]);
+        named_bar_sync(1 + 2 * grp, 128);  // the group has finished reading the previous tile's staging
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h2 * 32 + q * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h2 * 32 + q * 8 + 4);
+            uint4 pk;
+            pk.x = pack2<true>(__uint_as_float(v[h2][q * 8 + 0]) + b0.x, __uint_as_float(v[h2][q * 8 + 1]) + b0.y);
+            pk.y = pack2<true>(__uint_as_float(v[h2][q * 8 + 2]) + b0.z, __uint_as_float(v[h2][q * 8 + 3]) + b0.w);
+            pk.z = pack2<true>(__uint_as_float(v[h2][q * 8 + 4]) + b1.x, __uint_as_float(v[h2][q * 8 + 5]) + b1.y);
+            pk.w = pack2<true>(__uint_as_float(v[h2][q * 8 + 6]) + b1.z, __uint_as_float(v[h2][q * 8 + 7]) + b1.w);
+            sts128(stage + (uint32_t)row * 128u + ((uint32_t)((h2 * 4 + q) ^ (row & 7)) << 4), pk);
+          }
+        named_bar_sync(2 + 2 * grp, 128);
+        // (a) the stem output itself: 16 rows x 1 KB, lanes along the bytes of a row
+        uint16_t* obase = reinterpret_cast<uint16_t*>(p.out) + (((int64_t)n * p.H + Y0) * p.W + X0) * 64;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int idx = et + 128 * k;
+          const int rp = idx >> 3, ch = idx & 7;  // tile pixel (row-major, 8 per image row), 16-byte chunk
+          const uint4 val = lds128(stage + (uint32_t)rp * 128u + ((uint32_t)(ch ^ (rp & 7)) << 4));
+          *reinterpret_cast<uint4*>(obase + ((int64_t)(rp >> 3) * p.W + (rp & 7)) * 64 + ch * 8) = val;
+        }
+        // (b) pooled partial maxima: 9 x 5 pooled pixels touch this tile
+        for (int i = et; i < 9 * 5 * 8; i += 128) {
+          const int ch = i & 7, pp = i >> 3;
+          const int pyl = pp / 5, pxl = pp - pyl * 5;
+          const int PY = (Y0 >> 1) + pyl, PX = (X0 >> 1) + pxl;
+          if (PY >= Hq || PX >= Wq) continue;
+          uint4 m = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy) {
+            const int ry = 2 * pyl + dy;
+            if (ry < 0 || ry > 15) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+              const int rx = 2 * pxl + dx;
+              if (rx < 0 || rx > 7) continue;
+              const int rp = ry * 8 + rx;
+              const uint4 val = lds128(stage + (uint32_t)rp * 128u + ((uint32_t)(ch ^ (rp & 7)) << 4));
+              m.x = act_max2(m.x, val.x);
+              m.y = act_max2(m.y, val.y);
+              m.z = act_max2(m.z, val.z);
+              m.w = act_max2(m.w, val.w);
+            }
+          }
+          red_max_act8(p.pool_out + (((int64_t)n * Hq + PY) * Wq + PX) * 64 + ch * 8, m);
+        }
+      }
+    } else
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n_tile, X0, Y0, n;
       decode(t, n_tile, X0, Y0, n);
@@ -925,7 +1103,8 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
 
 size_t conv_halo2_smem_bytes(const ConvHalo2Params& p) {
   const size_t b = p.b_stages ? (size_t)p.b_stages * p.b_bytes : (size_t)p.nslabs * (p.stem ? 1 : 9) * p.b_bytes;
-  return (size_t)p.a_stages * p.a_stage_bytes + b + kHaloCtlBytes + kHaloBiasBytes + 1024;
+  return (size_t)p.a_stages * p.a_stage_bytes + b + kHaloCtlBytes + kHaloBiasBytes + 1024 +
+         (p.stem ? kStemRawRing * kStemRawBytes + (p.pool_out ? 2 * 16384 : 0) : 0);
 }
 
 namespace {
@@ -954,9 +1133,16 @@ cudaError_t halo2_dispatch(const ConvHalo2Params& p, int grid, size_t smem, cuda
 }
 }  // namespace
 
-cudaError_t launch_conv_halo2(const ConvHalo2Params& p, int num_sms, cudaStream_t st) {
-  const int total_tiles = p.n_tiles * p.tiles_x * p.tiles_y * p.NB;
-  const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+cudaError_t launch_conv_halo2(const ConvHalo2Params& p0, int num_sms, cudaStream_t st) {
+  ConvHalo2Params p = p0;
+  const int64_t total_tiles = (int64_t)p.n_tiles * p.tiles_x * p.tiles_y * p.NB;
+  const int64_t dmax = p.n_tiles > p.tiles_x ? (p.n_tiles > p.tiles_y ? p.n_tiles : p.tiles_y)
+                                             : (p.tiles_x > p.tiles_y ? p.tiles_x : p.tiles_y);
+  if (total_tiles * dmax >= (1ll << 32)) return cudaErrorInvalidValue;  // FastDiv exactness bound
+  p.div_n_tiles = make_fastdiv((uint32_t)p.n_tiles);
+  p.div_tx = make_fastdiv((uint32_t)p.tiles_x);
+  p.div_ty = make_fastdiv((uint32_t)p.tiles_y);
+  const int grid = total_tiles < num_sms ? (int)total_tiles : num_sms;
   return halo2_dispatch(p, grid, conv_halo2_smem_bytes(p), st, false);
 }
 

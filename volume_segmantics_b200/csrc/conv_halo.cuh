@@ -72,6 +72,7 @@ struct ConvHaloParams {
   // chain (accumulator wait, TMEM load, pack, fences, barriers; about 1 us, measured) is the
   // throughput limit of the small-K layers, and two chains run concurrently.
   int32_t epi_groups;
+  int32_t mma_warps;  // 2: two MMA issuing warps on alternate tiles (resident weights, ncs == 1)
   FastDiv div_n_tiles, div_tx, div_ty;  // set by the launcher
   // Timing experiments only (results are wrong when set): bit 0 = no halo TMA loads,
   // bit 1 = one MMA per slab, bit 2 = no output stores.
@@ -128,6 +129,12 @@ struct ConvHalo2Params {
   int32_t a_stages, a_stage_bytes;
   int32_t b_stages, b_bytes;
   HeadFuse head;
+  // Stem only (MODE 1): fused 3x3 stride-2 pad-1 max-pool (torchvision ResNet.maxpool).  The
+  // epilogue stages the ReLU'd tile in shared memory, writes it with coalesced stores and
+  // max-reduces the part of every pooling window that lies inside the tile into the
+  // zero-initialised pooled tensor [NB, H/2, W/2, cout] with 16-byte red.max (values >= 0).
+  uint16_t* pool_out;
+  FastDiv div_n_tiles, div_tx, div_ty;  // set by the launcher
 };
 constexpr int HALO2_LOAD_WARPS = 4;
 constexpr int HALO2_THREADS = 32 * (HALO2_LOAD_WARPS + 2 + 8);
@@ -136,7 +143,9 @@ size_t conv_halo2_smem_bytes(const ConvHalo2Params& p);
 cudaError_t launch_conv_halo2(const ConvHalo2Params& p, int num_sms, cudaStream_t st);
 
 constexpr int HALO_EPI_WARPS = 8;
-constexpr int HALO_THREADS = 96 + 32 * HALO_EPI_WARPS;
+constexpr int HALO_MMA2_WARP = 3 + HALO_EPI_WARPS;   // second MMA issuer (mma_warps == 2)
+constexpr int HALO_STORE_WARP = 4 + HALO_EPI_WARPS;  // TMA store issuer of the shared-memory epilogue
+constexpr int HALO_THREADS = 32 * (5 + HALO_EPI_WARPS);
 constexpr int HALO_MAX_A_STAGES = 8;
 constexpr int HALO_MAX_B_STAGES = 8;
 

@@ -97,6 +97,8 @@ struct ConvPlan {
   bool grouped_halo = false;  // groups > 1, 3x3 stride 1: one resident-weight halo launch per 64-channel block
   int n_blocks = 0;
   bool stem_tc = false;   // 7x7/2 single-channel stem on tensor cores (halo2 kernel, MODE 1)
+  int pool_op = -1;       // stem: index of the MAXPOOL op fused into its epilogue (per workspace), or -1
+  bool fused_away = false;  // MAXPOOL: computed by the preceding stem launch
   bool halo2_ok = false, use_halo2 = false;  // cp.async-assembled halo (concat / up-sampled / narrow sources)
   vsb::ConvHalo2Params h2params{};
   // spatial-size dependent
@@ -150,6 +152,8 @@ struct vsb_engine {
   bool no_halo = false;
   bool no_tma_epilogue = false;  // vsb_set_flag("tma_epilogue", 0): per-thread global stores in the halo epilogue
   int halo_a_stages_max = 8;     // vsb_set_flag("halo_a_stages", n)
+  bool no_fuse_pool = false;     // vsb_set_flag("fuse_pool", 0): separate max-pool kernel after the stem
+  bool no_mma2 = false;          // vsb_set_flag("mma_warps", 1): a single MMA issuing warp everywhere
   bool no_epi_groups = false;    // vsb_set_flag("epi_groups", 0): one epilogue group even for BN <= 64
   unsigned long long* d_halo_prof = nullptr;  // vsb_set_flag("halo_prof", 1): per-launch cycle accounting to stderr
   int halo_dbg = 0;              // vsb_set_flag("halo_dbg", bits): timing experiments, see ConvHaloParams::dbg
@@ -616,8 +620,19 @@ int configure_halo_pipeline(vsb_engine* e, ConvPlan& cp, vsb::ConvHaloParams& h,
     h.out_buf_bytes = ot.dtype == 0 ? (h.BN / 64) * 16384 : (int)align_up((size_t)128 * op.cout * 4, 1024);
     h.out_bufs = h.out_buf_bytes <= 16384 ? 2 : 1;
     h.res_bufs = has_res ? h.out_bufs : 0;
+    // Only where the weights stay resident next to the staging buffers: streamed-weight
+    // launches (BN >= 128) need the shared memory for their B ring (measured: 5 instead of 8
+    // weight stages cost more than the scattered stores).
+    const size_t staging = (size_t)(h.out_bufs + h.res_bufs) * h.out_buf_bytes;
+    const size_t all = 227 * 1024 - 1024 - 1024 - 2048 * 4;
+    if ((size_t)h.ncs * 9 * h.b_bytes + 3 * (size_t)h.a_stage_bytes + staging > all) {
+      tma_epi = false;
+      h.out_bufs = h.res_bufs = 0;
+      h.out_buf_bytes = 0;
+    }
   }
   h.epi_groups = (tma_epi && h.out_bufs == 2 && h.BN <= 64 && !e->no_epi_groups) ? 2 : 1;
+  h.mma_warps = 1;
   const size_t usable = 227 * 1024 - 1024 - 1024 - 2048 * 4 - (size_t)(h.out_bufs + h.res_bufs) * h.out_buf_bytes;
   const size_t res_bytes = (size_t)h.ncs * 9 * h.b_bytes;
   if (h.n_tiles == 1 && res_bytes + 2 * (size_t)h.a_stage_bytes <= usable) {
@@ -632,6 +647,8 @@ int configure_halo_pipeline(vsb_engine* e, ConvPlan& cp, vsb::ConvHaloParams& h,
       h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, (usable - 3 * (size_t)h.a_stage_bytes) / h.b_bytes);
     }
   }
+  // two MMA warps need the tile sequence to be the A-ring slab sequence (one slab per tile)
+  if (h.b_stages == 0 && h.ncs == 1 && h.a_stages >= 2 && !e->no_mma2) h.mma_warps = 2;
   if (tma_epi) {
     TmaDesc m;
     int rc;
@@ -669,7 +686,12 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
   e->tens[0].first_def = -1;
   for (int i = 0; i < (int)e->ops.size(); ++i) {
     const vsb_op& op = e->ops[i];
-    if (op.out >= 0 && e->tens[op.out].first_def < 0 && op.out != 0) e->tens[op.out].first_def = i;
+    if (op.out >= 0 && e->tens[op.out].first_def < 0 && op.out != 0) {
+      e->tens[op.out].first_def = i;
+      // a max-pool right after its producer may be computed inside the producer's launch (stem
+      // fusion): its output must exist -- and alias nothing the producer reads -- one op earlier
+      if (op.kind == VSB_OP_MAXPOOL && i > 0 && e->ops[i - 1].out == op.src[0]) e->tens[op.out].first_def = i - 1;
+    }
     for (int s = 0; s < op.n_src; ++s) e->tens[op.src[s]].last_use = i;
     if (op.res >= 0) e->tens[op.res].last_use = i;
   }
@@ -697,9 +719,9 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
     size_of[e->tens[0].ptr] = e->tens[0].bytes;
   }
   for (int i = 0; i < (int)e->ops.size(); ++i) {
-    const vsb_op& op = e->ops[i];
-    if (op.out > 0 && e->tens[op.out].first_def == i) {
-      TensorBuf& b = e->tens[op.out];
+    for (int t = 1; t < nt_; ++t) {
+      TensorBuf& b = e->tens[t];
+      if (b.first_def != i || b.ptr) continue;
       void* p = nullptr;
       int rc = alloc(b.bytes, &p);
       if (rc) return rc;
@@ -748,6 +770,20 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
       h.a_stages = 4;
       h.b_stages = 0;
       h.b_bytes = cp.BN * 128;
+      // fuse the following 3x3/2 max-pool (torchvision ResNet.maxpool) into the epilogue
+      cp.pool_op = -1;
+      h.pool_out = nullptr;
+      if (i + 1 < (int)e->ops.size()) {
+        const vsb_op& nx = e->ops[i + 1];
+        e->conv[i + 1].fused_away = false;
+        if (!e->no_fuse_pool && nx.kind == VSB_OP_MAXPOOL && nx.src[0] == op.out && op.relu && cp.BN == 64 &&
+            op.cout == 64 && ot.H % 16 == 0 && ot.W % 8 == 0 && e->tens[nx.out].H == ot.H / 2 &&
+            e->tens[nx.out].W == ot.W / 2) {
+          cp.pool_op = i + 1;
+          h.pool_out = (uint16_t*)e->tens[nx.out].ptr;
+          e->conv[i + 1].fused_away = true;
+        }
+      }
       continue;
     }
     if (cp.grouped_halo) {
@@ -1014,6 +1050,14 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
     vsb::ConvHalo2Params h = cp.h2params;
     h.NB = nb;
     h.n_base = n0;
+    if (cp.pool_op >= 0) {
+      // the pooled tensor is max-reduced into: zero is the identity of max over ReLU outputs
+      const TensorBuf& pt = e->tens[e->ops[cp.pool_op].out];
+      const size_t per_img = (size_t)pt.H * pt.W * pt.C * 2;
+      ProfScope ps(e, PC_POOL, cp.pool_op);
+      e->launches -= 1;  // a driver memset, not one of our kernels
+      CK(cudaMemsetAsync((uint8_t*)pt.ptr + (size_t)n0 * per_img, 0, (size_t)nb * per_img, e->stream));
+    }
     ProfScope ps(e, PC_STEM, oi);
     CK(vsb::launch_conv_halo2(h, e->num_sms, e->stream));
     return VSB_OK;
@@ -1115,6 +1159,7 @@ int run_op(vsb_engine* e, int i, int n0, int nb) {
     case VSB_OP_CONV:
       return run_conv(e, i, n0, nb);
     case VSB_OP_MAXPOOL: {
+      if (e->conv[i].fused_away && e->conv_impl == 0 && !e->no_halo) return VSB_OK;  // done by the stem epilogue
       const TensorBuf& s = e->tens[op.src[0]];
       const TensorBuf& o = e->tens[op.out];
       ProfScope ps(e, PC_POOL, i);
@@ -1591,6 +1636,8 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
     if (value && !e->d_halo_prof) CK(cudaMalloc(&e->d_halo_prof, 32 * 8));
     if (!value && e->d_halo_prof) { cudaFree(e->d_halo_prof); e->d_halo_prof = nullptr; }
   }
+  else if (n == "fuse_pool") { e->no_fuse_pool = value == 0; free_workspace(e); }
+  else if (n == "mma_warps") { e->no_mma2 = value < 2; free_workspace(e); }
   else if (n == "epi_groups") { e->no_epi_groups = value == 0; free_workspace(e); }
   else if (n == "tma_epilogue") { e->no_tma_epilogue = value == 0; free_workspace(e); }
   else if (n == "halo_a_stages") { e->halo_a_stages_max = std::max(2, std::min(value, (int)vsb::HALO_MAX_A_STAGES)); free_workspace(e); }
