@@ -36,14 +36,31 @@ __device__ __forceinline__ long long dev_clock() {
   return t;
 }
 struct ProfClock {
+  // accumulates in registers (slots are compile-time constants); flush() adds them to global
+  // memory once, so the measurement does not put a global round trip into every lap
   unsigned long long* out;
   long long t;
-  __device__ __forceinline__ ProfClock(unsigned long long* o) : out(o), t(o ? dev_clock() : 0) {}
-  __device__ __forceinline__ void lap(int slot) {
+  unsigned long long a[8];
+  __device__ __forceinline__ ProfClock(unsigned long long* o) : out(o), t(o ? dev_clock() : 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 0;
+  }
+  template <int SLOT>
+  __device__ __forceinline__ void lap() {
     if (out) {
       const long long n = dev_clock();
-      out[slot] += (unsigned long long)(n - t);
+      a[SLOT] += (unsigned long long)(n - t);
       t = n;
+    }
+  }
+  template <int SLOT>
+  __device__ __forceinline__ void count() {
+    if (out) a[SLOT] += 1;
+  }
+  __device__ __forceinline__ void flush(int base) {
+    if (out) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out[base + i] += a[i];
     }
   }
 };
@@ -105,6 +122,20 @@ __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t off16) {
   return (d & 0xffffffff00000000ull) | (uint32_t)((uint32_t)d + off16);
 }
 
+// K-major operand descriptor for the compact layouts: pitch 32 -> SW32 (6), 64 -> SW64 (4),
+// 128 -> SW128 (2); sbo = byte distance between consecutive 8-row groups.
+template <int PITCH>
+__device__ __forceinline__ uint64_t desc_compact(uint32_t addr, uint32_t sbo) {
+  constexpr uint64_t layout = PITCH == 128 ? 2ull : (PITCH == 64 ? 4ull : 6ull);
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
+         (layout << 61);
+}
+// Swizzle<B,4,3> of a byte offset relative to a 1024-byte aligned base.
+template <int PITCH>
+__device__ __forceinline__ uint32_t swz(uint32_t off) {
+  constexpr uint32_t mask = PITCH == 128 ? 7u : (PITCH == 64 ? 3u : 1u);
+  return off ^ (((off >> 7) & mask) << 4);
+}
 // All MMAs of one 64-channel (or narrower) slab against RESIDENT weights, issued
 // back-to-back by the elected lane: NTAPS taps x KSTEPS K-steps, compile-time offsets.
 template <int NTAPS, int KSTEPS>
@@ -143,8 +174,11 @@ __device__ __forceinline__ void issue_slab_masked(uint32_t d_tmem, uint64_t a_de
 
 }  // namespace
 
+template <int KC>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
+  constexpr int P = 2 * KC;        // bytes per halo pixel / weight row (128: SW128, 64: SW64)
+  constexpr int KSTEPS = KC / 16;  // tcgen05.mma K-steps per slab and tap
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -204,23 +238,25 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     // ===================== A producer: halo boxes (+ residual tiles) =====================
     int as = 0;
     uint32_t aph = 0;
-    const uint32_t a_box_bytes = (uint32_t)(HW * HH * 128);
+    const uint32_t a_box_bytes = (uint32_t)(HW * HH * P);
     int rb = 0;
     uint32_t rph = 0;
     unsigned long long* pr = (p.prof && blockIdx.x == 0 && lane == 0) ? p.prof : nullptr;
     const long long pstart = pr ? dev_clock() : 0;
+    ProfClock pc(pr);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n_tile, X0, Y0, n;
       halo_decode(p, t, n_tile, X0, Y0, n);
-      if (pr) pr[2] += 1;
+      pc.count<2>();
       if (p.res_map) {
         // residual tile of this output tile, in the epilogue's staging layout
         mbar_wait(&ctl->res_empty[rb], rph ^ 1);
         if (elect_one()) {
-          const int groups = p.BN >> 6;
-          mbar_arrive_expect_tx(&ctl->res_full[rb], (uint32_t)(groups * 16384));
+          const int groups = (p.BN + 63) >> 6;
+          const uint32_t gbytes = p.BN >= 64 ? 16384u : 8192u;  // 128 rows of 64 (or 32) channels
+          mbar_arrive_expect_tx(&ctl->res_full[rb], groups * gbytes);
           for (int g = 0; g < groups; ++g)
-            tma_load_5d(p.res_map, &ctl->res_full[rb], res_stage + (size_t)rb * p.out_buf_bytes + g * 16384,
+            tma_load_5d(p.res_map, &ctl->res_full[rb], res_stage + (size_t)rb * p.out_buf_bytes + g * gbytes,
                         p.cout_off + n_tile * p.BN + g * 64, X0, 0, Y0, n);
         }
         __syncwarp();
@@ -230,17 +266,15 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         }
       }
       for (int cs = 0; cs < p.ncs; ++cs) {
-        {
-          ProfClock pc(pr);
-          mbar_wait(&ctl->a_empty[as], aph ^ 1);
-          pc.lap(1);
-        }
+        pc.lap<3>();
+        mbar_wait(&ctl->a_empty[as], aph ^ 1);
+        pc.lap<1>();
         if (elect_one()) {
           if (p.dbg & 1) {
             mbar_arrive(&ctl->a_full[as]);
           } else {
             mbar_arrive_expect_tx(&ctl->a_full[as], a_box_bytes);
-            tma_load_5d(p.map, &ctl->a_full[as], a_ring + (size_t)as * p.a_stage_bytes, p.cin_off + cs * 64, X0 - p.dil, 0,
+            tma_load_5d(p.map, &ctl->a_full[as], a_ring + (size_t)as * p.a_stage_bytes, p.cin_off + cs * KC, X0 - p.dil, 0,
                         Y0 - p.dil, n);
           }
         }
@@ -251,7 +285,10 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         }
       }
     }
-    if (pr) pr[0] += (unsigned long long)(dev_clock() - pstart);
+    if (pr) {
+      pc.a[0] = (unsigned long long)(dev_clock() - pstart);
+      pc.flush(0);
+    }
   } else if (warp == 2) {
     // ===================== B producer: weight images =====================
     if (resident) {
@@ -295,27 +332,26 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       int as = mw, bs = 0, acc = mw;
       uint32_t aph = 0, bph = 0, acc_phase = 0;
       const uint32_t idesc = umma_idesc_act(128, p.BN);
-      const uint32_t sbo = (uint32_t)HW * 128;
-      const uint64_t a_desc0 = umma_smem_desc_sw128(smem_u32(a_ring), sbo);
-      const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(b_area), 1024);
+      const uint64_t a_desc0 = desc_compact<P>(smem_u32(a_ring), (uint32_t)HW * P);
+      const uint64_t b_desc0 = desc_compact<P>(smem_u32(b_area), 8 * P);
       const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4;
       const uint32_t b_step = (uint32_t)p.b_bytes >> 4;
-      const uint32_t row_units = (uint32_t)(p.dil * HW * 8);  // one dilated halo row, in 16-byte units
-      const uint32_t col_units = (uint32_t)(p.dil * 8);
+      const uint32_t row_units = (uint32_t)(p.dil * HW * (P / 16));  // one dilated halo row, in 16-byte units
+      const uint32_t col_units = (uint32_t)(p.dil * (P / 16));
       if (resident) mbar_wait(&ctl->w_full, 0);
       unsigned long long* pr = (p.prof && blockIdx.x == 0 && lane == 0 && mw == 0) ? p.prof : nullptr;
       const long long mstart = pr ? dev_clock() : 0;
       ProfClock pc(pr);
       for (int t = blockIdx.x + mw * gridDim.x; t < total_tiles; t += MW * gridDim.x) {
-        pc.lap(7);
+        pc.lap<3>();
         mbar_wait(&ctl->acc_empty[acc], acc_phase ^ 1);
-        pc.lap(5);
+        pc.lap<1>();
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
         for (int cs = 0; cs < p.ncs; ++cs) {
-          pc.lap(7);
+          pc.lap<3>();
           mbar_wait(&ctl->a_full[as], aph);
-          pc.lap(6);
+          pc.lap<2>();
           tc_fence_after_sync();
           const uint64_t a_stage_desc = desc_add(a_desc0, as * a_step);
           if (resident) {
@@ -323,11 +359,11 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               if (p.dbg & 2)
                 umma_bf16_ss(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), idesc, cs != 0 ? 1u : 0u);
               else if (p.use_kmask)
-                issue_slab_masked<9, 4>(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), b_step, row_units,
-                                        col_units, idesc, cs != 0, p.kmask[cs]);
+                issue_slab_masked<9, KSTEPS>(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), b_step, row_units,
+                                             col_units, idesc, cs != 0, p.kmask[cs]);
               else
-                issue_slab_resident<9, 4>(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), b_step, row_units,
-                                          col_units, idesc, cs != 0);
+                issue_slab_resident<9, KSTEPS>(d_tmem, a_stage_desc, desc_add(b_desc0, cs * 9 * b_step), b_step,
+                                               row_units, col_units, idesc, cs != 0);
               umma_commit(&ctl->a_empty[as]);
               if (cs == p.ncs - 1) umma_commit(&ctl->acc_full[acc]);
             }
@@ -341,7 +377,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
                 const uint64_t at = desc_add(a_stage_desc, (tap / 3) * row_units + (tap % 3) * col_units);
                 const uint64_t bt = desc_add(b_desc0, bs * b_step);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < KSTEPS; ++k)
                   umma_bf16_ss(d_tmem, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc,
                                (tap | k) != 0 ? 1u : (cs != 0 ? 1u : 0u));
                 umma_commit(&ctl->b_empty[bs]);
@@ -369,16 +405,19 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           acc_phase ^= 1;
         }
       }
-      if (pr) pr[4] += (unsigned long long)(dev_clock() - mstart);
+      if (pr) {
+        pc.a[0] = (unsigned long long)(dev_clock() - mstart);
+        pc.a[4] = pc.a[5] = pc.a[6] = pc.a[7] = 0;
+        pc.flush(8);
+      }
     }
   } else if (warp == HALO_STORE_WARP) {
     // ===================== TMA store issuer (shared-memory epilogue) =====================
     // Waits until an epilogue group has filled a staging buffer, hands it to TMA and gives the
-    // buffer back once TMA has read it (one store behind, so the wait is normally already over).
+    // buffer back once TMA has read it.
     if (smem_epi && lane == 0) {
       int ob = 0;
       uint32_t oph = 0;
-      int prev_ob = -1;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(&ctl->out_full[ob], oph);
         if (!(p.dbg & 4)) {
@@ -387,29 +426,22 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           if (p.out_f32) {
             tma_store_5d(p.out_map, out_stage + (size_t)ob * p.out_buf_bytes, 0, X0, 0, Y0, n);
           } else {
-            for (int g = 0; g < (p.BN >> 6); ++g)
-              tma_store_5d(p.out_map, out_stage + (size_t)ob * p.out_buf_bytes + g * 16384, p.cout_off + g * 64, X0, 0,
+            const uint32_t gbytes = p.BN >= 64 ? 16384u : 8192u;
+            for (int g = 0; g < ((p.BN + 63) >> 6); ++g)
+              tma_store_5d(p.out_map, out_stage + (size_t)ob * p.out_buf_bytes + g * gbytes, p.cout_off + g * 64, X0, 0,
                            Y0, n);
           }
         }
         tma_store_commit();
-        if (p.out_bufs == 2) {
-          if (prev_ob >= 0) {
-            tma_store_wait_read<1>();
-            mbar_arrive(&ctl->out_empty[prev_ob]);
-          }
-          prev_ob = ob;
-        } else {
-          tma_store_wait_read<0>();
-          mbar_arrive(&ctl->out_empty[ob]);
-        }
+        // hand the buffer back as soon as TMA has read it (this warp has nothing else to do;
+        // releasing one store late would make the two epilogue groups wait for each other)
+        tma_store_wait_read<0>();
+        mbar_arrive(&ctl->out_empty[ob]);
         if (++ob == p.out_bufs) {
           ob = 0;
           oph ^= 1;
         }
       }
-      tma_store_wait_read<0>();
-      if (prev_ob >= 0) mbar_arrive(&ctl->out_empty[prev_ob]);
       tma_store_wait_all<0>();
     }
   } else if (smem_epi) {
@@ -432,12 +464,12 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     const long long estart = pr ? dev_clock() : 0;
     ProfClock pc(pr);
     for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles; t += G * gridDim.x) {
-      if (pr) pr[15] += 1;
+      pc.count<7>();
       const uint32_t ost = out_addr0 + (uint32_t)ob * p.out_buf_bytes;
       const uint32_t rst = res_addr0 + (uint32_t)rb * p.out_buf_bytes;
-      pc.lap(14);
+      pc.lap<6>();
       mbar_wait(&ctl->acc_full[acc], acc_phase);
-      pc.lap(10);
+      pc.lap<2>();
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(quarter * 32) << 16);
       if (!p.out_f32) {
@@ -449,16 +481,19 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         tmem_ld_wait();
         if (has_res) mbar_wait(&ctl->res_full[rb], rph);
         mbar_wait(&ctl->out_empty[ob], oph ^ 1);  // TMA has read the previous tile out of this buffer
-        pc.lap(11);
+        pc.lap<3>();
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           const int c = c_begin + ci * c_step;
           if (c >= p.BN) break;
-          const uint32_t row_off = (uint32_t)(c >> 6) * 16384u + (uint32_t)row * 128u;
+          // staging rows hold 64 channels (128 B, SW128) or, for BN == 32, 32 channels (64 B, SW64)
+          const bool wide = p.BN >= 64;
+          const uint32_t row_off = wide ? (uint32_t)(c >> 6) * 16384u + (uint32_t)row * 128u : (uint32_t)row * 64u;
+          const uint32_t swz_row = wide ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
           const int j0 = (c & 63) >> 3;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint32_t off = row_off + ((uint32_t)((j0 + q) ^ (row & 7)) << 4);
+            const uint32_t off = row_off + (((uint32_t)(j0 + q) ^ swz_row) << 4);
             const float4 b0 = *reinterpret_cast<const float4*>(bt + c + q * 8);
             const float4 b1 = *reinterpret_cast<const float4*>(bt + c + q * 8 + 4);
             float f0 = __uint_as_float(v[ci][q * 8 + 0]) + b0.x, f1 = __uint_as_float(v[ci][q * 8 + 1]) + b0.y;
@@ -491,7 +526,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           tmem_ld_wait();
         }
         mbar_wait(&ctl->out_empty[ob], oph ^ 1);
-        pc.lap(11);
+        pc.lap<3>();
         if (active) {
           const uint32_t row_off = (uint32_t)row * f32_pitch;
 #pragma unroll
@@ -510,7 +545,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           }
         }
       }
-      pc.lap(12);
+      pc.lap<4>();
       // publish: staging buffer to the async proxy / store warp, accumulator stage and
       // residual buffer back to their producers -- one arrival per warp
       tc_fence_before_sync();
@@ -521,7 +556,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         mbar_arrive(&ctl->acc_empty[acc]);
         if (has_res) mbar_arrive(&ctl->res_empty[rb]);
       }
-      pc.lap(13);
+      pc.lap<5>();
       acc += G;
       if (acc >= p.acc_stages) {
         acc -= p.acc_stages;
@@ -541,7 +576,10 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         }
       }
     }
-    if (pr) pr[8] += (unsigned long long)(dev_clock() - estart);
+    if (pr) {
+      pc.a[0] = (unsigned long long)(dev_clock() - estart);
+      pc.flush(16);
+    }
   } else {
     // ===================== direct epilogue (per-thread global stores) =====================
     int acc = 0;
@@ -649,20 +687,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-// K-major operand descriptor for the compact layouts: pitch 32 -> SW32 (6), 64 -> SW64 (4),
-// 128 -> SW128 (2); sbo = byte distance between consecutive 8-row groups.
-template <int PITCH>
-__device__ __forceinline__ uint64_t desc_compact(uint32_t addr, uint32_t sbo) {
-  constexpr uint64_t layout = PITCH == 128 ? 2ull : (PITCH == 64 ? 4ull : 6ull);
-  return (uint64_t)((addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
-         (layout << 61);
-}
-// Swizzle<B,4,3> of a byte offset relative to a 1024-byte aligned base.
-template <int PITCH>
-__device__ __forceinline__ uint32_t swz(uint32_t off) {
-  constexpr uint32_t mask = PITCH == 128 ? 7u : (PITCH == 64 ? 3u : 1u);
-  return off ^ (((off >> 7) & mask) << 4);
 }
 }  // namespace
 
@@ -1153,7 +1177,9 @@ size_t conv_halo_smem_bytes(const ConvHaloParams& p) {
 }
 
 cudaError_t conv_halo_configure() {
-  cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   ConvHalo2Params q{};
   q.stem = 1;
   if (e == cudaSuccess) e = halo2_dispatch(q, 0, 0, nullptr, true);
@@ -1178,7 +1204,8 @@ cudaError_t launch_conv_halo(const ConvHaloParams& p0, int num_sms, cudaStream_t
   p.div_tx = make_fastdiv((uint32_t)p.tiles_x);
   p.div_ty = make_fastdiv((uint32_t)p.tiles_y);
   const int grid = total_tiles < num_sms ? (int)total_tiles : num_sms;
-  conv_halo_kernel<<<grid, HALO_THREADS, conv_halo_smem_bytes(p), st>>>(p);
+  if (p.kc == 32) conv_halo_kernel<32><<<grid, HALO_THREADS, conv_halo_smem_bytes(p), st>>>(p);
+  else conv_halo_kernel<64><<<grid, HALO_THREADS, conv_halo_smem_bytes(p), st>>>(p);
   return cudaGetLastError();
 }
 

@@ -43,7 +43,8 @@ struct ConvHaloParams {
   int32_t NB, H, W;
   int32_t n_base;            // first image of this launch
   int32_t cin_off, cout_off; // channel window of this launch (grouped conv = one 64-channel block per launch)
-  int32_t ncs;               // input channels of the launch / 64
+  int32_t kc;                // channels per K-slab: 64 (default when 0) or 32 (Cin % 64 != 0)
+  int32_t ncs;               // input channels of the launch / kc
   int32_t dil;
   int32_t tiles_x, tiles_y;
   int32_t a_stages, a_stage_bytes;

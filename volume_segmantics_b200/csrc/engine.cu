@@ -152,6 +152,7 @@ struct vsb_engine {
   bool no_halo = false;
   bool no_tma_epilogue = false;  // vsb_set_flag("tma_epilogue", 0): per-thread global stores in the halo epilogue
   int halo_a_stages_max = 8;     // vsb_set_flag("halo_a_stages", n)
+  bool sync_each = false;        // vsb_set_flag("sync_each", 1): synchronise after every op and name the one that failed
   bool no_fuse_pool = false;     // vsb_set_flag("fuse_pool", 0): separate max-pool kernel after the stem
   bool no_mma2 = false;          // vsb_set_flag("mma_warps", 1): a single MMA issuing warp everywhere
   bool no_epi_groups = false;    // vsb_set_flag("epi_groups", 0): one epilogue group even for BN <= 64
@@ -456,12 +457,22 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
           }
         }
       }
+  // 32-channel-slab variant only for BN >= 64: 32 -> 32 layers run faster on the MT-tiled halo2 kernel
   cp.halo_ok = op.n_src == 1 && !cp.ps && !cp.s2 && op.kh == 3 && op.kw == 3 && op.pad == op.dil &&
-               (op.dil == 1 || op.dil == 2) && e->tdesc[op.src[0]].channels % 64 == 0;
+               (op.dil == 1 || op.dil == 2) &&
+               (e->tdesc[op.src[0]].channels % 64 == 0 || (e->tdesc[op.src[0]].channels % 32 == 0 && cp.BN >= 64));
   if (cp.halo_ok) {
-    const int ncs = op.cin / 64;
-    const size_t img = (size_t)cp.BN * 128;
+    // K-slabs of 64 channels (128-byte rows, SW128) or, when Cin is only a multiple of 32,
+    // of 32 channels (64-byte rows, SW64)
+    const int kc = op.cin % 64 == 0 ? 64 : 32, P = 2 * kc, ksteps = kc / 16;
+    const uint32_t swz_mask = P == 128 ? 7u : 3u;
+    const int ncs = op.cin / kc;
+    const size_t img = (size_t)cp.BN * P;
     std::vector<uint8_t> hp((size_t)cp.n_tiles * ncs * 9 * img, 0);
+    auto woff = [&](int n, int ch) {  // byte offset of 16-byte chunk `ch` of row n in a swizzled image
+      uint32_t off = (uint32_t)(n * P + ch * 16);
+      return off ^ (((off >> 7) & swz_mask) << 4);
+    };
     for (int nt = 0; nt < cp.n_tiles; ++nt)
       for (int cs = 0; cs < ncs; ++cs)
         for (int tap = 0; tap < 9; ++tap) {
@@ -469,30 +480,31 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
           for (int n = 0; n < cp.BN; ++n) {
             const int o = nt * cp.BN + n;
             if (o >= op.cout) break;
-            const int64_t wrow = (((int64_t)o * 3 + tap / 3) * 3 + tap % 3) * op.cin + cs * 64;
-            for (int ch = 0; ch < 8; ++ch)
-              memcpy(dst + (size_t)n * 128 + ((ch ^ (n & 7)) * 16), e->h_weights.data() + op.w_off + (wrow + ch * 8) * 2, 16);
+            const int64_t wrow = (((int64_t)o * 3 + tap / 3) * 3 + tap % 3) * op.cin + cs * kc;
+            for (int ch = 0; ch < kc / 8; ++ch)
+              memcpy(dst + woff(n, ch), e->h_weights.data() + op.w_off + (wrow + ch * 8) * 2, 16);
           }
         }
     CK(cudaMalloc(&cp.d_whalo, hp.size()));
     CK(cudaMemcpy(cp.d_whalo, hp.data(), hp.size(), cudaMemcpyHostToDevice));
+    cp.hparams.kc = kc;
     // K-steps (tap, 16-channel block) whose weights are all zero need no MMA (structured
-    // sparsity of the space-to-depth convolutions, plan.py): bit tap*4+k of kmask[slab].
+    // sparsity of the space-to-depth convolutions, plan.py): bit tap*ksteps+k of kmask[slab].
     cp.hparams.use_kmask = 0;
     if (cp.n_tiles == 1 && ncs <= vsb::HALO_KMASK_SLABS) {
       bool any_zero = false;
       for (int cs = 0; cs < ncs; ++cs) {
         uint64_t m = 0;
         for (int tap = 0; tap < 9; ++tap)
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < ksteps; ++k) {
             bool nz = false;
             const uint8_t* im = hp.data() + ((size_t)cs * 9 + tap) * img;
             for (int n = 0; n < cp.BN && !nz; ++n)
               for (int ch = 2 * k; ch < 2 * k + 2 && !nz; ++ch) {
-                const uint64_t* q = reinterpret_cast<const uint64_t*>(im + (size_t)n * 128 + ((ch ^ (n & 7)) * 16));
+                const uint64_t* q = reinterpret_cast<const uint64_t*>(im + woff(n, ch));
                 nz = (q[0] | q[1]) != 0;
               }
-            if (nz) m |= 1ull << (tap * 4 + k);
+            if (nz) m |= 1ull << (tap * ksteps + k);
             else any_zero = true;
           }
         cp.hparams.kmask[cs] = m;
@@ -614,10 +626,12 @@ int configure_halo_pipeline(vsb_engine* e, ConvPlan& cp, vsb::ConvHaloParams& h,
   h.out_buf_bytes = 0;
   const bool has_res = op.res >= 0;
   bool tma_epi = !e->no_tma_epilogue && h.n_tiles == 1;
-  if (ot.dtype == 0) tma_epi = tma_epi && h.BN % 64 == 0 && h.BN <= 128 && op.cout % 64 == 0;
+  if (ot.dtype == 0)
+    tma_epi = tma_epi && ((h.BN % 64 == 0 && h.BN <= 128 && op.cout % 64 == 0) || (h.BN == 32 && op.cout == 32));
   else tma_epi = tma_epi && !has_res && op.cout % 4 == 0 && op.cout <= 32 && op.cout <= h.BN;
   if (tma_epi) {
-    h.out_buf_bytes = ot.dtype == 0 ? (h.BN / 64) * 16384 : (int)align_up((size_t)128 * op.cout * 4, 1024);
+    h.out_buf_bytes = ot.dtype == 0 ? (h.BN >= 64 ? (h.BN / 64) * 16384 : 8192)
+                                    : (int)align_up((size_t)128 * op.cout * 4, 1024);
     h.out_bufs = h.out_buf_bytes <= 16384 ? 2 : 1;
     h.res_bufs = has_res ? h.out_bufs : 0;
     // Only where the weights stay resident next to the staging buffers: streamed-weight
@@ -648,17 +662,27 @@ int configure_halo_pipeline(vsb_engine* e, ConvPlan& cp, vsb::ConvHaloParams& h,
     }
   }
   // two MMA warps need the tile sequence to be the A-ring slab sequence (one slab per tile)
-  if (h.b_stages == 0 && h.ncs == 1 && h.a_stages >= 2 && !e->no_mma2) h.mma_warps = 2;
+  if (h.b_stages == 0 && h.ncs == 1 && h.a_stages >= 2 && !e->no_mma2) {
+    // A ring stage must always meet the same MMA warp: with an odd depth the two warps would
+    // alternate on a stage, and the one running ahead could mistake the previous phase of that
+    // stage's mbarrier for its own (parity aliasing) -- seen as a launch failure at depth 7.
+    // Depth 3 keeps one warp and all three stages (measured faster than 2 + 2).
+    if (h.a_stages != 3) {
+      h.mma_warps = 2;
+      h.a_stages &= ~1;
+    }
+  }
   if (tma_epi) {
     TmaDesc m;
     int rc;
-    if (ot.dtype == 0) rc = make_tensor_map(e, &m, ot, nb, false, 64, 8, 16, 1);
+    const int obox = h.BN >= 64 ? 64 : 32;  // channels per staging row (SW128 / SW64)
+    if (ot.dtype == 0) rc = make_tensor_map(e, &m, ot, nb, false, obox, 8, 16, 1);
     else rc = make_tensor_map(e, &m, ot, nb, false, op.cout, 8, 16, 1, true);
     if (rc) return rc;
     CK(cudaMemcpy(cp.d_maps + (VSB_MAX_SRC - 2), &m, sizeof(m), cudaMemcpyHostToDevice));
     h.out_map = cp.d_maps + (VSB_MAX_SRC - 2);
     if (has_res) {
-      rc = make_tensor_map(e, &m, e->tens[op.res], nb, false, 64, 8, 16, 1);
+      rc = make_tensor_map(e, &m, e->tens[op.res], nb, false, obox, 8, 16, 1);
       if (rc) return rc;
       CK(cudaMemcpy(cp.d_maps + (VSB_MAX_SRC - 3), &m, sizeof(m), cudaMemcpyHostToDevice));
       h.res_map = cp.d_maps + (VSB_MAX_SRC - 3);
@@ -817,6 +841,7 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
         h.dil = op.dil;
         h.tiles_x = tx;
         h.tiles_y = ty;
+        h.kc = 64;
         h.b_bytes = 64 * 128;
         h.a_stage_bytes = (int)align_up((size_t)HW * HH * 128, 1024);
         {
@@ -936,17 +961,19 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
       vsb::ConvHaloParams& h = cp.hparams;
       h.dil = op.dil;
       const int HW = 8 + 2 * op.dil, HH = 16 + 2 * op.dil;
-      h.ncs = op.cin / 64;
+      const int kc = h.kc ? h.kc : 64;
+      h.kc = kc;
+      h.ncs = op.cin / kc;
       h.BN = cp.BN;
       h.n_tiles = cp.n_tiles;
-      h.b_bytes = cp.BN * 128;
-      h.a_stage_bytes = (int)align_up((size_t)HW * HH * 128, 1024);
+      h.b_bytes = cp.BN * 2 * kc;
+      h.a_stage_bytes = (int)align_up((size_t)HW * HH * 2 * kc, 1024);
       int fit = configure_halo_pipeline(e, cp, h, op, ot, nb);
       if (fit < 0) return fit;
       if (eff >= 0.6 && fit == 0 && (h.b_stages == 0 || h.b_stages >= 2)) {
         TmaDesc hm;
         const TensorBuf& st = e->tens[op.src[0]];
-        int rc = make_tensor_map(e, &hm, st, nb, false, 64, HW, HH, 1);
+        int rc = make_tensor_map(e, &hm, st, nb, false, kc, HW, HH, 1);
         if (rc) return rc;
         // the halo map lives in slot VSB_MAX_SRC - 1 of this op's map array (single-source op)
         CK(cudaMemcpy(cp.d_maps + (VSB_MAX_SRC - 1), &hm, sizeof(hm), cudaMemcpyHostToDevice));
@@ -1038,11 +1065,11 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
       CK(cudaMemcpyAsync(v, e->d_halo_prof, sizeof(v), cudaMemcpyDeviceToHost, e->stream));
       CK(cudaStreamSynchronize(e->stream));
       fprintf(stderr,
-              "[halo_prof] op %d BN %d ncs %d a_stages %d b_stages %d acc %d groups %d | producer: total %llu wait_a_empty %llu tiles %llu"
-              " | mma: total %llu wait_acc_empty %llu wait_a_full %llu issue %llu | epi: total %llu store_rd %llu acc_full %llu"
-              " ld+bar1 %llu math %llu arrive+bar2 %llu store %llu tiles %llu\n",
-              oi, h.BN, h.ncs, h.a_stages, h.b_stages, h.acc_stages, h.epi_groups, v[0], v[1], v[2], v[4], v[5], v[6], v[7], v[8],
-              v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+              "[halo_prof] op %d BN %d kc %d ncs %d a_stages %d b_stages %d acc %d groups %d mma %d | producer: total %llu wait_a_empty %llu tiles %llu"
+              " | mma0: total %llu wait_acc_empty %llu wait_a_full %llu issue %llu | epi0: total %llu acc_full %llu"
+              " ld+waits %llu math %llu publish %llu loop %llu tiles %llu\n",
+              oi, h.BN, h.kc, h.ncs, h.a_stages, h.b_stages, h.acc_stages, h.epi_groups, h.mma_warps, v[0], v[1], v[2], v[8],
+              v[9], v[10], v[11], v[16], v[18], v[19], v[20], v[21], v[22], v[23]);
     }
     return VSB_OK;
   }
@@ -1228,6 +1255,12 @@ int run_network(vsb_engine* e, int nb, int* head_idx) {
       for (int k = i; k < j; ++k) {
         int rc = run_op(e, k, n0, cnt);
         if (rc) return rc;
+        if (e->sync_each) {  // debugging aid (vsb_set_flag("sync_each", 1)): localise a failing launch
+          const cudaError_t se = cudaStreamSynchronize(e->stream);
+          if (se != cudaSuccess)
+            return fail(VSB_ERR_CUDA, "op %d (kind %d, cin %d, cout %d) failed: %s", k, e->ops[k].kind, e->ops[k].cin,
+                        e->ops[k].cout, cudaGetErrorString(se));
+        }
       }
     }
     i = j;
@@ -1636,6 +1669,7 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
     if (value && !e->d_halo_prof) CK(cudaMalloc(&e->d_halo_prof, 32 * 8));
     if (!value && e->d_halo_prof) { cudaFree(e->d_halo_prof); e->d_halo_prof = nullptr; }
   }
+  else if (n == "sync_each") e->sync_each = value != 0;
   else if (n == "fuse_pool") { e->no_fuse_pool = value == 0; free_workspace(e); }
   else if (n == "mma_warps") { e->no_mma2 = value < 2; free_workspace(e); }
   else if (n == "epi_groups") { e->no_epi_groups = value == 0; free_workspace(e); }
