@@ -293,10 +293,17 @@ def run_ours(args):
     conv_ms, conv_n = stages["conv_tc"]
     conv_flops = 2.0 * macs_px * padded_px * args.steps
     roofline = None
+    traffic = None  # DRAM bytes per conv launch from the committed ncu capture of one batch (profiles/)
+    tpath = ROOT / "profiles" / "r01_conv_traffic.json"
+    if tpath.exists() and size == 1024:
+        traffic = json.loads(tpath.read_text()).get("dram_bytes_per_conv_launch")
     if conv_ms > 0:
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "tcgen05 conv kernels (conv_halo_kernel, conv_halo2_kernel<>, conv_tc_kernel<>)", "achieved": ach,
-                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, average over the conv launches of one "
+                                      "batch of 32 slices of 1024^2 (profiles/r01_ncu_batch32_dram.csv)" if traffic else None,
+                    "peak_source": peak_src,
                     "launches": conv_n, "avg_launch_ms": conv_ms / max(1, conv_n),
                     "flops_per_launch": conv_flops / max(1, conv_n),
                     "share_of_step": conv_ms / ms_prof,
