@@ -80,8 +80,11 @@ static __device__ __noinline__ void epilogue_group8_generic(EpiOut p, uint32_t a
 
 // 8 accumulator columns of one pixel (channels ch..ch+7): + bias, + residual, ReLU, store.
 // Fast path: 16-bit output, cout % 8 == 0 (whole group in range).
+// `pre` / `use_pre`: residual chunk already in registers (prefetched before the accumulator was ready); passed
+// by value so the caller's prefetch arrays are never address-taken (a pointer select put them in local memory).
 __device__ __forceinline__ void epilogue_group8(const EpiOut& p, const uint32_t* v8, const float* bias_s,
-                                                int64_t pix, int ch, const uint4* res_pre = nullptr) {
+                                                int64_t pix, int ch, uint4 pre = make_uint4(0u, 0u, 0u, 0u),
+                                                bool use_pre = false) {
   if (p.out_f32 || (p.cout & 7)) {
     epilogue_group8_generic(p, v8[0], v8[1], v8[2], v8[3], v8[4], v8[5], v8[6], v8[7], bias_s, pix, ch);
     return;
@@ -95,7 +98,7 @@ __device__ __forceinline__ void epilogue_group8(const EpiOut& p, const uint32_t*
   float f6 = __uint_as_float(v8[6]) + b1.z, f7 = __uint_as_float(v8[7]) + b1.w;
   const int64_t off = pix * p.cout + ch;
   if (p.residual) {
-    const uint4 rv = res_pre ? *res_pre : __ldg(reinterpret_cast<const uint4*>(p.residual + off));
+    const uint4 rv = use_pre ? pre : __ldg(reinterpret_cast<const uint4*>(p.residual + off));
     float2 r;
     r = unpack_act2(rv.x); f0 += r.x; f1 += r.y;
     r = unpack_act2(rv.y); f2 += r.x; f3 += r.y;
@@ -113,10 +116,15 @@ __device__ __forceinline__ void epilogue_group8(const EpiOut& p, const uint32_t*
 
 // 32 accumulator columns [c, c+32) of one pixel.
 __device__ __forceinline__ void epilogue_chunk32(const EpiOut& p, const uint32_t (&v)[32], const float* bias_s,
-                                                 int64_t pix, int ch_base, const uint4* res_pre = nullptr) {
+                                                 int64_t pix, int ch_base) {
 #pragma unroll
-  for (int g8 = 0; g8 < 4; ++g8)
-    epilogue_group8(p, &v[g8 * 8], bias_s, pix, ch_base + g8 * 8, res_pre ? res_pre + g8 : nullptr);
+  for (int g8 = 0; g8 < 4; ++g8) epilogue_group8(p, &v[g8 * 8], bias_s, pix, ch_base + g8 * 8);
+}
+// Same with the residual of the chunk prefetched into `pre` (valid when use_pre).
+__device__ __forceinline__ void epilogue_chunk32_pre(const EpiOut& p, const uint32_t (&v)[32], const float* bias_s,
+                                                     int64_t pix, int ch_base, const uint4 (&pre)[4], bool use_pre) {
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) epilogue_group8(p, &v[g8 * 8], bias_s, pix, ch_base + g8 * 8, pre[g8], use_pre);
 }
 
 // Issue the residual loads of one 32-channel chunk early (before the accumulator is ready)

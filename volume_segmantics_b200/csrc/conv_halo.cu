@@ -290,7 +290,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       pc.flush(0);
     }
   } else if (warp == 2) {
-    // ===================== B producer: weight images =====================
+    // ===================== B producer: weight images; then TMA store issuer =====================
     if (resident) {
       if (elect_one()) {
         const uint32_t total = (uint32_t)(p.ncs * 9 * p.b_bytes);
@@ -300,6 +300,37 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
                        &ctl->w_full);
       }
       __syncwarp();
+      // Shared-memory epilogue (resident launches only): wait until an epilogue group has filled a
+      // staging buffer, hand it to TMA and give the buffer back once TMA has read it.
+      if (smem_epi && lane == 0) {
+        int ob = 0;
+        uint32_t oph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          mbar_wait(&ctl->out_full[ob], oph);
+          if (!(p.dbg & 4)) {
+            int n_tile, X0, Y0, n;
+            halo_decode(p, t, n_tile, X0, Y0, n);
+            if (p.out_f32) {
+              tma_store_5d(p.out_map, out_stage + (size_t)ob * p.out_buf_bytes, 0, X0, 0, Y0, n);
+            } else {
+              const uint32_t gbytes = p.BN >= 64 ? 16384u : 8192u;
+              for (int g = 0; g < ((p.BN + 63) >> 6); ++g)
+                tma_store_5d(p.out_map, out_stage + (size_t)ob * p.out_buf_bytes + g * gbytes, p.cout_off + g * 64, X0,
+                             0, Y0, n);
+            }
+          }
+          tma_store_commit();
+          // this warp has nothing else to do; releasing one store late would make the two
+          // epilogue groups wait for each other
+          tma_store_wait_read<0>();
+          mbar_arrive(&ctl->out_empty[ob]);
+          if (++ob == p.out_bufs) {
+            ob = 0;
+            oph ^= 1;
+          }
+        }
+        tma_store_wait_all<0>();
+      }
     } else {
       int bs = 0;
       uint32_t bph = 0;
@@ -410,39 +441,6 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         pc.a[4] = pc.a[5] = pc.a[6] = pc.a[7] = 0;
         pc.flush(8);
       }
-    }
-  } else if (warp == HALO_STORE_WARP) {
-    // ===================== TMA store issuer (shared-memory epilogue) =====================
-    // Waits until an epilogue group has filled a staging buffer, hands it to TMA and gives the
-    // buffer back once TMA has read it.
-    if (smem_epi && lane == 0) {
-      int ob = 0;
-      uint32_t oph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        mbar_wait(&ctl->out_full[ob], oph);
-        if (!(p.dbg & 4)) {
-          int n_tile, X0, Y0, n;
-          halo_decode(p, t, n_tile, X0, Y0, n);
-          if (p.out_f32) {
-            tma_store_5d(p.out_map, out_stage + (size_t)ob * p.out_buf_bytes, 0, X0, 0, Y0, n);
-          } else {
-            const uint32_t gbytes = p.BN >= 64 ? 16384u : 8192u;
-            for (int g = 0; g < ((p.BN + 63) >> 6); ++g)
-              tma_store_5d(p.out_map, out_stage + (size_t)ob * p.out_buf_bytes + g * gbytes, p.cout_off + g * 64, X0, 0,
-                           Y0, n);
-          }
-        }
-        tma_store_commit();
-        // hand the buffer back as soon as TMA has read it (this warp has nothing else to do;
-        // releasing one store late would make the two epilogue groups wait for each other)
-        tma_store_wait_read<0>();
-        mbar_arrive(&ctl->out_empty[ob]);
-        if (++ob == p.out_bufs) {
-          ob = 0;
-          oph ^= 1;
-        }
-      }
-      tma_store_wait_all<0>();
     }
   } else if (smem_epi) {
     // ===================== epilogue through shared memory (stores by the store warp) =====================
@@ -605,13 +603,17 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       mbar_wait(&ctl->acc_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(quarter * 32) << 16);
-      for (int c = half * 32; c < p.BN; c += 64) {
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {  // BN <= 256: at most four 32-column chunks per thread
+        const int c = half * 32 + ci * 64;
+        if (c >= p.BN) break;
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c, v);
         tmem_ld_wait();
         if (valid) {
-          const uint4* rp = (c == half * 32 && have0) ? rpre0 : ((c == half * 32 + 64 && have1) ? rpre1 : nullptr);
-          epilogue_chunk32(eo, v, bias_s, pix, ch0 + c, rp);
+          if (ci == 0) epilogue_chunk32_pre(eo, v, bias_s, pix, ch0 + c, rpre0, have0);
+          else if (ci == 1) epilogue_chunk32_pre(eo, v, bias_s, pix, ch0 + c, rpre1, have1);
+          else epilogue_chunk32(eo, v, bias_s, pix, ch0 + c);
         }
       }
       tc_fence_before_sync();

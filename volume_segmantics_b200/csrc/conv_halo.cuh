@@ -145,8 +145,10 @@ cudaError_t launch_conv_halo2(const ConvHalo2Params& p, int num_sms, cudaStream_
 
 constexpr int HALO_EPI_WARPS = 8;
 constexpr int HALO_MMA2_WARP = 3 + HALO_EPI_WARPS;   // second MMA issuer (mma_warps == 2)
-constexpr int HALO_STORE_WARP = 4 + HALO_EPI_WARPS;  // TMA store issuer of the shared-memory epilogue
-constexpr int HALO_THREADS = 32 * (5 + HALO_EPI_WARPS);
+// 12 warps = 384 threads: ptxas sizes the register file for the block rounded up to 128 threads, so a 13th
+// warp would cap the kernel at 128 registers (spills in the epilogue).  The TMA-store issuer of the
+// shared-memory epilogue is therefore the weight-producer warp (2), idle once resident weights are loaded.
+constexpr int HALO_THREADS = 32 * (4 + HALO_EPI_WARPS);
 constexpr int HALO_MAX_A_STAGES = 8;
 constexpr int HALO_MAX_B_STAGES = 8;
 

@@ -143,7 +143,8 @@ struct vsb_engine {
   // workspace
   int ws_Hp = 0, ws_Wp = 0, ws_nb = 0;
   std::vector<TensorBuf> tens;
-  std::vector<void*> ws_allocs;
+  uint8_t* arena = nullptr;   // one allocation holding every activation tensor of the workspace
+  size_t arena_bytes = 0;
   bool keep_all = false;
   bool ws_keep = false;
 
@@ -575,9 +576,9 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
   return VSB_OK;
 }
 
+// Forget the current workspace layout (the arena itself is kept and only ever grows; it is
+// released by release_arena() when the engine is destroyed or a new plan is loaded).
 void free_workspace(vsb_engine* e) {
-  for (void* p : e->ws_allocs) cudaFree(p);
-  e->ws_allocs.clear();
   e->tens.clear();
   e->ws_Hp = e->ws_Wp = e->ws_nb = 0;
 }
@@ -661,6 +662,8 @@ int configure_halo_pipeline(vsb_engine* e, ConvPlan& cp, vsb::ConvHaloParams& h,
       h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, (usable - 3 * (size_t)h.a_stage_bytes) / h.b_bytes);
     }
   }
+  // the store issuer of the shared-memory epilogue lives in the resident branch of the weight-producer warp
+  if (tma_epi && h.b_stages != 0) return fail(VSB_ERR_UNSUPPORTED, "internal: shared-memory epilogue with streamed weights");
   // two MMA warps need the tile sequence to be the A-ring slab sequence (one slab per tile)
   if (h.b_stages == 0 && h.ncs == 1 && h.a_stages >= 2 && !e->no_mma2) {
     // A ring stage must always meet the same MMA warp: with an odd depth the two warps would
@@ -719,44 +722,49 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
     for (int s = 0; s < op.n_src; ++s) e->tens[op.src[s]].last_use = i;
     if (op.res >= 0) e->tens[op.res].last_use = i;
   }
-  // allocation with reuse of dead buffers (best fit)
-  struct Block { void* p; size_t bytes; };
+  // Allocation with reuse of dead buffers (best fit) inside ONE arena: the layout is planned on
+  // offsets first, then the arena only ever grows.  A direction change of an anisotropic volume
+  // (new Hp x Wp) therefore costs no cudaFree / cudaMalloc churn (measured: 0.05 - 1.1 s per
+  // direction with per-tensor allocations).
+  struct Block { size_t off; size_t bytes; };
   std::vector<Block> freeb;
-  auto alloc = [&](size_t bytes, void** out) -> int {
+  size_t arena_end = 0;
+  std::vector<size_t> offs(nt_, (size_t)-1), blk_bytes(nt_, 0);
+  auto alloc = [&](size_t bytes, size_t* off, size_t* got) {
     int best = -1;
     if (!e->keep_all)
       for (int i = 0; i < (int)freeb.size(); ++i)
         if (freeb[i].bytes >= bytes && (best < 0 || freeb[i].bytes < freeb[best].bytes)) best = i;
     if (best >= 0 && freeb[best].bytes <= bytes * 2) {
-      *out = freeb[best].p;
+      *off = freeb[best].off;
+      *got = freeb[best].bytes;
       freeb.erase(freeb.begin() + best);
-      return VSB_OK;
+      return;
     }
-    CK(cudaMalloc(out, bytes));
-    e->ws_allocs.push_back(*out);
-    return VSB_OK;
+    *off = arena_end;
+    *got = bytes;
+    arena_end += align_up(bytes, 1024);
   };
-  std::map<void*, size_t> size_of;
-  {
-    int rc = alloc(e->tens[0].bytes, &e->tens[0].ptr);
-    if (rc) return rc;
-    size_of[e->tens[0].ptr] = e->tens[0].bytes;
-  }
+  alloc(e->tens[0].bytes, &offs[0], &blk_bytes[0]);
   for (int i = 0; i < (int)e->ops.size(); ++i) {
     for (int t = 1; t < nt_; ++t) {
       TensorBuf& b = e->tens[t];
-      if (b.first_def != i || b.ptr) continue;
-      void* p = nullptr;
-      int rc = alloc(b.bytes, &p);
-      if (rc) return rc;
-      b.ptr = p;
-      if (!size_of.count(p)) size_of[p] = b.bytes;
+      if (b.first_def != i || offs[t] != (size_t)-1) continue;
+      alloc(b.bytes, &offs[t], &blk_bytes[t]);
     }
     // free tensors whose last use is this op
     for (int t = 0; t < nt_; ++t)
-      if (e->tens[t].ptr && e->tens[t].last_use == i && e->tdesc[t].dtype == 0)
-        freeb.push_back({e->tens[t].ptr, size_of[e->tens[t].ptr]});
+      if (offs[t] != (size_t)-1 && e->tens[t].last_use == i && e->tdesc[t].dtype == 0) freeb.push_back({offs[t], blk_bytes[t]});
   }
+  if (arena_end > e->arena_bytes) {
+    if (e->arena) cudaFree(e->arena);
+    e->arena = nullptr;
+    e->arena_bytes = 0;
+    CK(cudaMalloc(&e->arena, arena_end));
+    e->arena_bytes = arena_end;
+  }
+  for (int t = 0; t < nt_; ++t)
+    if (offs[t] != (size_t)-1) e->tens[t].ptr = e->arena + offs[t];
   e->ws_Hp = Hp; e->ws_Wp = Wp; e->ws_nb = nb; e->ws_keep = e->keep_all;
 
   // tensor maps + tile geometry of the tcgen05 convolutions
@@ -1428,6 +1436,9 @@ void vsb_destroy(vsb_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   free_workspace(e);
+  cudaFree(e->arena);
+  e->arena = nullptr;
+  e->arena_bytes = 0;
   free_plan(e);
   close_peers(e);
   cudaFree(e->d_vol_owned);
