@@ -763,8 +763,17 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
     // published (wait_group -> fence.proxy.async -> arrive) once `depth` newer ones exist.
     // depth = a_stages / 2 leaves the other half of the ring published ahead of the MMA
     // warp (depth = a_stages - 1 would run loader and MMA in lock-step).
-    const int depth = p.a_stages / 2 > 1 ? p.a_stages / 2 : 1;
-    int inflight = 0, oldest = 0;
+    const bool MW2 = MODE == 0 && p.mma_warps == 2;
+    const int ring_len = MW2 ? p.a_stages / 2 : p.a_stages;
+    // (with half-rings a stage is reused after ring_len issues of its parity, so at most ring_len - 1
+    // groups may stay unpublished or the loader would wait for a stage nobody was told about)
+    const int depth = MW2 ? (ring_len > 1 ? ring_len - 1 : 1) : (p.a_stages / 2 > 1 ? p.a_stages / 2 : 1);
+    int inflight = 0;
+    int rpos[2] = {0, 0};
+    uint32_t rph[2] = {0, 0};
+    int tile_k = 0;
+    uint8_t fifo[8];  // stages in issue order (at most a_stages <= 8 unpublished)
+    int fifo_head = 0, fifo_tail = 0;
     const uint32_t ring_addr = smem_u32(a_ring);
     // Per-thread copy table: which halo pixel / 16-byte chunk this thread fetches in its
     // it-th copy of every stage, and where it lands (identical for every stage and slab).
@@ -841,10 +850,15 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
         }
         continue;
       }
+      // With two MMA warps (alternate tiles) the ring is split in two halves, one per tile parity,
+      // so a stage only ever meets one consumer warp (see the parity-aliasing note in engine.cu).
+      const int par = MW2 ? (tile_k & 1) : 0;
+      ++tile_k;
       for (int s = 0; s < p.nslabs; ++s) {
         const HaloSrc& sv = p.src[p.slab_src[s]];
         const int c0 = p.slab_c0[s];
-        mbar_wait(&ctl->a_empty[as], aph ^ 1);
+        const int as = par * ring_len + rpos[par];
+        mbar_wait(&ctl->a_empty[as], rph[par] ^ 1);
         const uint32_t stage_addr = ring_addr + (uint32_t)as * p.a_stage_bytes;
         const uint16_t* img = sv.ptr + (int64_t)n * sv.Hs * sv.Ws * sv.C + c0;
         const int up = sv.up;
@@ -861,6 +875,8 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
           }
         }
         cp_async_commit();
+        fifo[fifo_tail] = (uint8_t)as;
+        fifo_tail = (fifo_tail + 1) & 7;
         if (++inflight > depth) {
           switch (depth) {  // all but the `depth` most recent groups have landed
             case 1: cp_async_wait<1>(); break;
@@ -869,21 +885,21 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
             default: cp_async_wait<4>(); break;
           }
           fence_proxy_async_smem();
-          mbar_arrive(&ctl->a_full[oldest]);
-          if (++oldest == p.a_stages) oldest = 0;
+          mbar_arrive(&ctl->a_full[fifo[fifo_head]]);
+          fifo_head = (fifo_head + 1) & 7;
           --inflight;
         }
-        if (++as == p.a_stages) {
-          as = 0;
-          aph ^= 1;
+        if (++rpos[par] == ring_len) {
+          rpos[par] = 0;
+          rph[par] ^= 1;
         }
       }
     }
     cp_async_wait<0>();
     fence_proxy_async_smem();
-    while (inflight-- > 0) {
-      mbar_arrive(&ctl->a_full[oldest]);
-      if (++oldest == p.a_stages) oldest = 0;
+    while (fifo_head != fifo_tail) {
+      mbar_arrive(&ctl->a_full[fifo[fifo_head]]);
+      fifo_head = (fifo_head + 1) & 7;
     }
   } else if (warp == HALO2_LOAD_WARPS + 1) {
     // ===================== B producer =====================
@@ -916,9 +932,17 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
         }
       }
     }
-  } else if (warp == HALO2_LOAD_WARPS) {
-    // ===================== MMA issuer =====================
-    int as = 0, bs = 0, acc = 0;
+  } else if (warp == HALO2_LOAD_WARPS || warp == HALO2_MMA2_WARP) {
+    // ===================== MMA issuer(s) =====================
+    // mma_warps == 2 (MODE 0, resident weights): alternate tiles, own half of the A ring and own
+    // accumulator stage per warp -- one warp cannot issue N <= 64 MMAs as fast as they execute.
+    const bool MW2 = MODE == 0 && p.mma_warps == 2;
+    const int mw = warp == HALO2_LOAD_WARPS ? 0 : 1;
+    if (mw == 1 && !MW2) goto mma_done;
+    {
+    const int ring_len = MW2 ? p.a_stages / 2 : p.a_stages;
+    const int ring_base = MW2 ? mw * ring_len : 0;
+    int rpos = 0, bs = 0, acc = MW2 ? mw : 0;
     uint32_t aph = 0, bph = 0, acc_phase = 0;
     const uint32_t idesc = umma_idesc_act(128, p.BN);
     const uint64_t a_desc0 = desc_compact<P>(smem_u32(a_ring), MODE == 0 ? HW * P : 8 * P);
@@ -927,11 +951,12 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
     const uint32_t b_step = (uint32_t)p.b_bytes >> 4;
     constexpr uint32_t PX = P / 16;  // one pixel, in descriptor address units
     if (resident) mbar_wait(&ctl->w_full, 0);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x + (MW2 ? mw * (int)gridDim.x : 0); t < total_tiles; t += (MW2 ? 2 : 1) * gridDim.x) {
       mbar_wait(&ctl->acc_empty[acc], acc_phase ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
       for (int s = 0; s < p.nslabs; ++s) {
+        const int as = ring_base + rpos;
         mbar_wait(&ctl->a_full[as], aph);
         tc_fence_after_sync();
         const uint64_t a_stage_desc = desc_add(a_desc0, as * a_step);
@@ -984,16 +1009,20 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
             }
           }
         }
-        if (++as == p.a_stages) {
-          as = 0;
+        if (++rpos == ring_len) {
+          rpos = 0;
           aph ^= 1;
         }
       }
-      if (++acc == 2) {
+      if (MW2) {
+        acc_phase ^= 1;  // own accumulator stage, every tile
+      } else if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    }
+  mma_done:;
   } else {
     // ===================== epilogue =====================
     int acc = 0;

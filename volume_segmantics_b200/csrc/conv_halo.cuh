@@ -135,10 +135,12 @@ struct ConvHalo2Params {
   // max-reduces the part of every pooling window that lies inside the tile into the
   // zero-initialised pooled tensor [NB, H/2, W/2, cout] with 16-byte red.max (values >= 0).
   uint16_t* pool_out;
+  int32_t mma_warps;  // 2: two MMA issuing warps on alternate tiles (MODE 0, resident weights, even a_stages >= 4)
   FastDiv div_n_tiles, div_tx, div_ty;  // set by the launcher
 };
 constexpr int HALO2_LOAD_WARPS = 4;
-constexpr int HALO2_THREADS = 32 * (HALO2_LOAD_WARPS + 2 + 8);
+constexpr int HALO2_MMA2_WARP = HALO2_LOAD_WARPS + 2 + 8;  // second MMA issuer (mma_warps == 2)
+constexpr int HALO2_THREADS = 32 * (HALO2_LOAD_WARPS + 2 + 8 + 1);
 
 size_t conv_halo2_smem_bytes(const ConvHalo2Params& p);
 cudaError_t launch_conv_halo2(const ConvHalo2Params& p, int num_sms, cudaStream_t st);

@@ -155,6 +155,7 @@ struct vsb_engine {
   int halo_a_stages_max = 8;     // vsb_set_flag("halo_a_stages", n)
   bool sync_each = false;        // vsb_set_flag("sync_each", 1): synchronise after every op and name the one that failed
   bool no_fuse_pool = false;     // vsb_set_flag("fuse_pool", 0): separate max-pool kernel after the stem
+  bool halo2_mma2 = false;       // vsb_set_flag("halo2_mma2", 1): two MMA warps in the cp.async halo kernel as well
   bool no_mma2 = false;          // vsb_set_flag("mma_warps", 1): a single MMA issuing warp everywhere
   bool no_epi_groups = false;    // vsb_set_flag("epi_groups", 0): one epilogue group even for BN <= 64
   unsigned long long* d_halo_prof = nullptr;  // vsb_set_flag("halo_prof", 1): per-launch cycle accounting to stderr
@@ -938,6 +939,13 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
         h.a_stages = 3;
         h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, (budget - 3 * (size_t)h.a_stage_bytes) / h.b_bytes);
       }
+      h.mma_warps = 1;
+      // measured neutral (these layers are bound by the cp.async halo assembly, not by MMA issue):
+      // off unless vsb_set_flag("halo2_mma2", 1)
+      if (e->halo2_mma2 && h.b_stages == 0 && h.a_stages >= 4 && !e->no_mma2) {
+        h.mma_warps = 2;
+        h.a_stages &= ~1;  // two half-rings, one per MMA warp
+      }
       if (eff >= 0.6 && (h.b_stages == 0 || h.b_stages >= 2)) {
         for (int s = 0; s < op.n_src; ++s) {
           const TensorBuf& st = e->tens[op.src[s]];
@@ -1682,6 +1690,7 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
   }
   else if (n == "sync_each") e->sync_each = value != 0;
   else if (n == "fuse_pool") { e->no_fuse_pool = value == 0; free_workspace(e); }
+  else if (n == "halo2_mma2") { e->halo2_mma2 = value != 0; free_workspace(e); }
   else if (n == "mma_warps") { e->no_mma2 = value < 2; free_workspace(e); }
   else if (n == "epi_groups") { e->no_epi_groups = value == 0; free_workspace(e); }
   else if (n == "tma_epilogue") { e->no_tma_epilogue = value == 0; free_workspace(e); }
