@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== slicer tests"; timeout 600 python -m pytest tests/test_slicer_gpu.py tests/test_ragged_gpu.py tests/test_predictor_gpu.py -m gpu -q -x 2>&1 | tail -3
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:slicer_rows -s 2 -c 2 -f -o gpurun_out/r01_slicer_rows python tests/slicer_bench.py > gpurun_out/ncu_slicer.log 2>&1; tail -1 gpurun_out/ncu_slicer.log
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:slicer_xplane -s 1 -c 2 -f -o gpurun_out/r01_slicer_xplane python tests/slicer_bench.py > gpurun_out/ncu_slicer2.log 2>&1; tail -1 gpurun_out/ncu_slicer2.log

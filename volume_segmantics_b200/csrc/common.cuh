@@ -42,6 +42,16 @@ __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 #endif
 }
+// Same without the +-65504 clamp, for values known to be small (one F2FP instruction).
+__device__ __forceinline__ uint32_t pack_act2_small(float lo, float hi) {
+  uint32_t r;
+#if VSB_ACT_F16
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+#else
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+#endif
+  return r;
+}
 __device__ __forceinline__ float2 unpack_act2(uint32_t v) {
 #if VSB_ACT_F16
   return __half22float2(*reinterpret_cast<__half2*>(&v));

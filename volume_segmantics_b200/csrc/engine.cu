@@ -1284,9 +1284,12 @@ int run_network(vsb_engine* e, int nb, int* head_idx) {
   return VSB_OK;
 }
 
-int auto_batch(const vsb_engine* e, int64_t Hp, int64_t Wp, int64_t S) {
+int auto_batch(const vsb_engine* e, int64_t Hp, int64_t Wp, int64_t S, bool xplane) {
   if (e->batch_override > 0) return (int)std::min<int64_t>(e->batch_override, S);
-  const int64_t target_px = 32ll << 20;  // measured: 32 slices of 1024^2 per launch beat 16 by 6 %
+  // measured: 32 slices of 1024^2 per launch beat 16 by 6 %, larger batches are neutral for the
+  // network.  x-plane directions (slice index along x) take 128 slices: the slicer then reads 128
+  // contiguous bytes per (row, column) and the head merges 1 KB runs of keys instead of 256 B.
+  const int64_t target_px = xplane ? (128ll << 20) : (32ll << 20);
   int64_t nb = std::max<int64_t>(1, target_px / (Hp * Wp));
   nb = std::min<int64_t>(nb, 256);
   if (nb >= 32) nb = nb / 32 * 32;
@@ -1303,7 +1306,7 @@ int predict_range(vsb_engine* e, int d, int64_t s_begin, int64_t s_end) {
   if (s_begin < 0 || s_end > g.S || s_begin > s_end) return fail(VSB_ERR_INVALID, "bad slice range");
   if (s_begin == s_end) return VSB_OK;
   if (e->vote_mode && !e->d_votes) return fail(VSB_ERR_STATE, "vote buffer missing");
-  const int nbmax = auto_batch(e, g.Hp, g.Wp, s_end - s_begin);
+  const int nbmax = auto_batch(e, g.Hp, g.Wp, s_end - s_begin, g.stride_s == 1);
   e->keep_all = false;
   rc = build_workspace(e, (int)g.Hp, (int)g.Wp, nbmax);
   if (rc) return rc;
@@ -1416,6 +1419,15 @@ int vsb_create(int device, vsb_engine** out) {
   e->encode = (EncodeTiledFn)fn;
   CK(vsb::conv_tc_configure());
   CK(vsb::conv_halo_configure());
+  {
+    // the slicer normalises with one FMA per pixel; it must reproduce the reference formula for all 256 inputs
+    const int bad = vsb::slicer_norm_selfcheck(e->stream);
+    if (bad != 0) {
+      cudaStreamDestroy(e->own_stream);
+      delete e;
+      return fail(VSB_ERR_UNSUPPORTED, "slicer normalisation self-check failed (%d of 256 byte values differ)", bad);
+    }
+  }
   e->no_halo = getenv("VSB_NO_HALO") != nullptr;
   if (getenv("VSB_FUSE_HEAD")) e->no_fuse_head = false;
   if (const char* sb = getenv("VSB_SUB_BATCH_MB")) e->sub_batch_mb = atoi(sb);

@@ -50,6 +50,9 @@ struct HeadArgs {
   int64_t nvox;
 };
 
+// Number of byte values (0..255) whose fused-multiply-add normalisation differs from the reference
+// formula in this build's 16-bit format (must be 0), or -1 on a CUDA error.
+int slicer_norm_selfcheck(cudaStream_t st);
 void launch_slicer(const uint8_t* vol, const vsb_direction& g, int64_t s0, int nb, uint16_t* out,
                    cudaStream_t st);
 void launch_stem7x7(const uint16_t* in, int NB, int Hin, int Win, const void* w_bf16,

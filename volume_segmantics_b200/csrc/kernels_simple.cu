@@ -34,29 +34,51 @@ __device__ __forceinline__ uint16_t normalise_u8(int v) {
 // ---------------------------------------------------------------------------
 // Slicer.  Replaces datasets.py:122 (vol[i] on the rotate_array_to_axis / np.rot90 view),
 // :125-127 (PadIfNeeded) and :129-135 (normalise).  HBM-bound: 1 B read + 2 B written per
-// padded pixel.  The 256-entry normalisation table is replicated 32 times in shared memory
-// (entry [v][lane]) so the per-pixel lookups of a warp never collide on a bank.
+// padded pixel.
+// The normalisation (v/255 - 0.449)/0.226, evaluated by numpy in fp32 with two divisions, is
+// reproduced per pixel by ONE fused multiply-add: fma(v, A, B) with A = 1/(255*0.226),
+// B = -0.449/0.226 differs from the reference by up to 65 fp32 ulps, but rounds to the same
+// 16-bit value for every one of the 256 inputs -- checked exhaustively against
+// normalise_u8() for this build's 16-bit format when an engine is created
+// (vsb_slicer_norm_selfcheck) and by the bit-exact slicer tests.  A shared-memory lookup
+// table (the previous version) was limited by the LSU instruction queue (ncu: mio_throttle).
 // ---------------------------------------------------------------------------
-struct SlicerLut {
-  uint16_t t[256][32];
-};
-__device__ __forceinline__ void slicer_lut_fill(SlicerLut& lut) {
-  // 256 threads: thread v computes entry v and writes its 32 copies
-  const uint32_t val = normalise_u8(threadIdx.x);
-  uint4 q;
-  q.x = q.y = q.z = q.w = val | (val << 16);
-  uint4* dst = reinterpret_cast<uint4*>(&lut.t[threadIdx.x][0]);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) dst[i] = q;
+#define VSB_NORM_A __uint_as_float(0x3c8e25f0u) /* float(1 / (255 * 0.226)) = 0.017352074 */
+#define VSB_NORM_B __uint_as_float(0xbffe4d07u) /* float(-0.449 / 0.226)    = -1.9867257  */
+__device__ __forceinline__ float byte_to_float(uint32_t word, int j) {
+  // 0x4B0000vv is the float 8388608 + v: one byte-permute and one exact subtraction
+  return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440 + j)) - 8388608.0f;
 }
 // 8 source bytes (two little-endian words) -> 8 normalised 16-bit pixels
-__device__ __forceinline__ uint4 slicer_lookup8(const SlicerLut& lut, uint32_t lo, uint32_t hi, int lane) {
-  uint4 o;
-  o.x = lut.t[lo & 0xff][lane] | ((uint32_t)lut.t[(lo >> 8) & 0xff][lane] << 16);
-  o.y = lut.t[(lo >> 16) & 0xff][lane] | ((uint32_t)lut.t[lo >> 24][lane] << 16);
-  o.z = lut.t[hi & 0xff][lane] | ((uint32_t)lut.t[(hi >> 8) & 0xff][lane] << 16);
-  o.w = lut.t[(hi >> 16) & 0xff][lane] | ((uint32_t)lut.t[hi >> 24][lane] << 16);
+__device__ __forceinline__ uint4 slicer_norm8(uint32_t lo, uint32_t hi) {
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[j] = fmaf(byte_to_float(lo, j), VSB_NORM_A, VSB_NORM_B);
+    f[4 + j] = fmaf(byte_to_float(hi, j), VSB_NORM_A, VSB_NORM_B);
+  }
+  uint4 o;  // normalised values lie in [-2, 2.5]: no saturation needed
+  o.x = pack_act2_small(f[0], f[1]);
+  o.y = pack_act2_small(f[2], f[3]);
+  o.z = pack_act2_small(f[4], f[5]);
+  o.w = pack_act2_small(f[6], f[7]);
   return o;
+}
+__global__ void slicer_norm_check_kernel(int* mismatches) {
+  const uint32_t v = threadIdx.x;  // 256 threads
+  const uint4 o = slicer_norm8(v, 0u);
+  if ((uint16_t)(o.x & 0xffffu) != normalise_u8((int)v)) atomicAdd(mismatches, 1);
+}
+int slicer_norm_selfcheck(cudaStream_t st) {
+  int* d = nullptr;
+  int h = -1;
+  if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return -1;
+  cudaMemsetAsync(d, 0, sizeof(int), st);
+  slicer_norm_check_kernel<<<1, 256, 0, st>>>(d);
+  cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  cudaFree(d);
+  return h;
 }
 
 // Case A: image columns are contiguous voxels (or any stride when the batch is small).
@@ -65,9 +87,7 @@ __device__ __forceinline__ uint4 slicer_lookup8(const SlicerLut& lut, uint32_t l
 __global__ void __launch_bounds__(256) slicer_rows_kernel(const uint8_t* __restrict__ vol,
                                                           vsb_direction g, int64_t s0, int nb,
                                                           uint16_t* __restrict__ out) {
-  __shared__ __align__(16) SlicerLut lut;
-  slicer_lut_fill(lut);
-  __syncthreads();
+  // (a variant with 32-bit row / column arithmetic measured slower under ncu: 25.2 vs 20.3 us)
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)nb * g.Hp;
   const int chunks = (int)(g.Wp >> 4);
@@ -96,66 +116,84 @@ __global__ void __launch_bounds__(256) slicer_rows_kernel(const uint8_t* __restr
         }
       }
       uint4* o = reinterpret_cast<uint4*>(orow + ch * 16);
-      o[0] = slicer_lookup8(lut, w[0], w[1], lane);
-      o[1] = slicer_lookup8(lut, w[2], w[3], lane);
+      o[0] = slicer_norm8(w[0], w[1]);
+      o[1] = slicer_norm8(w[2], w[3]);
     }
   }
 }
 
 // Case B: the slice index runs along x (unit stride; directions 2,5,8,11).  A tile of
-// 128 image columns x 32 slices is read with the slice index fastest (4 slices per 32-bit
-// load, 32 contiguous bytes per column), transposed through shared memory and written
-// with the column index fastest (16 bytes per lane, 256 contiguous bytes per slice row).
-constexpr int XP_COLS = 128;
-constexpr int XP_PITCH = XP_COLS + 4;  // bytes per slice row of the tile: conflict-free both ways
+// 64 image columns x 128 slices is read with the slice index fastest (16-byte loads, 128
+// contiguous bytes per column -- x-plane batches are 128 slices for exactly this reason),
+// kept in shared memory as 32-bit words of four consecutive slices of one column, and written
+// with the column index fastest: a thread reads the words of 8 columns x 4 slices and emits
+// four 16-byte rows (8 pixels each), 128 contiguous bytes per slice row across 8 lanes.
+// Word pitch 33: both the stores (4 columns x 8 lanes) and the loads (8 column groups x 4
+// slice quads) of a warp touch 32 different banks.
+constexpr int XP_COLS = 64, XP_SLICES = 128, XP_WPITCH = XP_SLICES / 4 + 1;
 __global__ void __launch_bounds__(256) slicer_xplane_kernel(const uint8_t* __restrict__ vol,
                                                             vsb_direction g, int64_t s0, int nb,
                                                             uint16_t* __restrict__ out) {
-  __shared__ __align__(16) SlicerLut lut;
-  __shared__ __align__(16) uint8_t tile[32 * XP_PITCH];
-  slicer_lut_fill(lut);
-  const int lane = threadIdx.x & 31;
+  __shared__ uint32_t tile[XP_COLS * XP_WPITCH];
   const int64_t ctiles = (g.Wp + XP_COLS - 1) / XP_COLS;
-  const int64_t stiles = (nb + 31) >> 5;
+  const int64_t stiles = (nb + XP_SLICES - 1) / XP_SLICES;
   const int64_t total = g.Hp * ctiles * stiles;
-  const bool fast = ((s0 | g.base | g.stride_r | g.stride_c) & 3) == 0 && ((uintptr_t)vol & 3) == 0;
+  const bool fast = ((s0 | g.base | g.stride_r | g.stride_c) & 15) == 0 && ((uintptr_t)vol & 15) == 0;
+  const int64_t slice_elems = g.Hp * g.Wp;
   for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
     const int64_t ct = t % ctiles;
     const int64_t pr = (t / ctiles) % g.Hp;
     const int64_t stile = t / (ctiles * g.Hp);
     const int64_t r = reflect101(pr - g.pad_top, g.H);
-    const uint8_t* rowp = vol + g.base + (s0 + stile * 32) * g.stride_s + r * g.stride_r;
-    const int sl_left = (int)(nb - stile * 32 < 32 ? nb - stile * 32 : 32);
+    const uint8_t* rowp = vol + g.base + (s0 + stile * XP_SLICES) * g.stride_s + r * g.stride_r;
+    const int sl_left = (int)(nb - stile * XP_SLICES < XP_SLICES ? nb - stile * XP_SLICES : XP_SLICES);
     __syncthreads();
-    // load: 8 lanes cover the 32 slices of one column, a warp covers 4 columns
+    // load: 8 lanes cover the 128 slices of one column (16 bytes each), a warp covers 4 columns
 #pragma unroll
     for (int it = 0; it < XP_COLS / 32; ++it) {
       const int cc = it * 32 + (threadIdx.x >> 3), sg = threadIdx.x & 7;
       const int64_t pc = ct * XP_COLS + cc;
-      uint32_t v = 0;
+      uint32_t v[4] = {0u, 0u, 0u, 0u};
       if (pc < g.Wp) {
         const int64_t c = reflect101(pc - g.pad_left, g.W);
-        const uint8_t* p = rowp + c * g.stride_c + 4 * sg;
-        if (fast && 4 * sg + 3 < sl_left) {
-          v = __ldg(reinterpret_cast<const uint32_t*>(p));
+        const uint8_t* p = rowp + c * g.stride_c + 16 * sg;
+        if (fast && 16 * sg + 15 < sl_left) {
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
         } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (4 * sg + j < sl_left) v |= (uint32_t)__ldg(p + j) << (8 * j);
+          for (int j = 0; j < 16; ++j)
+            if (16 * sg + j < sl_left) v[j >> 2] |= (uint32_t)__ldg(p + j) << (8 * (j & 3));
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) tile[(4 * sg + j) * XP_PITCH + cc] = (uint8_t)(v >> (8 * j));
+      for (int q = 0; q < 4; ++q) tile[cc * XP_WPITCH + 4 * sg + q] = v[q];
     }
     __syncthreads();
-    // store: 16 lanes cover the 128 columns of one slice row, a warp covers 2 slices
+    // store: thread = (slice quad sq, column group k): 8 columns x 4 slices -> four 16-byte rows
+    {
+      const int sq = threadIdx.x >> 3, k = threadIdx.x & 7;
+      const int64_t pc = ct * XP_COLS + 8 * k;
+      const int sl0 = 4 * sq;  // first slice of the quad, tile-local
+      if (pc < g.Wp && sl0 < sl_left) {  // Wp is a multiple of 32, so a chunk of 8 columns is all in or all out
+        uint32_t w[8];
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int ss = it * 16 + (threadIdx.x >> 4), k = threadIdx.x & 15;
-      const int64_t s = stile * 32 + ss, pc = ct * XP_COLS + 8 * k;
-      if (s < nb && pc < g.Wp) {  // Wp is a multiple of 32, so a chunk of 8 is all in or all out
-        const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile + ss * XP_PITCH + 8 * k);
-        *reinterpret_cast<uint4*>(out + ((s * g.Hp + pr) * g.Wp + pc)) = slicer_lookup8(lut, tw[0], tw[1], lane);
+        for (int i = 0; i < 8; ++i) w[i] = tile[(8 * k + i) * XP_WPITCH + sq];
+        uint16_t* o0 = out + (((stile * XP_SLICES + sl0) * g.Hp + pr) * g.Wp + pc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (sl0 + j < sl_left) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaf(byte_to_float(w[i], j), VSB_NORM_A, VSB_NORM_B);
+            uint4 o;
+            o.x = pack_act2_small(f[0], f[1]);
+            o.y = pack_act2_small(f[2], f[3]);
+            o.z = pack_act2_small(f[4], f[5]);
+            o.w = pack_act2_small(f[6], f[7]);
+            *reinterpret_cast<uint4*>(o0 + j * slice_elems) = o;
+          }
+        }
       }
     }
   }
@@ -164,7 +202,7 @@ __global__ void __launch_bounds__(256) slicer_xplane_kernel(const uint8_t* __res
 void launch_slicer(const uint8_t* vol, const vsb_direction& g, int64_t s0, int nb, uint16_t* out,
                    cudaStream_t st) {
   if (g.stride_s == 1 && nb >= 8) {
-    const int64_t total = g.Hp * ((g.Wp + XP_COLS - 1) / XP_COLS) * ((nb + 31) / 32);
+    const int64_t total = g.Hp * ((g.Wp + XP_COLS - 1) / XP_COLS) * ((nb + XP_SLICES - 1) / XP_SLICES);
     const int grid = (int)(total < 148 * 8 ? total : 148 * 8);
     slicer_xplane_kernel<<<grid, 256, 0, st>>>(vol, g, s0, nb, out);
   } else {
