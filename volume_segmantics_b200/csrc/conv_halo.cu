@@ -772,8 +772,22 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
     int rpos[2] = {0, 0};
     uint32_t rph[2] = {0, 0};
     int tile_k = 0;
-    uint8_t fifo[8];  // stages in issue order (at most a_stages <= 8 unpublished)
+    uint8_t fifo[8];  // stages in issue order (at most a_stages <= 8 unpublished); 0xFF = fetched by TMA, nothing to publish
     int fifo_head = 0, fifo_tail = 0;
+    auto publish_oldest = [&]() {
+      switch (depth) {  // all but the `depth` most recent groups have landed
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        default: cp_async_wait<4>(); break;
+      }
+      if (fifo[fifo_head] != 0xFF) {
+        fence_proxy_async_smem();
+        mbar_arrive(&ctl->a_full[fifo[fifo_head]]);
+      }
+      fifo_head = (fifo_head + 1) & 7;
+      --inflight;
+    };
     const uint32_t ring_addr = smem_u32(a_ring);
     // Per-thread copy table: which halo pixel / 16-byte chunk this thread fetches in its
     // it-th copy of every stage, and where it lands (identical for every stage and slab).
@@ -860,6 +874,29 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
         const int as = par * ring_len + rpos[par];
         mbar_wait(&ctl->a_empty[as], rph[par] ^ 1);
         const uint32_t stage_addr = ring_addr + (uint32_t)as * p.a_stage_bytes;
+        if (p.src_map[p.slab_src[s]]) {
+          // whole halo of this slab by one TMA box (zero fill outside the image): thread 0 arrives
+          // with the byte count, the other loader threads arrive at once; the stage is complete
+          // when the bytes have landed -- it takes no part in the cp.async publishing queue
+          if (ptid == 0) {
+            mbar_arrive_expect_tx(&ctl->a_full[as], (uint32_t)(HW * HH * P));
+            tma_load_5d(p.src_map[p.slab_src[s]], &ctl->a_full[as], a_ring + (size_t)as * p.a_stage_bytes, c0, X0 - 1, 0,
+                        Y0 - 1, n);
+          } else {
+            mbar_arrive(&ctl->a_full[as]);
+          }
+          // keep the publishing queue in step with the ring: an (empty) group and a placeholder entry,
+          // so an older cp.async stage is still published after `depth` further ring stages
+          cp_async_commit();
+          fifo[fifo_tail] = 0xFF;
+          fifo_tail = (fifo_tail + 1) & 7;
+          if (++inflight > depth) publish_oldest();
+          if (++rpos[par] == ring_len) {
+            rpos[par] = 0;
+            rph[par] ^= 1;
+          }
+          continue;
+        }
         const uint16_t* img = sv.ptr + (int64_t)n * sv.Hs * sv.Ws * sv.C + c0;
         const int up = sv.up;
         const uint32_t row_elems = (uint32_t)sv.Ws * sv.C, px_elems = (uint32_t)sv.C;
@@ -877,18 +914,7 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
         cp_async_commit();
         fifo[fifo_tail] = (uint8_t)as;
         fifo_tail = (fifo_tail + 1) & 7;
-        if (++inflight > depth) {
-          switch (depth) {  // all but the `depth` most recent groups have landed
-            case 1: cp_async_wait<1>(); break;
-            case 2: cp_async_wait<2>(); break;
-            case 3: cp_async_wait<3>(); break;
-            default: cp_async_wait<4>(); break;
-          }
-          fence_proxy_async_smem();
-          mbar_arrive(&ctl->a_full[fifo[fifo_head]]);
-          fifo_head = (fifo_head + 1) & 7;
-          --inflight;
-        }
+        if (++inflight > depth) publish_oldest();
         if (++rpos[par] == ring_len) {
           rpos[par] = 0;
           rph[par] ^= 1;
@@ -898,7 +924,7 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
     cp_async_wait<0>();
     fence_proxy_async_smem();
     while (fifo_head != fifo_tail) {
-      mbar_arrive(&ctl->a_full[fifo[fifo_head]]);
+      if (fifo[fifo_head] != 0xFF) mbar_arrive(&ctl->a_full[fifo[fifo_head]]);
       fifo_head = (fifo_head + 1) & 7;
     }
   } else if (warp == HALO2_LOAD_WARPS + 1) {

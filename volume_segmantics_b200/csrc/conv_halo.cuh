@@ -112,6 +112,7 @@ struct HeadFuse {
 constexpr int HALO2_MAX_SLABS = 64;
 struct ConvHalo2Params {
   HaloSrc src[6];
+  const TmaDesc* src_map[6];  // non-null: the source's slabs are fetched by TMA (box {kc, 8*MT+2, 1, 18, 1}); never for up-sampled sources
   int32_t n_src, nslabs;
   int32_t stem;  // 1: 7x7 stride-2 single-channel stem (im2col rows built by the loaders)
   int32_t kc;    // channels per slab (16 / 32 / 64), uniform

@@ -155,6 +155,7 @@ struct vsb_engine {
   int halo_a_stages_max = 8;     // vsb_set_flag("halo_a_stages", n)
   bool sync_each = false;        // vsb_set_flag("sync_each", 1): synchronise after every op and name the one that failed
   bool no_fuse_pool = false;     // vsb_set_flag("fuse_pool", 0): separate max-pool kernel after the stem
+  bool no_halo2_tma = false;     // vsb_set_flag("halo2_tma", 0): cp.async loaders for every halo2 source
   bool halo2_mma2 = false;       // vsb_set_flag("halo2_mma2", 1): two MMA warps in the cp.async halo kernel as well
   bool no_mma2 = false;          // vsb_set_flag("mma_warps", 1): a single MMA issuing warp everywhere
   bool no_epi_groups = false;    // vsb_set_flag("epi_groups", 0): one epilogue group even for BN <= 64
@@ -320,7 +321,7 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
     if (op.b_off >= 0) memcpy(bias.data(), e->h_weights.data() + op.b_off, (size_t)op.cout * 4);
     CK(cudaMalloc(&cp.d_bias_pad, op.cout * 4));
     CK(cudaMemcpy(cp.d_bias_pad, bias.data(), op.cout * 4, cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * VSB_MAX_SRC));
+    CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * 2 * VSB_MAX_SRC));  // [0,6): per-tap / halo / epilogue maps, [6,12): halo2 source maps
     cp.grouped_halo = true;
     return VSB_OK;
   }
@@ -374,7 +375,7 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
     if (op.b_off >= 0) memcpy(bias.data(), e->h_weights.data() + op.b_off, (size_t)op.cout * 4);
     CK(cudaMalloc(&cp.d_bias_pad, op.cout * 4));
     CK(cudaMemcpy(cp.d_bias_pad, bias.data(), op.cout * 4, cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * VSB_MAX_SRC));
+    CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * 2 * VSB_MAX_SRC));  // [0,6): per-tap / halo / epilogue maps, [6,12): halo2 source maps
     cp.grouped_s2 = true;
     cp.tc = true;  // shares the workspace-time tile / tensor-map set-up of the per-tap kernel
     return VSB_OK;
@@ -573,7 +574,7 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
   if (op.b_off >= 0) memcpy(bias.data(), e->h_weights.data() + op.b_off, (size_t)op.cout * 4);
   CK(cudaMalloc(&cp.d_bias_pad, n_total * 4));
   CK(cudaMemcpy(cp.d_bias_pad, bias.data(), n_total * 4, cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * VSB_MAX_SRC));
+  CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * 2 * VSB_MAX_SRC));  // [0,6): per-tap / halo / epilogue maps, [6,12): halo2 source maps
   return VSB_OK;
 }
 
@@ -954,6 +955,16 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
           h.src[s].Hs = st.H;
           h.src[s].Ws = st.W;
           h.src[s].up = op.src_up[s];
+          // sources read at their own resolution arrive by ONE TMA box per slab (same swizzled
+          // compact-pitch layout the cp.async loaders write); up-sampled ones keep the loaders
+          h.src_map[s] = nullptr;
+          if (!op.src_up[s] && !e->no_halo2_tma) {
+            TmaDesc m;
+            int rc = make_tensor_map(e, &m, st, nb, false, h.kc, 8 * mt + 2, 18, 1);
+            if (rc) return rc;
+            CK(cudaMemcpy(cp.d_maps + VSB_MAX_SRC + s, &m, sizeof(m), cudaMemcpyHostToDevice));
+            h.src_map[s] = cp.d_maps + VSB_MAX_SRC + s;
+          }
         }
         h.wpacked = cp.d_whalo;
         h.bias = cp.d_bias_pad;
@@ -1702,6 +1713,7 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
   }
   else if (n == "sync_each") e->sync_each = value != 0;
   else if (n == "fuse_pool") { e->no_fuse_pool = value == 0; free_workspace(e); }
+  else if (n == "halo2_tma") { e->no_halo2_tma = value == 0; free_workspace(e); }
   else if (n == "halo2_mma2") { e->halo2_mma2 = value != 0; free_workspace(e); }
   else if (n == "mma_warps") { e->no_mma2 = value < 2; free_workspace(e); }
   else if (n == "epi_groups") { e->no_epi_groups = value == 0; free_workspace(e); }
