@@ -1,12 +1,19 @@
 #!/bin/bash
-# One GPU round trip: base kernels, tcgen05 probes, whole network, end to end.
+# Full validation on a B200 box (run as: gpurun --timeout 2400 -- 'bash tests/gpu_round.sh').
+# Writes the artefacts that get copied into profiles/.
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/smi.log 2>&1
-echo "== base tests" ; timeout 900 python -m pytest tests/test_slicer_gpu.py tests/test_merge_gpu.py -m gpu -q -x 2>&1 | tail -15 | tee gpurun_out/t_base.log
-: > gpurun_out/probes.log
-for grp in 0,1,2 3,4,5,6 7,8,9 10,11,12,13 14,15,16,17,18,19,20; do
-  timeout 240 python tests/bringup_gpu.py --probe $grp >> gpurun_out/probes.log 2>&1 || echo "group $grp exit $?" >> gpurun_out/probes.log
-done
-echo "== probes"; grep -E "probe|exit|Error|error" gpurun_out/probes.log | tail -60
-echo "== net"; timeout 900 python tests/bringup_gpu.py > gpurun_out/net.log 2>&1; tail -12 gpurun_out/net.log
-echo "== net tests"; timeout 1200 python -m pytest tests/test_network_gpu.py tests/test_predictor_gpu.py -m gpu -q 2>&1 | tail -30 | tee gpurun_out/t_net.log
+echo "== gpu tests"; timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 | tee gpurun_out/gpu_tests.log
+echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+echo "== slicer/head bandwidth"; timeout 300 python tests/slicer_bench.py 2>&1 | tail -5 | tee gpurun_out/slicer_head_bw.txt
+echo "== per-layer table"; timeout 600 python tests/layer_profile.py 1024 64 > gpurun_out/layers.txt 2>&1; tail -2 gpurun_out/layers.txt
+echo "== other architectures"; timeout 900 python tests/arch_timing.py 2>&1 | tail -4 | tee gpurun_out/arch_timing.txt
+echo "== bench"; timeout 1200 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}, d['e2e']['value'], d['roofline']['frac'], d['roofline']['other_stage_ms_per_step'])
+PY
+# ncu (only after the plain runs above exited 0):
+#   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
+#       --log-file gpurun_out/ncu_batch32_dram.csv python tests/layer_profile.py 1024 32
+#   ncu --set full --import-source on --clock-control none -k regex:conv_halo_kernel -s 13 -c 1 -f -o gpurun_out/conv_halo_layer3 \
+#       python tests/layer_profile.py 1024 16 16
