@@ -1082,6 +1082,7 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
         tmem_ld_wait();
         tc_fence_before_sync();
         mbar_arrive(&ctl->acc_empty[grp]);
+        if (p.out_map && et == 0) tma_store_wait_read<0>();  // ... and so has the TMA store issued from it
         named_bar_sync(1 + 2 * grp, 128);  // the group has finished reading the previous tile's staging
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2)
@@ -1096,9 +1097,17 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
             pk.w = pack2<true>(__uint_as_float(v[h2][q * 8 + 6]) + b1.z, __uint_as_float(v[h2][q * 8 + 7]) + b1.w);
             sts128(stage + (uint32_t)row * 128u + ((uint32_t)((h2 * 4 + q) ^ (row & 7)) << 4), pk);
           }
+        if (p.out_map) fence_proxy_async_smem();
         named_bar_sync(2 + 2 * grp, 128);
-        // (a) the stem output itself: 16 rows x 1 KB, lanes along the bytes of a row
+        // (a) the stem output itself: one TMA store of the staged tile, or 16 rows x 1 KB with lanes
+        // along the bytes of a row
         uint16_t* obase = reinterpret_cast<uint16_t*>(p.out) + (((int64_t)n * p.H + Y0) * p.W + X0) * 64;
+        if (p.out_map) {
+          if (et == 0) {
+            tma_store_5d(p.out_map, pool_stage + grp * 16384, 0, X0, 0, Y0, n);
+            tma_store_commit();
+          }
+        } else
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int idx = et + 128 * k;
@@ -1132,6 +1141,7 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
           red_max_act8(p.pool_out + (((int64_t)n * Hq + PY) * Wq + PX) * 64 + ch * 8, m);
         }
       }
+      if (p.out_map && et == 0) tma_store_wait_all<0>();
     } else
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n_tile, X0, Y0, n;

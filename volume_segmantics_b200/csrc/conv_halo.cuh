@@ -136,6 +136,7 @@ struct ConvHalo2Params {
   // max-reduces the part of every pooling window that lies inside the tile into the
   // zero-initialised pooled tensor [NB, H/2, W/2, cout] with 16-byte red.max (values >= 0).
   uint16_t* pool_out;
+  const TmaDesc* out_map;  // stem + pool: the staged output tile is written by TMA (box {64, 8, 1, 16, 1}); null: coalesced stores
   int32_t mma_warps;  // 2: two MMA issuing warps on alternate tiles (MODE 0, resident weights, even a_stages >= 4)
   FastDiv div_n_tiles, div_tx, div_ty;  // set by the launcher
 };

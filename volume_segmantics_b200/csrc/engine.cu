@@ -816,6 +816,14 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
           cp.pool_op = i + 1;
           h.pool_out = (uint16_t*)e->tens[nx.out].ptr;
           e->conv[i + 1].fused_away = true;
+          if (!e->no_tma_epilogue) {
+            if (!cp.d_maps) CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * 2 * VSB_MAX_SRC));
+            TmaDesc m;
+            int rc = make_tensor_map(e, &m, ot, nb, false, 64, 8, 16, 1);
+            if (rc) return rc;
+            CK(cudaMemcpy(cp.d_maps, &m, sizeof(m), cudaMemcpyHostToDevice));
+            h.out_map = cp.d_maps;
+          }
         }
       }
       continue;
