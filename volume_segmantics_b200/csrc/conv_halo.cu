@@ -111,7 +111,7 @@ __device__ __forceinline__ void halo_decode(const ConvHaloParams& p, int t, int&
   q = fdiv(sp, p.div_ty);
   const int ty = (int)(sp - q * p.div_ty.d);
   n = (int)q + p.n_base;
-  X0 = tx * 8;
+  X0 = tx * (p.mt == 2 ? 16 : 8);
   Y0 = ty * 16;
 }
 
@@ -194,7 +194,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.n_tiles * p.tiles_x * p.tiles_y * p.NB;
-  const int HW = 8 + 2 * p.dil, HH = 16 + 2 * p.dil;
+  const int MT = p.mt == 2 ? 2 : 1;  // 8 x 16 tiles per stage (2 only with streamed weights + direct epilogue)
+  const int HW = 8 * MT + 2 * p.dil, HH = 16 + 2 * p.dil;
   const bool resident = p.b_stages == 0;
   const uint32_t acc_cols = 512u / (uint32_t)p.acc_stages;
   const int G = p.epi_groups == 2 ? 2 : 1;     // epilogue groups (alternate tiles)
@@ -407,10 +408,22 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               if (elect_one()) {
                 const uint64_t at = desc_add(a_stage_desc, (tap / 3) * row_units + (tap % 3) * col_units);
                 const uint64_t bt = desc_add(b_desc0, bs * b_step);
+                if (MT == 2) {
+                  // second tile of the stage: 8 pixels to the right, next accumulator column range
+                  const uint32_t d2 = d_tmem + (uint32_t)p.BN;
+                  const uint64_t at2 = desc_add(at, 8 * (P / 16));
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k)
-                  umma_bf16_ss(d_tmem, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc,
-                               (tap | k) != 0 ? 1u : (cs != 0 ? 1u : 0u));
+                  for (int k = 0; k < KSTEPS; ++k) {
+                    const uint32_t accf = (tap | k) != 0 ? 1u : (cs != 0 ? 1u : 0u);
+                    umma_bf16_ss(d_tmem, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc, accf);
+                    umma_bf16_ss(d2, desc_add(at2, 2 * k), desc_add(bt, 2 * k), idesc, accf);
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k)
+                    umma_bf16_ss(d_tmem, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc,
+                                 (tap | k) != 0 ? 1u : (cs != 0 ? 1u : 0u));
+                }
                 umma_commit(&ctl->b_empty[bs]);
                 if (tap == 8) {
                   umma_commit(&ctl->a_empty[as]);
@@ -590,30 +603,35 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n_tile, X0, Y0, n;
       halo_decode(p, t, n_tile, X0, Y0, n);
-      const int ox = X0 + xi, oy = Y0 + yi;
-      const bool valid = ox < p.W && oy < p.H;
-      const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
       const int ch0 = p.cout_off + n_tile * p.BN;
-      uint4 rpre0[4], rpre1[4];
-      bool have0 = false, have1 = false;
-      if (valid) {
-        if (half * 32 < p.BN) have0 = prefetch_residual32(eo, pix, ch0 + half * 32, rpre0);
-        if (half * 32 + 64 < p.BN) have1 = prefetch_residual32(eo, pix, ch0 + half * 32 + 64, rpre1);
-      }
-      mbar_wait(&ctl->acc_full[acc], acc_phase);
-      tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {  // BN <= 256: at most four 32-column chunks per thread
-        const int c = half * 32 + ci * 64;
-        if (c >= p.BN) break;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c, v);
-        tmem_ld_wait();
+      for (int m = 0; m < MT; ++m) {
+        const int ox = X0 + m * 8 + xi, oy = Y0 + yi;
+        const bool valid = ox < p.W && oy < p.H;
+        const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
+        uint4 rpre0[4], rpre1[4];
+        bool have0 = false, have1 = false;
         if (valid) {
-          if (ci == 0) epilogue_chunk32_pre(eo, v, bias_s, pix, ch0 + c, rpre0, have0);
-          else if (ci == 1) epilogue_chunk32_pre(eo, v, bias_s, pix, ch0 + c, rpre1, have1);
-          else epilogue_chunk32(eo, v, bias_s, pix, ch0 + c);
+          if (half * 32 < p.BN) have0 = prefetch_residual32(eo, pix, ch0 + half * 32, rpre0);
+          if (half * 32 + 64 < p.BN) have1 = prefetch_residual32(eo, pix, ch0 + half * 32 + 64, rpre1);
+        }
+        if (m == 0) {
+          mbar_wait(&ctl->acc_full[acc], acc_phase);
+          tc_fence_after_sync();
+        }
+        const uint32_t taddr =
+            tmem_base + (uint32_t)acc * acc_cols + (uint32_t)(m * p.BN) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {  // BN <= 256: at most four 32-column chunks per thread
+          const int c = half * 32 + ci * 64;
+          if (c >= p.BN) break;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c, v);
+          tmem_ld_wait();
+          if (valid) {
+            if (ci == 0) epilogue_chunk32_pre(eo, v, bias_s, pix, ch0 + c, rpre0, have0);
+            else if (ci == 1) epilogue_chunk32_pre(eo, v, bias_s, pix, ch0 + c, rpre1, have1);
+            else epilogue_chunk32(eo, v, bias_s, pix, ch0 + c);
+          }
         }
       }
       tc_fence_before_sync();

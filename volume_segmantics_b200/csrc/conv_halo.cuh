@@ -74,6 +74,11 @@ struct ConvHaloParams {
   // throughput limit of the small-K layers, and two chains run concurrently.
   int32_t epi_groups;
   int32_t mma_warps;  // 2: two MMA issuing warps on alternate tiles (resident weights, ncs == 1)
+  // Streamed-weight launches only: mt == 2 makes a stage two horizontally adjacent 8 x 16 tiles (one
+  // (16+2d)-wide halo box, accumulators in two column ranges), so every weight image streamed through the
+  // B ring feeds twice the MMAs -- N >= 128 layers are bound by shared-memory traffic (operand reads +
+  // incoming weights), not by math.
+  int32_t mt;
   FastDiv div_n_tiles, div_tx, div_ty;  // set by the launcher
   // Timing experiments only (results are wrong when set): bit 0 = no halo TMA loads,
   // bit 1 = one MMA per slab, bit 2 = no output stores.

@@ -155,6 +155,8 @@ struct vsb_engine {
   int halo_a_stages_max = 8;     // vsb_set_flag("halo_a_stages", n)
   bool sync_each = false;        // vsb_set_flag("sync_each", 1): synchronise after every op and name the one that failed
   bool no_fuse_pool = false;     // vsb_set_flag("fuse_pool", 0): separate max-pool kernel after the stem
+  int halo_mt_max_bn = 128;      // vsb_set_flag("halo_mt_bn", n): largest BN that gets two tiles per stage
+  bool no_halo_mt = false;       // vsb_set_flag("halo_mt", 1): one tile per stage in streamed-weight conv_halo launches
   bool no_halo2_tma = false;     // vsb_set_flag("halo2_tma", 0): cp.async loaders for every halo2 source
   bool halo2_mma2 = false;       // vsb_set_flag("halo2_mma2", 1): two MMA warps in the cp.async halo kernel as well
   bool no_mma2 = false;          // vsb_set_flag("mma_warps", 1): a single MMA issuing warp everywhere
@@ -664,6 +666,21 @@ int configure_halo_pipeline(vsb_engine* e, ConvPlan& cp, vsb::ConvHaloParams& h,
       h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, (usable - 3 * (size_t)h.a_stage_bytes) / h.b_bytes);
     }
   }
+  // two tiles per stage for streamed-weight launches (see ConvHaloParams::mt)
+  h.mt = 1;
+  // (BN = 256 would leave a single 512-column accumulator stage: the epilogue no longer overlaps the next
+  // tile's MMAs -- measured slower for layer3, so only BN <= 128)
+  if (h.b_stages != 0 && !tma_epi && !e->no_halo_mt && ot.W % 16 == 0 && h.BN <= e->halo_mt_max_bn) {
+    const int HW2 = 16 + 2 * op.dil, HH2 = 16 + 2 * op.dil;
+    const size_t a2 = align_up((size_t)HW2 * HH2 * 2 * h.kc, 1024);
+    if (usable >= 2 * a2 + 3 * (size_t)h.b_bytes) {
+      h.mt = 2;
+      h.a_stage_bytes = (int)a2;
+      h.a_stages = 2;
+      h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, (usable - 2 * a2) / h.b_bytes);
+      h.acc_stages = h.BN <= 64 ? 4 : (h.BN <= 128 ? 2 : 1);
+    }
+  }
   // the store issuer of the shared-memory epilogue lives in the resident branch of the weight-producer warp
   if (tma_epi && h.b_stages != 0) return fail(VSB_ERR_UNSUPPORTED, "internal: shared-memory epilogue with streamed weights");
   // two MMA warps need the tile sequence to be the A-ring slab sequence (one slab per tile)
@@ -1008,7 +1025,7 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
       if (eff >= 0.6 && fit == 0 && (h.b_stages == 0 || h.b_stages >= 2)) {
         TmaDesc hm;
         const TensorBuf& st = e->tens[op.src[0]];
-        int rc = make_tensor_map(e, &hm, st, nb, false, kc, HW, HH, 1);
+        int rc = make_tensor_map(e, &hm, st, nb, false, kc, 8 * h.mt + 2 * op.dil, HH, 1);
         if (rc) return rc;
         // the halo map lives in slot VSB_MAX_SRC - 1 of this op's map array (single-source op)
         CK(cudaMemcpy(cp.d_maps + (VSB_MAX_SRC - 1), &hm, sizeof(hm), cudaMemcpyHostToDevice));
@@ -1023,7 +1040,7 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
         h.NB = nb;
         h.H = ot.H;
         h.W = ot.W;
-        h.tiles_x = tx;
+        h.tiles_x = (ot.W + 8 * h.mt - 1) / (8 * h.mt);
         h.tiles_y = ty;
         cp.use_halo = true;
       }
@@ -1721,6 +1738,8 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
   }
   else if (n == "sync_each") e->sync_each = value != 0;
   else if (n == "fuse_pool") { e->no_fuse_pool = value == 0; free_workspace(e); }
+  else if (n == "halo_mt_bn") { e->halo_mt_max_bn = value; free_workspace(e); }
+  else if (n == "halo_mt") { e->no_halo_mt = value < 2; free_workspace(e); }
   else if (n == "halo2_tma") { e->no_halo2_tma = value == 0; free_workspace(e); }
   else if (n == "halo2_mma2") { e->halo2_mma2 = value != 0; free_workspace(e); }
   else if (n == "mma_warps") { e->no_mma2 = value < 2; free_workspace(e); }
