@@ -174,12 +174,22 @@ int vsb_set_batch(vsb_engine* e, int32_t slices_per_batch);
  * 1: CUDA-core convolutions everywhere (bring-up / cross-check);
  * 2: as 1 but also without the dedicated 7x7 stem kernel.                   */
 int vsb_set_conv_impl(vsb_engine* e, int32_t impl);
-/* Tuning / cross-check switches: "halo" (1: halo-tile conv kernels, default),
- * "fuse_head" (1: softmax/argmax/merge inside the last conv's epilogue; default 0:
- *   bit-identical, but measured slower than the separate head kernel),
- * "sub_batch_mb" (L2 budget for depth-first sub-batches, 0 = off, default),
- * "tma_epilogue" (1: halo-kernel epilogue through shared memory + TMA store, default),
- * "halo_a_stages" (maximum depth of the halo ring, 2..8, default 8).              */
+/* Tuning / cross-check switches (every alternative computes the same arithmetic; tests/test_engine_paths_gpu.py
+ * checks that the pipeline switches give bit-identical logits):
+ *   "halo" (1)            halo-tile conv kernels; 0: per-tap TMA kernel everywhere
+ *   "tma_epilogue" (1)    epilogue through shared memory + TMA store where weights stay resident; 0: per-thread stores
+ *   "epi_groups" (1)      two epilogue groups on alternate tiles for BN <= 64; 0: one group
+ *   "mma_warps" (2)       two MMA-issuing warps for resident-weight, one-slab launches; 1: one
+ *   "halo_mt" (2)         two tiles per stage for streamed-weight launches with BN <= "halo_mt_bn" (128); 1: one
+ *   "halo_a_stages" (8)   maximum depth of the halo ring, 2..8
+ *   "halo2_tma" (1)       non-up-sampled sources of the cp.async halo kernel fetched by TMA; 0: by the loader warps
+ *   "halo2_mma2" (0)      second MMA warp in the cp.async halo kernel (measured neutral)
+ *   "fuse_pool" (1)       3x3/2 max-pool inside the stem's epilogue; 0: separate kernel
+ *   "fuse_head" (0)       softmax/argmax/merge inside the last conv's epilogue (bit-identical, measured slower)
+ *   "sub_batch_mb" (0)    L2 budget for depth-first sub-batches, 0 = off
+ * Debugging aids: "sync_each" (synchronise after every op and name the one that failed), "halo_prof" (per-launch
+ * cycle accounting of the conv_halo roles on stderr), "halo_dbg" (timing experiments that skip loads / MMAs /
+ * stores -- results are wrong while set).                                                                        */
 int vsb_set_flag(vsb_engine* e, const char* name, int32_t value);
 
 /* ---- test hooks (bit-exact criteria of BASELINE.json) ---------------------
