@@ -91,8 +91,10 @@ __global__ void __launch_bounds__(256) slicer_rows_kernel(const uint8_t* __restr
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)nb * g.Hp;
   const int chunks = (int)(g.Wp >> 4);
+  const uint32_t Hp32 = (uint32_t)g.Hp;
   for (int64_t rowid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); rowid < rows; rowid += (int64_t)gridDim.x * 8) {
-    const int64_t s = rowid / g.Hp, pr = rowid - s * g.Hp;
+    const uint32_t s32 = (uint32_t)rowid / Hp32;  // rows < 2^31 (launcher)
+    const int64_t s = s32, pr = (int64_t)((uint32_t)rowid - s32 * Hp32);
     const int64_t r = reflect101(pr - g.pad_top, g.H);
     const uint8_t* rowp = vol + g.base + (s0 + s) * g.stride_s + r * g.stride_r;
     uint16_t* orow = out + rowid * g.Wp;
@@ -140,10 +142,15 @@ __global__ void __launch_bounds__(256) slicer_xplane_kernel(const uint8_t* __res
   const int64_t total = g.Hp * ctiles * stiles;
   const bool fast = ((s0 | g.base | g.stride_r | g.stride_c) & 15) == 0 && ((uintptr_t)vol & 15) == 0;
   const int64_t slice_elems = g.Hp * g.Wp;
+  const uint32_t ctiles32 = (uint32_t)ctiles, Hp32 = (uint32_t)g.Hp;
+  const bool no_pad_x = g.pad_left == 0 && g.W == g.Wp;
   for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
-    const int64_t ct = t % ctiles;
-    const int64_t pr = (t / ctiles) % g.Hp;
-    const int64_t stile = t / (ctiles * g.Hp);
+    // total < 2^31 (launcher): 32-bit divisions
+    const uint32_t q1 = (uint32_t)t / ctiles32;
+    const int64_t ct = (uint32_t)t - q1 * ctiles32;
+    const uint32_t q2 = q1 / Hp32;
+    const int64_t pr = q1 - q2 * Hp32;
+    const int64_t stile = q2;
     const int64_t r = reflect101(pr - g.pad_top, g.H);
     const uint8_t* rowp = vol + g.base + (s0 + stile * XP_SLICES) * g.stride_s + r * g.stride_r;
     const int sl_left = (int)(nb - stile * XP_SLICES < XP_SLICES ? nb - stile * XP_SLICES : XP_SLICES);
@@ -155,7 +162,7 @@ __global__ void __launch_bounds__(256) slicer_xplane_kernel(const uint8_t* __res
       const int64_t pc = ct * XP_COLS + cc;
       uint32_t v[4] = {0u, 0u, 0u, 0u};
       if (pc < g.Wp) {
-        const int64_t c = reflect101(pc - g.pad_left, g.W);
+        const int64_t c = no_pad_x ? pc : reflect101(pc - g.pad_left, g.W);
         const uint8_t* p = rowp + c * g.stride_c + 16 * sg;
         if (fast && 16 * sg + 15 < sl_left) {
           const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
@@ -204,11 +211,18 @@ void launch_slicer(const uint8_t* vol, const vsb_direction& g, int64_t s0, int n
   if (g.stride_s == 1 && nb >= 8) {
     const int64_t total = g.Hp * ((g.Wp + XP_COLS - 1) / XP_COLS) * ((nb + XP_SLICES - 1) / XP_SLICES);
     const int grid = (int)(total < 148 * 8 ? total : 148 * 8);
-    slicer_xplane_kernel<<<grid, 256, 0, st>>>(vol, g, s0, nb, out);
-  } else {
-    const int64_t blocks = ((int64_t)nb * g.Hp + 7) / 8;
+    if (total < (1ll << 31)) {  // the kernel decodes tiles with 32-bit divisions
+      slicer_xplane_kernel<<<grid, 256, 0, st>>>(vol, g, s0, nb, out);
+      return;
+    }
+  }
+  // the row kernel splits row ids with a 32-bit division: keep nb * Hp below 2^31 per launch
+  const int64_t max_nb = ((1ll << 31) - 1) / g.Hp > 0 ? ((1ll << 31) - 1) / g.Hp : 1;
+  for (int64_t b0 = 0; b0 < nb; b0 += max_nb) {
+    const int cnt = (int)(nb - b0 < max_nb ? nb - b0 : max_nb);
+    const int64_t blocks = ((int64_t)cnt * g.Hp + 7) / 8;
     const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
-    slicer_rows_kernel<<<grid, 256, 0, st>>>(vol, g, s0, nb, out);
+    slicer_rows_kernel<<<grid, 256, 0, st>>>(vol, g, s0 + b0, cnt, out + b0 * g.Hp * g.Wp);
   }
 }
 
