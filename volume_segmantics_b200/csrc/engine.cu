@@ -155,6 +155,7 @@ struct vsb_engine {
   int halo_a_stages_max = 8;     // vsb_set_flag("halo_a_stages", n)
   bool sync_each = false;        // vsb_set_flag("sync_each", 1): synchronise after every op and name the one that failed
   bool no_fuse_pool = false;     // vsb_set_flag("fuse_pool", 0): separate max-pool kernel after the stem
+  int halo_ab_override = 0;      // vsb_set_flag("halo_ab", a*10+b): ring depths of streamed-weight launches (tuning aid)
   int halo_mt_max_bn = 128;      // vsb_set_flag("halo_mt_bn", n): largest BN that gets two tiles per stage
   bool no_halo_mt = false;       // vsb_set_flag("halo_mt", 1): one tile per stage in streamed-weight conv_halo launches
   bool no_halo2_tma = false;     // vsb_set_flag("halo2_tma", 0): cp.async loaders for every halo2 source
@@ -664,6 +665,13 @@ int configure_halo_pipeline(vsb_engine* e, ConvPlan& cp, vsb::ConvHaloParams& h,
     if (h.b_stages >= 6 && usable >= 3 * (size_t)h.a_stage_bytes + 4 * (size_t)h.b_bytes) {
       h.a_stages = 3;
       h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, (usable - 3 * (size_t)h.a_stage_bytes) / h.b_bytes);
+    }
+  }
+  if (h.b_stages != 0 && e->halo_ab_override > 0) {  // tuning aid: a_stages * 10 + b_stages for streamed launches
+    const int a = e->halo_ab_override / 10, b = e->halo_ab_override % 10;
+    if (a >= 2 && b >= 2 && (size_t)a * h.a_stage_bytes + (size_t)b * h.b_bytes <= usable) {
+      h.a_stages = a;
+      h.b_stages = b;
     }
   }
   // two tiles per stage for streamed-weight launches (see ConvHaloParams::mt)
@@ -1738,6 +1746,7 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
   }
   else if (n == "sync_each") e->sync_each = value != 0;
   else if (n == "fuse_pool") { e->no_fuse_pool = value == 0; free_workspace(e); }
+  else if (n == "halo_ab") { e->halo_ab_override = value; free_workspace(e); }
   else if (n == "halo_mt_bn") { e->halo_mt_max_bn = value; free_workspace(e); }
   else if (n == "halo_mt") { e->no_halo_mt = value < 2; free_workspace(e); }
   else if (n == "halo2_tma") { e->no_halo2_tma = value == 0; free_workspace(e); }
