@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define VSB_ABI_VERSION 1
+#define VSB_ABI_VERSION 2
 
 #define VSB_OK 0
 #define VSB_ERR_INVALID -1   /* bad argument / plan */
@@ -35,13 +35,13 @@ typedef struct vsb_engine vsb_engine;
 /* ---- network plan ------------------------------------------------------
  * The host (Python) folds BatchNorm into the convolutions and lowers the
  * smp network (model_2d.py:10-39) into a flat op list over numbered tensors.
- * Tensor 0 is the network input: [nb, Hp, Wp, 1] bf16, written by the slicer.
+ * Tensor 0 is the network input: [nb, Hp, Wp, 1] 16-bit (see vsb_act_dtype), written by the slicer.
  * Spatial size of tensor t is (Hp >> ds_log2, Wp >> ds_log2); ds_log2 == -1
  * means 1x1 (global pooled).  Layout of every tensor is NHWC.               */
 typedef struct {
   int32_t channels;
   int32_t ds_log2;
-  int32_t dtype; /* 0 = bf16, 1 = f32 */
+  int32_t dtype; /* 0 = 16-bit activation format of the build (vsb_act_dtype), 1 = f32 */
   int32_t reserved;
 } vsb_tensor_desc;
 
@@ -68,7 +68,7 @@ typedef struct {
   int32_t relu;
   int32_t mode, factor;        /* UPSAMPLE: mode/factor. HEAD: factor = bilinear
                                   upsampling of the logits (1 = none)         */
-  int64_t w_off;               /* byte offset in the weight blob of bf16
+  int64_t w_off;               /* byte offset in the weight blob of 16-bit
                                   [cout][kh][kw][cin/groups] (OHWI)           */
   int64_t b_off;               /* byte offset of f32 [cout] bias              */
 } vsb_op;
@@ -112,6 +112,18 @@ int vsb_direction_geometry(int64_t Z, int64_t Y, int64_t X, int32_t d, vsb_direc
 int vsb_set_volume(vsb_engine* e, const uint8_t* vol, int32_t on_device, int64_t Z, int64_t Y,
                    int64_t X);
 
+/* The same for volumes that are not uint8 (datasets.py:129-135: integer slices of ANY bit depth are
+ * cast to float32 and divided by 255, float32 slices are used as they are; then (x - 0.449) / 0.226 in
+ * fp32).  dtype: 0 float32, 2 uint8, 3 int8, 4 uint16, 5 int16, 7 int32 -- the types cv2.copyMakeBorder
+ * (albumentations PadIfNeeded, augmentations.py:61-65) pads without conversion.  float64 / float16
+ * volumes fail in the reference too (double input to a float model), so they are refused here.         */
+int vsb_set_volume_typed(vsb_engine* e, const void* vol, int32_t dtype, int32_t on_device, int64_t Z, int64_t Y,
+                         int64_t X);
+
+/* Residency token: incremented whenever the engine's resident volume changes, so the host shim can tell
+ * that the array it is asked to predict is the one a previous call left in HBM (vsb_raw_clip_to_volume). */
+int vsb_volume_generation(vsb_engine* e, int64_t* generation);
+
 /* Zero the key volume (start of a new prediction on the same data).         */
 int vsb_reset_keys(vsb_engine* e);
 
@@ -143,6 +155,23 @@ int vsb_bind_keys(vsb_engine* e, void* dev_ptr);
 int vsb_keys_ipc_export(vsb_engine* e, uint8_t* handle64);
 int vsb_peers_open(vsb_engine* e, int32_t n_ranks, int32_t my_rank, const uint8_t* handles64);
 int vsb_peers_close(vsb_engine* e);
+/* One host process driving several GPUs (the additive `cuda_devices` setting of the drop-in
+ * VolSeg2dPredictor): the peers are engine handles of THIS process, read through ordinary
+ * peer access.  engines[my_rank] must be `e`; every engine must already hold a volume of the same size.
+ *   vsb_set_volume_shard  allocate the whole uint8 volume, upload only voxels [v_begin, v_end) of it
+ *   vsb_volume_pull       copy voxels [v_begin, v_end) of `peer`'s volume into this engine's (NVLink
+ *                         peer copy on this engine's stream): N uploads of 1/N + an all-gather over
+ *                         NVLink instead of N uploads of the whole volume over PCIe
+ *   vsb_fetch_shard       max-reduce + unpack voxels [v_begin, v_end) over all peers' keys and copy
+ *                         them to the host (pointers address the SHARD's first element): every GPU
+ *                         downloads its own part of the result over its own PCIe link
+ * The caller orders the engines (all predictions finished before any vsb_fetch_shard; all shards
+ * fetched before the next vsb_reset_keys), e.g. with vsb_synchronize + a host barrier.                 */
+int vsb_peers_attach(vsb_engine* e, int32_t n_ranks, int32_t my_rank, vsb_engine* const* engines);
+int vsb_set_volume_shard(vsb_engine* e, const uint8_t* vol_host, int64_t Z, int64_t Y, int64_t X, int64_t v_begin,
+                         int64_t v_end);
+int vsb_volume_pull(vsb_engine* e, vsb_engine* peer, int64_t v_begin, int64_t v_end);
+int vsb_fetch_shard(vsb_engine* e, int64_t v_begin, int64_t v_end, uint8_t* labels_host, uint16_t* probs_fp16_host);
 int vsb_reduce_unpack_shard(vsb_engine* e, int64_t v_begin, int64_t v_end, uint8_t* labels_dev,
                             uint16_t* probs_fp16_dev);
 
@@ -193,14 +222,16 @@ int vsb_set_conv_impl(vsb_engine* e, int32_t impl);
 int vsb_set_flag(vsb_engine* e, const char* name, int32_t value);
 
 /* ---- test hooks (bit-exact criteria of BASELINE.json) ---------------------
- * Slicer only: padded+normalised bf16 images [nb, Hp, Wp] of direction d,
+ * Slicer only: padded+normalised 16-bit (vsb_act_dtype) images [nb, Hp, Wp] of direction d,
  * slices [s0, s0+nb) (datasets.py:120-142 + augmentations.py:46-65).         */
-int vsb_slice_batch(vsb_engine* e, int32_t d, int64_t s0, int32_t nb, uint16_t* out_bf16_host);
+int vsb_slice_batch(vsb_engine* e, int32_t d, int64_t s0, int32_t nb, uint16_t* out_act16_host);
+/* The same through the generic (typed) slicer kernels, whatever the dtype of the resident volume.     */
+int vsb_slice_batch_generic(vsb_engine* e, int32_t d, int64_t s0, int32_t nb, uint16_t* out_act16_host);
 /* Merge only: inject per-direction slice-space results [S,H,W] (cropped
  * dims) fp32 max-prob + uint8 label (host pointers) for direction d.         */
 int vsb_merge_injected(vsb_engine* e, int32_t d, const float* probs, const uint8_t* labels);
 /* Network only: images f32 [nb,Hp,Wp] (host, already padded+normalised; they
- * are rounded to bf16 as the slicer would) -> logits f32 [nb,Hp,Wp,C] (host). */
+ * are rounded to the 16-bit format as the slicer would) -> logits f32 [nb,Hp,Wp,C] (host). */
 int vsb_forward_logits(vsb_engine* e, const float* images, int32_t nb, int32_t Hp, int32_t Wp,
                        float* logits_out);
 /* Copy tensor `t` of the last vsb_forward_logits call to host as f32 NHWC.   */
@@ -218,13 +249,34 @@ int vsb_set_profiling(vsb_engine* e, int32_t on);
 int vsb_op_ms(vsb_engine* e, int32_t op, float* ms, int64_t* launches);
 
 /* ---- clip_to_uint8 (base_data_utils.py:243-287), SURVEY 8f-1 --------------
- * Elementwise part of the reference's pre-processing: NaN -> mean, clip to
- * [lower, upper], rescale to 0..255, truncate to uint8 -- the same IEEE double
- * operations in the same order as numpy (bit-exact given the same statistics, which
- * the host computes with numpy like the reference).  `data` and `out` are HOST
- * pointers; dtype: 0 f32, 1 f64, 2 u8, 3 i8, 4 u16, 5 i16, 6 u32, 7 i32, 8 i64.     */
+ * Elementwise part of the reference's pre-processing with host buffers: NaN -> mean, clip to
+ * [lower, upper], rescale to 0..255, truncate to uint8 -- the same IEEE operations in the same order
+ * and PRECISION as numpy: float32 arithmetic for float32 data (numpy keeps the array dtype; mean / lower
+ * / upper are then float32 values), float64 for float64 and integer data (astype(float)).  Bit-exact
+ * given the same statistics.  `data` and `out` are HOST pointers, streamed through the GPU in chunks;
+ * dtype: 0 f32, 1 f64, 2 u8, 3 i8, 4 u16, 5 i16, 6 u32, 7 i32, 8 i64.                                   */
 int vsb_clip_to_uint8(vsb_engine* e, const void* data, int32_t dtype, int64_t n, double mean,
                       double lower, double upper, uint8_t* out);
+
+
+/* ---- BaseDataManager._preprocess_data on the GPU (base_data_manager.py:29-42, base_data_utils.py:243-287)
+ * One upload of the raw volume, then:
+ *   vsb_raw_moments          out4 = {count of non-NaN voxels, nanmean, nanstd, count of NaNs}; two-pass
+ *                            float64 reduction with a fixed reduction order (bit-reproducible run to run;
+ *                            agrees with numpy's pairwise summation to rounding, not bit for bit).  For
+ *                            float32 data mean and std are rounded to float32 as numpy returns them.
+ *   vsb_raw_clip_to_volume   NaN -> mean, clip to [lower, upper], rescale to 0..255, truncate -- in float32
+ *                            arithmetic for float32 data and float64 otherwise, exactly the operations
+ *                            numpy performs (bit-exact given the same mean / lower / upper).  counts2 =
+ *                            {voxels > upper, voxels < lower} (the reference's two log lines).  The uint8
+ *                            result BECOMES THE ENGINE'S RESIDENT VOLUME (no second upload) and is also
+ *                            copied to out_host when that is not NULL.  Frees the raw volume.
+ * dtype codes as vsb_clip_to_uint8.                                                                        */
+int vsb_raw_upload(vsb_engine* e, const void* data_host, int32_t dtype, int64_t n);
+int vsb_raw_moments(vsb_engine* e, double* out4);
+int vsb_raw_clip_to_volume(vsb_engine* e, double mean, double lower, double upper, int64_t Z, int64_t Y, int64_t X,
+                           uint8_t* out_host, uint64_t* counts2);
+int vsb_raw_release(vsb_engine* e);
 
 #ifdef __cplusplus
 }

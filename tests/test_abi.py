@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in vsb200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
-    assert lib.vsb_abi_version() == 1
+    assert lib.vsb_abi_version() == 2
 
 
 def test_struct_layouts_match_header():

@@ -75,6 +75,8 @@ SIGNATURES = {
     "vsb_load_plan": (C.c_int, [_P, C.POINTER(TensorDesc), C.c_int32, C.POINTER(Op), C.c_int32, _P, C.c_size_t, C.c_int32]),
     "vsb_direction_geometry": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.POINTER(Direction)]),
     "vsb_set_volume": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64]),
+    "vsb_set_volume_typed": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64]),
+    "vsb_volume_generation": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "vsb_reset_keys": (C.c_int, [_P]),
     "vsb_predict_range": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64]),
     "vsb_predict": (C.c_int, [_P, C.c_uint32, C.c_int32]),
@@ -83,6 +85,10 @@ SIGNATURES = {
     "vsb_keys_ipc_export": (C.c_int, [_P, _P]),
     "vsb_peers_open": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "vsb_peers_close": (C.c_int, [_P]),
+    "vsb_peers_attach": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "vsb_set_volume_shard": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
+    "vsb_volume_pull": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
+    "vsb_fetch_shard": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "vsb_reduce_unpack_shard": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "vsb_fetch": (C.c_int, [_P, _P, _P]),
     "vsb_unpack_device": (C.c_int, [_P, _P, _P]),
@@ -95,11 +101,17 @@ SIGNATURES = {
     "vsb_set_conv_impl": (C.c_int, [_P, C.c_int32]),
     "vsb_set_flag": (C.c_int, [_P, C.c_char_p, C.c_int32]),
     "vsb_slice_batch": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int32, _P]),
+    "vsb_slice_batch_generic": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int32, _P]),
     "vsb_merge_injected": (C.c_int, [_P, C.c_int32, _P, _P]),
     "vsb_forward_logits": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vsb_debug_tensor": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "vsb_stage_ms": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "vsb_clip_to_uint8": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_double, C.c_double, C.c_double, _P]),
+    "vsb_raw_upload": (C.c_int, [_P, _P, C.c_int32, C.c_int64]),
+    "vsb_raw_moments": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "vsb_raw_clip_to_volume": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int64, C.c_int64, _P,
+                                         C.POINTER(C.c_uint64)]),
+    "vsb_raw_release": (C.c_int, [_P]),
     "vsb_set_profiling": (C.c_int, [_P, C.c_int32]),
     "vsb_op_ms": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
 }

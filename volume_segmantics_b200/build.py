@@ -15,7 +15,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libvsb200.so"          # fp16 activations/weights (default)
 LIB_BF16 = HERE / "libvsb200_bf16.so"  # bfloat16 variant (VSB200_VARIANT=bf16)
-SOURCES = ["engine.cu", "conv_tc.cu", "conv_halo.cu", "kernels_simple.cu", "kernels_head.cu"]
+SOURCES = ["engine.cu", "conv_tc.cu", "conv_halo.cu", "kernels_simple.cu", "kernels_head.cu", "kernels_ingest.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -52,7 +52,11 @@ def build(force: bool = False, verbose: bool = True) -> Path:
             raise RuntimeError(f"nvcc failed on {src}")
     for tag, lib, _ in variants:
         objs = [str(builddir / f"{src}.{tag}.o") for src in SOURCES]
-        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", str(lib), *objs]
+        # the CUDA runtime is linked as a shared library (libcudart.so.12, the one torch has already
+        # loaded when the host shim runs): the shipped artefact then carries none of the runtime's own
+        # entry-point names, and the engine shares one runtime instance with the plumbing
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "shared",
+               "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-o", str(lib), *objs]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

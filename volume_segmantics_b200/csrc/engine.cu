@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
@@ -129,16 +130,24 @@ struct vsb_engine {
   // volume
   const uint8_t* d_vol = nullptr;
   uint8_t* d_vol_owned = nullptr;
+  size_t vol_owned_bytes = 0;
+  int vol_dtype = 2;          // dtype code of the resident volume (2 = uint8; see vsb_set_volume_typed)
+  void* d_raw = nullptr;      // raw (unclipped) volume of the pre-processing calls (vsb_raw_*)
+  int raw_dtype = 0;
+  int64_t raw_n = 0;
+  int64_t vol_generation = 0;  // bumped whenever the resident volume changes (host-side residency token)
   int64_t Z = 0, Y = 0, X = 0;
   unsigned long long* d_keys = nullptr;
   unsigned long long* d_keys_owned = nullptr;
   uint8_t* d_votes = nullptr;
+  size_t votes_bytes = 0;  // capacity of d_votes (voxels x classes of the plan it was allocated for)
   int vote_mode = 0;
   uint8_t* d_labels = nullptr;
   uint16_t* d_probs = nullptr;
   // multi-GPU peers (CUDA IPC mappings of the other ranks' key volumes)
   int n_ranks = 1, my_rank = 0;
   unsigned long long* peer_keys[8] = {nullptr};
+  bool peers_ipc = false;  // peer_keys are CUDA-IPC mappings (closed with cudaIpcCloseMemHandle) vs same-process pointers
 
   // workspace
   int ws_Hp = 0, ws_Wp = 0, ws_nb = 0;
@@ -1360,7 +1369,8 @@ int predict_range(vsb_engine* e, int d, int64_t s_begin, int64_t s_end) {
     const int nb = (int)std::min<int64_t>(nbmax, s_end - s0);
     {
       ProfScope ps(e, PC_SLICER);
-      vsb::launch_slicer(e->d_vol, g, s0, nb, (uint16_t*)e->tens[0].ptr, e->stream);
+      if (e->vol_dtype == 2) vsb::launch_slicer(e->d_vol, g, s0, nb, (uint16_t*)e->tens[0].ptr, e->stream);
+      else vsb::launch_slicer_typed(e->d_vol, e->vol_dtype, g, s0, nb, (uint16_t*)e->tens[0].ptr, e->stream);
       CK(cudaGetLastError());
     }
     // fused head: the conv that produces the logits merges them in its own epilogue
@@ -1479,6 +1489,8 @@ int vsb_create(int device, vsb_engine** out) {
   return VSB_OK;
 }
 
+static void close_peers(vsb_engine* e);
+
 static void free_plan(vsb_engine* e) {
   for (ConvPlan& cp : e->conv) {
     cudaFree(cp.d_runs);
@@ -1491,9 +1503,12 @@ static void free_plan(vsb_engine* e) {
   cudaFree(e->d_weights);
   e->d_weights = nullptr;
   e->has_plan = false;
+  // the vote volume is sized by the class count of the plan that was loaded when it was allocated
+  cudaFree(e->d_votes);
+  e->d_votes = nullptr;
+  e->votes_bytes = 0;
+  e->vote_mode = 0;
 }
-
-static void close_peers(vsb_engine* e);
 
 void vsb_destroy(vsb_engine* e) {
   if (!e) return;
@@ -1506,6 +1521,7 @@ void vsb_destroy(vsb_engine* e) {
   free_plan(e);
   close_peers(e);
   cudaFree(e->d_vol_owned);
+  cudaFree(e->d_raw);
   cudaFree(e->d_keys_owned);
   cudaFree(e->d_votes);
   cudaFree(e->d_labels);
@@ -1563,30 +1579,22 @@ int vsb_load_plan(vsb_engine* e, const vsb_tensor_desc* tensors, int32_t n_tenso
   return VSB_OK;
 }
 
-int vsb_set_volume(vsb_engine* e, const uint8_t* vol, int32_t on_device, int64_t Z, int64_t Y, int64_t X) {
-  if (!e || !vol || Z <= 0 || Y <= 0 || X <= 0) return fail(VSB_ERR_INVALID, "bad volume arguments");
-  CK(cudaSetDevice(e->device));
-  CK(cudaStreamSynchronize(e->stream));
+static const int kDtypeBytes[9] = {4, 8, 1, 1, 2, 2, 4, 4, 8};
+
+// (Re)allocate everything that depends on the voxel count; zero the keys.  The volume buffer itself is
+// (re)allocated by the callers that own it.
+static int resize_voxel_state(vsb_engine* e, int64_t Z, int64_t Y, int64_t X) {
   const int64_t n = Z * Y * X;
-  const bool resize = n != e->Z * e->Y * e->X;
-  if (on_device) {
-    cudaFree(e->d_vol_owned);
-    e->d_vol_owned = nullptr;
-    e->d_vol = vol;
-  } else {
-    if (resize || !e->d_vol_owned) {
-      cudaFree(e->d_vol_owned);
-      e->d_vol_owned = nullptr;
-      CK(cudaMalloc(&e->d_vol_owned, align_up(n, 256)));
-    }
-    CK(cudaMemcpyAsync(e->d_vol_owned, vol, n, cudaMemcpyHostToDevice, e->stream));
-    e->d_vol = e->d_vol_owned;
-  }
+  const bool resize = n != e->Z * e->Y * e->X || !e->d_keys_owned;
   if (resize) {
+    // the other ranks map the key volume that is freed here: the exchange must be re-opened
+    // (vsb_keys_ipc_export / vsb_peers_open / vsb_peers_attach) after every change of the volume size
+    close_peers(e);
     cudaFree(e->d_keys_owned);
     e->d_keys_owned = nullptr;
     cudaFree(e->d_votes);
     e->d_votes = nullptr;
+    e->votes_bytes = 0;
     cudaFree(e->d_labels);
     e->d_labels = nullptr;
     cudaFree(e->d_probs);
@@ -1596,7 +1604,76 @@ int vsb_set_volume(vsb_engine* e, const uint8_t* vol, int32_t on_device, int64_t
   }
   e->Z = Z; e->Y = Y; e->X = X;
   CK(cudaMemsetAsync(e->d_keys, 0, n * 8, e->stream));
-  if (e->d_votes) CK(cudaMemsetAsync(e->d_votes, 0, align_up((size_t)n * e->num_classes, 4), e->stream));
+  if (e->d_votes) CK(cudaMemsetAsync(e->d_votes, 0, e->votes_bytes, e->stream));
+  return VSB_OK;
+}
+
+static int ensure_owned_volume(vsb_engine* e, size_t bytes) {
+  if (!e->d_vol_owned || e->vol_owned_bytes < bytes) {
+    cudaFree(e->d_vol_owned);
+    e->d_vol_owned = nullptr;
+    e->vol_owned_bytes = 0;
+    CK(cudaMalloc(&e->d_vol_owned, align_up(bytes, 256)));
+    e->vol_owned_bytes = align_up(bytes, 256);
+  }
+  return VSB_OK;
+}
+
+// Common body of vsb_set_volume / vsb_set_volume_typed / vsb_set_volume_shard: elements
+// [v_begin, v_end) of a host volume are uploaded (the whole volume for the first two).
+static int set_volume_impl(vsb_engine* e, const void* vol, int dtype, int on_device, int64_t Z, int64_t Y, int64_t X,
+                           int64_t v_begin, int64_t v_end) {
+  if (!e || !vol || Z <= 0 || Y <= 0 || X <= 0) return fail(VSB_ERR_INVALID, "bad volume arguments");
+  if (dtype < 0 || dtype > 8 || !vsb::slicer_typed_supported(dtype))
+    return fail(VSB_ERR_UNSUPPORTED,
+                "volume dtype code %d is not sliceable (supported: float32, uint8, int8, uint16, int16, int32)", dtype);
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  const int64_t n = Z * Y * X;
+  const size_t esz = (size_t)kDtypeBytes[dtype];
+  if (on_device) {
+    cudaFree(e->d_vol_owned);
+    e->d_vol_owned = nullptr;
+    e->vol_owned_bytes = 0;
+    e->d_vol = (const uint8_t*)vol;
+  } else {
+    int rc = ensure_owned_volume(e, (size_t)n * esz);
+    if (rc) return rc;
+    if (v_end > v_begin)
+      CK(cudaMemcpyAsync(e->d_vol_owned + (size_t)v_begin * esz, (const uint8_t*)vol + (size_t)v_begin * esz,
+                         (size_t)(v_end - v_begin) * esz, cudaMemcpyHostToDevice, e->stream));
+    e->d_vol = e->d_vol_owned;
+  }
+  e->vol_dtype = dtype;
+  e->vol_generation += 1;
+  return resize_voxel_state(e, Z, Y, X);
+}
+
+int vsb_set_volume(vsb_engine* e, const uint8_t* vol, int32_t on_device, int64_t Z, int64_t Y, int64_t X) {
+  return set_volume_impl(e, vol, 2, on_device, Z, Y, X, 0, Z * Y * X);
+}
+
+int vsb_set_volume_typed(vsb_engine* e, const void* vol, int32_t dtype, int32_t on_device, int64_t Z, int64_t Y,
+                         int64_t X) {
+  return set_volume_impl(e, vol, dtype, on_device, Z, Y, X, 0, Z * Y * X);
+}
+
+int vsb_set_volume_shard(vsb_engine* e, const uint8_t* vol_host, int64_t Z, int64_t Y, int64_t X, int64_t v_begin,
+                         int64_t v_end) {
+  if (v_begin < 0 || v_end > Z * Y * X || v_begin > v_end) return fail(VSB_ERR_INVALID, "bad voxel range");
+  return set_volume_impl(e, vol_host, 2, 0, Z, Y, X, v_begin, v_end);
+}
+
+int vsb_volume_pull(vsb_engine* e, vsb_engine* peer, int64_t v_begin, int64_t v_end) {
+  if (!e || !peer || !e->d_vol_owned || !peer->d_vol) return fail(VSB_ERR_STATE, "volume_pull: no volume set");
+  const int64_t n = e->Z * e->Y * e->X;
+  if (n != peer->Z * peer->Y * peer->X || e->vol_dtype != 2 || peer->vol_dtype != 2)
+    return fail(VSB_ERR_INVALID, "volume_pull: the two engines hold different volumes");
+  if (v_begin < 0 || v_end > n || v_begin > v_end) return fail(VSB_ERR_INVALID, "bad voxel range");
+  if (v_begin == v_end || e == peer) return VSB_OK;
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyPeerAsync(e->d_vol_owned + v_begin, e->device, peer->d_vol + v_begin, peer->device,
+                         (size_t)(v_end - v_begin), e->stream));
   return VSB_OK;
 }
 
@@ -1605,7 +1682,7 @@ int vsb_reset_keys(vsb_engine* e) {
   CK(cudaSetDevice(e->device));
   const int64_t n = e->Z * e->Y * e->X;
   CK(cudaMemsetAsync(e->d_keys, 0, n * 8, e->stream));
-  if (e->d_votes) CK(cudaMemsetAsync(e->d_votes, 0, align_up((size_t)n * e->num_classes, 4), e->stream));
+  if (e->d_votes) CK(cudaMemsetAsync(e->d_votes, 0, e->votes_bytes, e->stream));
   return VSB_OK;
 }
 
@@ -1683,10 +1760,15 @@ int vsb_set_vote_mode(vsb_engine* e, int32_t on) {
   if (on && !e->d_keys) return fail(VSB_ERR_STATE, "no volume set");
   CK(cudaSetDevice(e->device));
   e->vote_mode = on ? 1 : 0;
-  if (on && !e->d_votes) {
-    const size_t n = align_up((size_t)e->Z * e->Y * e->X * e->num_classes, 4);
-    CK(cudaMalloc(&e->d_votes, n));
-    CK(cudaMemsetAsync(e->d_votes, 0, n, e->stream));
+  const size_t need = align_up((size_t)e->Z * e->Y * e->X * e->num_classes, 4);
+  if (on && (!e->d_votes || e->votes_bytes < need)) {
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_votes);
+    e->d_votes = nullptr;
+    e->votes_bytes = 0;
+    CK(cudaMalloc(&e->d_votes, need));
+    e->votes_bytes = need;
+    CK(cudaMemsetAsync(e->d_votes, 0, need, e->stream));
   }
   return VSB_OK;
 }
@@ -1765,7 +1847,14 @@ int vsb_set_conv_impl(vsb_engine* e, int32_t impl) {
   return VSB_OK;
 }
 
+static int slice_batch_impl(vsb_engine* e, int32_t d, int64_t s0, int32_t nb, uint16_t* out, bool typed_path);
 int vsb_slice_batch(vsb_engine* e, int32_t d, int64_t s0, int32_t nb, uint16_t* out) {
+  return slice_batch_impl(e, d, s0, nb, out, false);
+}
+int vsb_slice_batch_generic(vsb_engine* e, int32_t d, int64_t s0, int32_t nb, uint16_t* out) {
+  return slice_batch_impl(e, d, s0, nb, out, true);
+}
+static int slice_batch_impl(vsb_engine* e, int32_t d, int64_t s0, int32_t nb, uint16_t* out, bool typed_path) {
   if (!e || !e->d_vol || !out || nb < 1) return fail(VSB_ERR_STATE, "no volume set / bad args");
   CK(cudaSetDevice(e->device));
   vsb_direction g;
@@ -1775,7 +1864,8 @@ int vsb_slice_batch(vsb_engine* e, int32_t d, int64_t s0, int32_t nb, uint16_t* 
   uint16_t* dbuf = nullptr;
   const size_t bytes = (size_t)nb * g.Hp * g.Wp * 2;
   CK(cudaMalloc(&dbuf, bytes));
-  vsb::launch_slicer(e->d_vol, g, s0, nb, dbuf, e->stream);
+  if (e->vol_dtype == 2 && !typed_path) vsb::launch_slicer(e->d_vol, g, s0, nb, dbuf, e->stream);
+  else vsb::launch_slicer_typed(e->d_vol, e->vol_dtype, g, s0, nb, dbuf, e->stream);
   cudaError_t err = cudaGetLastError();
   if (err == cudaSuccess) err = cudaMemcpyAsync(out, dbuf, bytes, cudaMemcpyDeviceToHost, e->stream);
   if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
@@ -1890,26 +1980,133 @@ int vsb_clip_to_uint8(vsb_engine* e, const void* data, int32_t dtype, int64_t n,
   if (!e || !data || !out || n <= 0 || dtype < 0 || dtype > 8) return fail(VSB_ERR_INVALID, "bad clip arguments");
   if (!(upper > lower)) return fail(VSB_ERR_INVALID, "clip range is empty (upper <= lower)");
   CK(cudaSetDevice(e->device));
-  static const int esz[9] = {4, 8, 1, 1, 2, 2, 4, 4, 8};
+  const int* esz = kDtypeBytes;
   // stream the volume through the GPU in chunks so a float64 1024^3 volume never needs 8 GiB at once
   const int64_t chunk = 256ll << 20;
   void* din = nullptr;
   uint8_t* dout = nullptr;
+  unsigned long long* dcnt = nullptr;
   CK(cudaMalloc(&din, (size_t)std::min(chunk, n) * esz[dtype]));
   cudaError_t err = cudaMalloc(&dout, (size_t)std::min(chunk, n));
+  if (err == cudaSuccess) err = cudaMalloc(&dcnt, 16);
+  if (err == cudaSuccess) err = cudaMemsetAsync(dcnt, 0, 16, e->stream);
   for (int64_t off = 0; err == cudaSuccess && off < n; off += chunk) {
     const int64_t m = std::min(chunk, n - off);
     err = cudaMemcpyAsync(din, (const uint8_t*)data + off * esz[dtype], (size_t)m * esz[dtype], cudaMemcpyHostToDevice,
                           e->stream);
     if (err != cudaSuccess) break;
-    vsb::launch_clip_u8(din, dtype, m, mean, lower, upper, dout, e->stream);
+    e->launches += 1;
+    vsb::launch_clip_count(din, dtype, m, mean, lower, upper, dout, dcnt, e->stream);
     err = cudaGetLastError();
     if (err == cudaSuccess) err = cudaMemcpyAsync(out + off, dout, (size_t)m, cudaMemcpyDeviceToHost, e->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
   }
   cudaFree(din);
   cudaFree(dout);
+  cudaFree(dcnt);
   CK(err);
+  return VSB_OK;
+}
+
+// ---- pre-processing on the GPU: raw volume -> statistics -> clipped uint8 volume ----
+int vsb_raw_upload(vsb_engine* e, const void* data, int32_t dtype, int64_t n) {
+  if (!e || !data || n <= 0 || dtype < 0 || dtype > 8) return fail(VSB_ERR_INVALID, "bad raw-volume arguments");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(e->d_raw);
+  e->d_raw = nullptr;
+  e->raw_n = 0;
+  CK(cudaMalloc(&e->d_raw, (size_t)n * kDtypeBytes[dtype]));
+  e->raw_dtype = dtype;
+  e->raw_n = n;
+  CK(cudaMemcpyAsync(e->d_raw, data, (size_t)n * kDtypeBytes[dtype], cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));  // the host buffer may go away
+  return VSB_OK;
+}
+
+int vsb_raw_release(vsb_engine* e) {
+  if (!e) return fail(VSB_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(e->d_raw);
+  e->d_raw = nullptr;
+  e->raw_n = 0;
+  return VSB_OK;
+}
+
+int vsb_raw_moments(vsb_engine* e, double* out4) {
+  if (!e || !e->d_raw || !out4) return fail(VSB_ERR_STATE, "no raw volume uploaded");
+  CK(cudaSetDevice(e->device));
+  const int np = vsb::moments_partials();
+  double* dpart = nullptr;
+  CK(cudaMalloc(&dpart, sizeof(double) * np));
+  std::vector<double> h(np);
+  double sum = 0, cnt = 0, sq = 0, nans = 0, mean = 0;
+  cudaError_t err = cudaSuccess;
+  for (int pass = 1; pass <= 2 && err == cudaSuccess; ++pass) {
+    e->launches += 1;
+    vsb::launch_moments(e->d_raw, e->raw_dtype, e->raw_n, pass, mean, dpart, e->stream);
+    err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaMemcpyAsync(h.data(), dpart, sizeof(double) * np, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) break;
+    // block partials are combined in block order: the same bits on every run
+    double a = 0, b = 0;
+    for (int i = 0; i < np; i += 2) { a += h[i]; b += h[i + 1]; }
+    if (pass == 1) {
+      sum = a; cnt = b;
+      mean = cnt > 0 ? sum / cnt : 0.0;
+      if (e->raw_dtype == 0) mean = (double)(float)mean;  // numpy returns (and subtracts) a float32 mean for float32 data
+    } else {
+      sq = a; nans = b;
+    }
+  }
+  cudaFree(dpart);
+  CK(err);
+  double sd = cnt > 0 ? sqrt(sq / cnt) : 0.0;
+  if (e->raw_dtype == 0) sd = (double)(float)sd;
+  out4[0] = cnt; out4[1] = mean; out4[2] = sd; out4[3] = nans;
+  return VSB_OK;
+}
+
+int vsb_raw_clip_to_volume(vsb_engine* e, double mean, double lower, double upper, int64_t Z, int64_t Y, int64_t X,
+                           uint8_t* out_host, uint64_t* counts2) {
+  if (!e || !e->d_raw) return fail(VSB_ERR_STATE, "no raw volume uploaded");
+  if (Z <= 0 || Y <= 0 || X <= 0 || Z * Y * X != e->raw_n) return fail(VSB_ERR_INVALID, "shape does not match the raw volume");
+  if (!(upper > lower)) return fail(VSB_ERR_INVALID, "clip range is empty (upper <= lower)");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  const int64_t n = e->raw_n;
+  int rc = ensure_owned_volume(e, (size_t)n);
+  if (rc) return rc;
+  unsigned long long* dcnt = nullptr;
+  CK(cudaMalloc(&dcnt, 16));
+  cudaError_t err = cudaMemsetAsync(dcnt, 0, 16, e->stream);
+  unsigned long long hc[2] = {0, 0};
+  if (err == cudaSuccess) {
+    e->launches += 1;
+    vsb::launch_clip_count(e->d_raw, e->raw_dtype, n, mean, lower, upper, e->d_vol_owned, dcnt, e->stream);
+    err = cudaGetLastError();
+  }
+  if (err == cudaSuccess) err = cudaMemcpyAsync(hc, dcnt, 16, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess && out_host) err = cudaMemcpyAsync(out_host, e->d_vol_owned, (size_t)n, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  cudaFree(dcnt);
+  cudaFree(e->d_raw);
+  e->d_raw = nullptr;
+  e->raw_n = 0;
+  CK(err);
+  if (counts2) { counts2[0] = hc[0]; counts2[1] = hc[1]; }
+  // the clipped volume is now the engine's resident uint8 volume (no second upload)
+  e->d_vol = e->d_vol_owned;
+  e->vol_dtype = 2;
+  e->vol_generation += 1;
+  return resize_voxel_state(e, Z, Y, X);
+}
+
+int vsb_volume_generation(vsb_engine* e, int64_t* gen) {
+  if (!e || !gen) return fail(VSB_ERR_INVALID, "null argument");
+  *gen = e->vol_generation;
   return VSB_OK;
 }
 
@@ -1927,9 +2124,10 @@ int vsb_keys_ipc_export(vsb_engine* e, uint8_t* handle64) {
 
 static void close_peers(vsb_engine* e) {
   for (int r = 0; r < 8; ++r) {
-    if (e->peer_keys[r] && r != e->my_rank) cudaIpcCloseMemHandle(e->peer_keys[r]);
+    if (e->peer_keys[r] && r != e->my_rank && e->peers_ipc) cudaIpcCloseMemHandle(e->peer_keys[r]);
     e->peer_keys[r] = nullptr;
   }
+  e->peers_ipc = false;
   e->n_ranks = 1;
   e->my_rank = 0;
 }
@@ -1943,6 +2141,7 @@ int vsb_peers_open(vsb_engine* e, int32_t n_ranks, int32_t my_rank, const uint8_
   close_peers(e);
   e->n_ranks = n_ranks;
   e->my_rank = my_rank;
+  e->peers_ipc = true;
   for (int r = 0; r < n_ranks; ++r) {
     if (r == my_rank) {
       e->peer_keys[r] = e->d_keys_owned;
@@ -1961,6 +2160,56 @@ int vsb_peers_open(vsb_engine* e, int32_t n_ranks, int32_t my_rank, const uint8_
   return VSB_OK;
 }
 
+// Same-process variant (one host process driving several GPUs, e.g. VolSeg2dPredictor with the
+// additive `cuda_devices` setting): the peers are engine handles of this process, their key volumes are
+// read through ordinary peer access.
+int vsb_peers_attach(vsb_engine* e, int32_t n_ranks, int32_t my_rank, vsb_engine* const* engines) {
+  if (!e || !engines || n_ranks < 1 || n_ranks > 8 || my_rank < 0 || my_rank >= n_ranks || engines[my_rank] != e)
+    return fail(VSB_ERR_INVALID, "bad peer arguments (1..8 engines, engines[my_rank] must be this engine)");
+  if (!e->d_keys_owned || e->d_keys != e->d_keys_owned) return fail(VSB_ERR_STATE, "no volume set / foreign key buffer bound");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  close_peers(e);
+  const int64_t n = e->Z * e->Y * e->X;
+  for (int r = 0; r < n_ranks; ++r) {
+    vsb_engine* q = engines[r];
+    if (!q || !q->d_keys_owned || q->Z * q->Y * q->X != n) return fail(VSB_ERR_STATE, "peer %d holds no volume of this size", r);
+    if (q->device != e->device) {
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, e->device, q->device));
+      if (!can) return fail(VSB_ERR_UNSUPPORTED, "GPU %d cannot access GPU %d", e->device, q->device);
+      const cudaError_t err = cudaDeviceEnablePeerAccess(q->device, 0);
+      if (err == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (err != cudaSuccess)
+        return fail(VSB_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", e->device, q->device, cudaGetErrorString(err));
+    }
+  }
+  e->n_ranks = n_ranks;
+  e->my_rank = my_rank;
+  e->peers_ipc = false;
+  for (int r = 0; r < n_ranks; ++r) e->peer_keys[r] = engines[r]->d_keys_owned;
+  return VSB_OK;
+}
+
+// reduce + unpack this rank's voxel shard (over the attached / opened peers, or alone) and copy it to
+// the host: labels_host / probs_host point at the SHARD's first element.  Synchronises the stream.
+int vsb_fetch_shard(vsb_engine* e, int64_t v_begin, int64_t v_end, uint8_t* labels_host, uint16_t* probs_host) {
+  if (!e || !e->d_keys_owned || !labels_host) return fail(VSB_ERR_STATE, "no volume set / null output");
+  const int64_t n = e->Z * e->Y * e->X, m = v_end - v_begin;
+  if (v_begin < 0 || v_end > n || m < 0 || (v_begin & 1)) return fail(VSB_ERR_INVALID, "bad shard (begin must be even)");
+  if (m == 0) return VSB_OK;
+  CK(cudaSetDevice(e->device));
+  if (!e->d_labels) CK(cudaMalloc(&e->d_labels, align_up(n, 256)));
+  if (probs_host && !e->d_probs) CK(cudaMalloc(&e->d_probs, align_up(n * 2, 256)));
+  int rc = vsb_reduce_unpack_shard(e, v_begin, v_end, e->d_labels, probs_host ? e->d_probs : nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(labels_host, e->d_labels, (size_t)m, cudaMemcpyDeviceToHost, e->stream));
+  if (probs_host) CK(cudaMemcpyAsync(probs_host, e->d_probs, (size_t)m * 2, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  prof_collect(e);
+  return VSB_OK;
+}
+
 int vsb_peers_close(vsb_engine* e) {
   if (!e) return fail(VSB_ERR_INVALID, "null engine");
   CK(cudaSetDevice(e->device));
@@ -1976,6 +2225,8 @@ int vsb_reduce_unpack_shard(vsb_engine* e, int64_t v_begin, int64_t v_end, uint8
     return fail(VSB_ERR_INVALID, "bad shard [%lld, %lld) (begin must be even)", (long long)v_begin, (long long)v_end);
   for (int r = 0; r < e->n_ranks; ++r)
     if (!e->peer_keys[r] && !(e->n_ranks == 1)) return fail(VSB_ERR_STATE, "peer %d not opened", r);
+  if (e->n_ranks > 1 && e->peer_keys[e->my_rank] != e->d_keys_owned)
+    return fail(VSB_ERR_STATE, "peer table is stale (the key volume was re-allocated): re-open the exchange");
   CK(cudaSetDevice(e->device));
   const unsigned long long* ks[8];
   if (e->n_ranks == 1) ks[0] = e->d_keys;

@@ -70,10 +70,16 @@ void launch_merge_injected(const float* probs, const uint8_t* labels, const vsb_
                            unsigned long long* keys, cudaStream_t st);
 void launch_unpack(const unsigned long long* keys, int64_t n, uint8_t* labels, uint16_t* probs,
                    cudaStream_t st);
-void launch_clip_u8(const void* in, int dtype, int64_t n, double mean, double lower, double upper, uint8_t* out,
-                    cudaStream_t st);
 void launch_reduce_unpack(const unsigned long long* const* keys, int n_ranks, int64_t v0, int64_t n, uint8_t* labels,
                           uint16_t* probs, cudaStream_t st);
+// kernels_ingest.cu: typed slicer (datasets.py:129-135 for non-uint8 volumes), moments, clip with counts
+bool slicer_typed_supported(int dtype);
+void launch_slicer_typed(const void* vol, int dtype, const vsb_direction& g, int64_t s0, int nb, uint16_t* out,
+                         cudaStream_t st);
+int moments_partials();  // doubles written per moments launch (2 per block, fixed grid)
+void launch_moments(const void* x, int dtype, int64_t n, int pass, double mean, double* partial, cudaStream_t st);
+void launch_clip_count(const void* in, int dtype, int64_t n, double mean, double lower, double upper, uint8_t* out,
+                       unsigned long long* counts, cudaStream_t st);
 void launch_f32_to_act(const float* in, uint16_t* out, int64_t n, cudaStream_t st);
 void launch_to_f32(const void* in, int is_f32, float* out, int64_t n, cudaStream_t st);
 

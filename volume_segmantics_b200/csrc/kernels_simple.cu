@@ -737,48 +737,6 @@ void launch_unpack(const unsigned long long* keys, int64_t n, uint8_t* labels, u
 }
 
 // ---------------------------------------------------------------------------
-// clip_to_uint8 (base_data_utils.py:243-287), elementwise part: NaN -> mean, clip to
-// [lower, upper], (x - lower) / (upper - lower), clip to [0, 1], * 255, truncate.
-// Same IEEE double operations in the same order as numpy, so the result is bit-exact
-// given the same (mean, lower, upper); the two reductions stay in numpy on the host.
-// dtype: 0 f32, 1 f64, 2 u8, 3 i8, 4 u16, 5 i16, 6 u32, 7 i32, 8 i64.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ double load_as_double(const void* p, int dtype, int64_t i) {
-  switch (dtype) {
-    case 0: return (double)((const float*)p)[i];
-    case 1: return ((const double*)p)[i];
-    case 2: return (double)((const uint8_t*)p)[i];
-    case 3: return (double)((const int8_t*)p)[i];
-    case 4: return (double)((const uint16_t*)p)[i];
-    case 5: return (double)((const int16_t*)p)[i];
-    case 6: return (double)((const uint32_t*)p)[i];
-    case 7: return (double)((const int32_t*)p)[i];
-    default: return (double)((const long long*)p)[i];
-  }
-}
-__global__ void __launch_bounds__(256) clip_u8_kernel(const void* __restrict__ in, int dtype, int64_t n,
-                                                      double mean, double lower, double upper,
-                                                      uint8_t* __restrict__ out) {
-  const double range = upper - lower;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    double x = load_as_double(in, dtype, i);
-    if (x != x) x = mean;                    // np.nan_to_num(nan=data_mean)
-    x = fmin(fmax(x, lower), upper);         // np.clip(data, lower, upper)
-    x = __dsub_rn(x, lower);                 // np.subtract
-    x = __ddiv_rn(x, range);                 // np.divide
-    x = fmin(fmax(x, 0.0), 1.0);             // np.clip(data, 0, 1)
-    x = __dmul_rn(x, 255.0);                 // np.multiply
-    out[i] = (uint8_t)(long long)x;          // astype(np.uint8): truncation
-  }
-}
-void launch_clip_u8(const void* in, int dtype, int64_t n, double mean, double lower, double upper, uint8_t* out,
-                    cudaStream_t st) {
-  const int64_t blocks = (n + 255) / 256;
-  clip_u8_kernel<<<(int)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, st>>>(in, dtype, n, mean, lower, upper, out);
-}
-
-// ---------------------------------------------------------------------------
 // Fused multi-GPU exchange: max-reduce of the packed keys over all ranks + unpack, for
 // the voxel shard [v0, v0 + n) owned by this rank.  keys[r] are the ranks' key volumes
 // (this rank's own buffer and CUDA-IPC mappings of the peers' buffers, read directly

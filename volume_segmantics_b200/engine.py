@@ -13,7 +13,16 @@ import numpy as np
 from . import _lib
 from .plan import B200SegmentationModel, Plan, lower_to_plan
 
+import weakref
+
 ALL_12 = (1 << 12) - 1
+
+
+def weights_version(model) -> tuple:
+    """Cheap fingerprint of a module's parameters and buffers: storage address and torch's
+    in-place version counter of every tensor.  Changes whenever weights are loaded, trained or
+    replaced; never read from `id()` (CPython reuses ids after garbage collection)."""
+    return tuple((k, t.data_ptr(), t._version, tuple(t.shape)) for k, t in model.state_dict(keep_vars=True).items())
 # directions whose image sets duplicate an earlier one (SURVEY.md 3.3)
 DUPLICATE_OF = {3: 1, 6: 4, 9: 7, 10: 0}
 
@@ -30,9 +39,11 @@ class Engine:
         self.h = h
         self.device = int(device)
         self._plan: Optional[Plan] = None
-        self._plan_key = None
+        self._plan_model = None  # weakref to the module whose weights are lowered
+        self._plan_version = None
         self.shape: Optional[Tuple[int, int, int]] = None
         self.classes = 0
+        self.resident = None  # (weakref to the host array whose content is resident, volume generation)
 
     def close(self) -> None:
         if getattr(self, "h", None):
@@ -55,23 +66,111 @@ class Engine:
                                    _ptr(plan.blob), plan.blob.size, plan.classes)
         )
         self._plan = plan
-        self._plan_key = id(model)
+        self._plan_model = weakref.ref(model)
+        self._plan_version = weights_version(model)
         self.classes = plan.classes
         self.shape = None
+        self.resident = None
 
     def ensure_model(self, model: B200SegmentationModel) -> None:
-        if self._plan_key != id(model):
+        """Re-lower unless `model` is the very module that was lowered last AND none of its
+        tensors has been written or re-allocated since (load_state_dict, optimizer steps and
+        any other in-place update bump torch's per-tensor version counter)."""
+        same = self._plan_model is not None and self._plan_model() is model
+        if not same or self._plan_version != weights_version(model):
             self.load_model(model)
 
     # -- volume -------------------------------------------------------------------
+    # dtypes the slicer ingests directly (datasets.py:129-135); codes of include/vsb200.h
+    VOLUME_DTYPES = {"float32": 0, "uint8": 2, "int8": 3, "uint16": 4, "int16": 5, "int32": 7}
+
     def set_volume(self, vol: np.ndarray) -> None:
-        if vol.dtype != np.uint8 or vol.ndim != 3:
-            raise ValueError("set_volume expects a 3-D uint8 array")
+        if vol.ndim != 3:
+            raise ValueError("set_volume expects a 3-D array")
+        code = self.VOLUME_DTYPES.get(vol.dtype.name)
+        if code is None:
+            raise ValueError(f"set_volume: dtype {vol.dtype} is not sliceable; options {sorted(self.VOLUME_DTYPES)}")
         vol = np.ascontiguousarray(vol)
         z, y, x = vol.shape
-        _lib.check(self.lib.vsb_set_volume(self.h, _ptr(vol), 0, z, y, x))
+        if code == 2:
+            _lib.check(self.lib.vsb_set_volume(self.h, _ptr(vol), 0, z, y, x))
+        else:
+            _lib.check(self.lib.vsb_set_volume_typed(self.h, _ptr(vol), code, 0, z, y, x))
         _lib.check(self.lib.vsb_synchronize(self.h))  # host buffer may go away
         self.shape = (z, y, x)
+        self.resident = None
+
+    def volume_generation(self) -> int:
+        g = C.c_int64()
+        _lib.check(self.lib.vsb_volume_generation(self.h, C.byref(g)))
+        return g.value
+
+    def set_volume_shard(self, vol: np.ndarray, v0: int, v1: int) -> None:
+        """Allocate the whole uint8 volume but upload only voxels [v0, v1) (multi-GPU ingest)."""
+        if vol.dtype != np.uint8 or vol.ndim != 3 or not vol.flags.c_contiguous:
+            raise ValueError("set_volume_shard expects a C-contiguous 3-D uint8 array")
+        z, y, x = vol.shape
+        _lib.check(self.lib.vsb_set_volume_shard(self.h, _ptr(vol), z, y, x, v0, v1))
+        self.shape = (z, y, x)
+        self.resident = None
+
+    def volume_pull(self, peer: "Engine", v0: int, v1: int) -> None:
+        _lib.check(self.lib.vsb_volume_pull(self.h, peer.h, v0, v1))
+
+    def attach_peers(self, engines: "list[Engine]", my_rank: int) -> None:
+        arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+        _lib.check(self.lib.vsb_peers_attach(self.h, len(engines), my_rank, arr))
+
+    def fetch_shard(self, v0: int, v1: int, labels: np.ndarray, probs: Optional[np.ndarray]) -> None:
+        """labels / probs: flat C-contiguous host arrays of the WHOLE volume; the shard lands at [v0, v1)."""
+        lp = C.c_void_p(labels.ctypes.data + v0)
+        pp = C.c_void_p(probs.ctypes.data + 2 * v0) if probs is not None else None
+        _lib.check(self.lib.vsb_fetch_shard(self.h, v0, v1, lp, pp))
+
+    # -- BaseDataManager._preprocess_data on the GPU ---------------------------------
+    def raw_upload(self, data: np.ndarray) -> None:
+        data = np.ascontiguousarray(data)
+        code = self.CLIP_DTYPES.get(data.dtype.name)
+        if code is None:
+            raise NotImplementedError(f"dtype {data.dtype} is not supported by the GPU pre-processing")
+        _lib.check(self.lib.vsb_raw_upload(self.h, _ptr(data), code, data.size))
+
+    def raw_moments(self):
+        """-> (count of non-NaN voxels, nanmean, nanstd, count of NaNs) of the uploaded raw volume."""
+        out = (C.c_double * 4)()
+        _lib.check(self.lib.vsb_raw_moments(self.h, out))
+        return int(out[0]), out[1], out[2], int(out[3])
+
+    def raw_clip_to_volume(self, mean: float, lower: float, upper: float, shape, want_host: bool = True):
+        """Clip / rescale / quantise the raw volume; the uint8 result becomes the engine's resident
+        volume and (want_host) is returned as a read-only ndarray carrying a residency token."""
+        z, y, x = shape
+        out = self._host_buffer((z, y, x), np.uint8) if want_host else None
+        cnt = (C.c_uint64 * 2)()
+        _lib.check(self.lib.vsb_raw_clip_to_volume(self.h, float(mean), float(lower), float(upper), z, y, x,
+                                                   _ptr(out) if want_host else None, cnt))
+        self.shape = (z, y, x)
+        self.resident = None
+        if want_host:
+            out.setflags(write=False)
+            self.resident = (weakref.ref(out), self.volume_generation())
+        return out, int(cnt[0]), int(cnt[1])
+
+    def raw_release(self) -> None:
+        _lib.check(self.lib.vsb_raw_release(self.h))
+
+    def holds(self, vol: np.ndarray) -> bool:
+        """True when `vol` is the (read-only) array a previous raw_clip_to_volume returned and the
+        engine's resident volume has not changed since: no second upload is needed."""
+        if self.resident is None:
+            return False
+        ref, gen = self.resident
+        return ref() is vol and not vol.flags.writeable and gen == self.volume_generation()
+
+    def reset_for(self, shape) -> None:
+        """New prediction on the resident volume (keys zeroed)."""
+        self.shape = tuple(shape)
+        self.reset()
 
     def set_volume_device(self, dev_ptr: int, shape: Tuple[int, int, int]) -> None:
         z, y, x = shape
@@ -102,6 +201,7 @@ class Engine:
         import torch
 
         tdt = {np.uint8: torch.uint8, np.float16: torch.float16}[dtype]
+        shape = tuple(int(v) for v in shape)
         pool = self.__dict__.setdefault("_pinned_pool", [])
         for entry in pool:
             tensor, ref = entry
@@ -199,10 +299,11 @@ class Engine:
         z, y, x = self.shape
         return _lib.direction_geometry(z, y, x, d)
 
-    def slice_batch(self, d: int, s0: int, nb: int) -> np.ndarray:
+    def slice_batch(self, d: int, s0: int, nb: int, generic: bool = False) -> np.ndarray:
         g = self.geometry(d)
         out = np.empty((nb, g.Hp, g.Wp), np.uint16)
-        _lib.check(self.lib.vsb_slice_batch(self.h, d, s0, nb, _ptr(out)))
+        fn = self.lib.vsb_slice_batch_generic if generic else self.lib.vsb_slice_batch
+        _lib.check(fn(self.h, d, s0, nb, _ptr(out)))
         return out
 
     def merge_injected(self, d: int, probs: np.ndarray, labels: np.ndarray) -> None:

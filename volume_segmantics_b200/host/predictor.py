@@ -24,27 +24,29 @@ DIRS_3 = 0b111
 DIRS_12 = (1 << 12) - 1
 
 
-def _as_uint8_volume(data_vol: np.ndarray) -> np.ndarray:
-    """The reference divides any integer slice by 255 and feeds floats as they
-    are (datasets.py:129-135).  The engine ingests uint8 (what clip_to_uint8
-    produces, base_data_utils.py:243-287); integer volumes already inside
-    0..255 convert losslessly, anything else is refused loudly."""
+def _as_engine_volume(data_vol: np.ndarray) -> np.ndarray:
+    """The reference slices whatever array it is given: integer slices of ANY bit depth are cast to
+    float32 and divided by 255, float32 slices are fed as they are (datasets.py:129-135).  The engine's
+    slicer does the same for uint8 / int8 / uint16 / int16 / int32 / float32 volumes.  Wider integers
+    are narrowed to int32 when their values fit (cv2.copyMakeBorder, which pads the reference's slices,
+    converts int64 to int32 itself).  float64 / float16 volumes fail in the reference as well -- the
+    network receives a double / half batch for float32 weights (vol_seg_2d_predictor.py:44) -- and are
+    refused here with the remedy."""
     vol = np.asarray(data_vol)
     if vol.ndim != 3:
         raise ValueError(f"expected a 3-D volume, got shape {vol.shape}")
-    if vol.dtype == np.uint8:
-        return np.ascontiguousarray(vol)
-    if np.issubdtype(vol.dtype, np.integer) or vol.dtype == np.bool_:
+    if vol.dtype.name in Engine.VOLUME_DTYPES:
+        return vol if vol.flags.c_contiguous else np.ascontiguousarray(vol)
+    if np.issubdtype(vol.dtype, np.integer):
         lo, hi = int(vol.min()), int(vol.max())
-        if lo >= 0 and hi <= 255:
-            return np.ascontiguousarray(vol.astype(np.uint8))
-        raise NotImplementedError(
-            f"integer volume with range [{lo}, {hi}] outside 0..255: enable clip_data "
-            "(the B200 slicer ingests uint8 volumes only)"
-        )
-    raise NotImplementedError(
-        f"volume dtype {vol.dtype} is not supported by the B200 slicer: enable clip_data so "
-        "the data is rescaled to uint8 first (reference default, 2d_model_predict_settings.yaml:4)"
+        if lo >= -(2**31) and hi < 2**31:
+            return np.ascontiguousarray(vol.astype(np.int32))
+        raise ValueError(f"integer volume with range [{lo}, {hi}] does not fit int32 (cv2 pads int32 at most)")
+    if vol.dtype == np.bool_:
+        return np.ascontiguousarray(vol.astype(np.uint8))
+    raise TypeError(
+        f"volume dtype {vol.dtype}: the reference feeds float volumes to the float32 network unchanged, which only "
+        "works for float32; convert the volume to float32 or enable clip_data (2d_model_predict_settings.yaml:4)"
     )
 
 
@@ -60,6 +62,10 @@ class VolSeg2dPredictor:
             self.model_file_path, True, self.model_device_num
         )
         self._engine = None
+        # additive setting (absent => the reference's single device): several GPUs of this host
+        devices = getattr(settings, "cuda_devices", None)
+        self._devices = [int(d) for d in devices] if devices and len(list(devices)) > 1 else None
+        self._group = None
 
     # -- engine plumbing -------------------------------------------------------
     @property
@@ -75,17 +81,38 @@ class VolSeg2dPredictor:
                 "cannot run on the B200 engine and there is no PyTorch fallback"
             )
         self.model._engine = self.engine
-        self.engine.ensure_model(self.model)  # re-lowers if .model was replaced
-        vol = _as_uint8_volume(data_vol)
+        # re-lowers when .model was replaced or its weights changed since they were lowered
+        self.engine.ensure_model(self.model)
         self.engine.set_vote_mode(False)
+        if isinstance(data_vol, np.ndarray) and self.engine.holds(data_vol):
+            # the array BaseDataManager's GPU pre-processing returned: its content is already resident
+            self.engine.reset_for(data_vol.shape)
+            return data_vol
+        vol = _as_engine_volume(data_vol)
         self.engine.set_volume(vol)
         return vol
 
     def _get_model_from_trainer(self, trainer):
-        # :28-29 ; weights are re-folded on the next prediction
+        # :28-29 ; the new module's weights are folded on the next prediction
         self.model = trainer.model
+        if self._engine is not None:
+            self._engine._plan_model = None
+
+    @property
+    def group(self):
+        if self._group is None:
+            from ..multi import LocalGroup
+
+            self._group = LocalGroup(self._devices)
+        return self._group
 
     def _run(self, data_vol, dir_mask: int, output_probs: bool = True):
+        if self._devices is not None:
+            vol = _as_engine_volume(data_vol)
+            if vol.dtype == np.uint8:
+                if not isinstance(self.model, B200SegmentationModel):
+                    raise TypeError("VolSeg2dPredictor.model must be a B200SegmentationModel")
+                return self.group.predict(self.model, vol, dir_mask, want_probs=output_probs)
         self._prepare(data_vol)
         self.engine.predict(dir_mask, skip_duplicates=True)
         return self.engine.fetch(want_probs=output_probs)

@@ -45,6 +45,10 @@ class B200SegmentationModel(nn.Module):
     def __init__(self, model_type_name: str, encoder_name: str, classes: int, in_channels: int = 1,
                  **_ignored):
         super().__init__()
+        if int(in_channels) != 1:
+            # the slicer writes ONE channel per voxel (vol_seg_2d_trainer.py:55 always builds in_channels=1);
+            # a wider first convolution would read channels nobody wrote
+            raise NotImplementedError(f"in_channels={in_channels}: the B200 engine slices single-channel volumes only")
         self.spec: NetSpec = build_netspec(model_type_name, encoder_name, classes, in_channels)
         self.model_type_name = model_type_name
         self.classes = classes
