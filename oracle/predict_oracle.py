@@ -166,6 +166,21 @@ class OraclePredictor:
             merge_vols_in_mem(prob_c, label_c)
         return label_c[0], prob_c[0]
 
+    # -- margin of a merged decision (test helper, not in the reference) ---------------
+    def class_best_over_directions(self, data_vol, dirs):
+        """[C,Z,Y,X] fp32: for every class the largest softmax probability any of the listed
+        directions assigns to it at a voxel.  The top-2 gap of this array is the reference's
+        margin between the label that wins the max-probability merge (:90-98) and the best
+        competing label -- the quantity BASELINE.json's "every disagreement at a voxel whose
+        reference top-2 margin is below tolerance" refers to for 3-way / 12-way results."""
+        out = None
+        for d in dirs:
+            sl = np.ascontiguousarray(direction_slices(data_vol, d))
+            _, _, full = self.predict_single_axis(sl, True, AXIS_Z, return_full=True)  # [S,C,H,W]
+            vol_c = np.stack([direction_to_volume(full[:, c], d) for c in range(full.shape[1])])
+            out = vol_c if out is None else np.maximum(out, vol_c)
+        return out
+
     # -- :118-136 one-hot vote variants ------------------------------------------
     def predict_single_axis_to_one_hot(self, data_vol, axis=AXIS_Z):
         pred, _ = self.predict_single_axis(data_vol, axis=axis)

@@ -86,6 +86,11 @@ def test_s2d_head_against_oracle_three_axes(engine, unet_r34):
     engine.set_volume(vol)
     engine.predict(0b111, True)
     labels, probs = engine.fetch()
-    want_l, want_p = po.OraclePredictor(oracle, 4).predict_3_ways_max_probs(vol)
+    ora = po.OraclePredictor(oracle, 4)
+    want_l, want_p = ora.predict_3_ways_max_probs(vol)
     assert np.abs(probs.astype(np.float32) - want_p.astype(np.float32)).max() < 2e-2
-    assert (labels == want_l).mean() > 0.98
+    bad = labels != want_l
+    cb = np.sort(ora.class_best_over_directions(vol, range(3)), axis=0)
+    assert not bad.any() or (cb[-1] - cb[-2])[bad].max() < 2e-2  # margin clause
+    print(f"[s2d head vs oracle] agreement {1 - bad.mean():.5f}")
+    assert 1 - bad.mean() > 0.997  # random-init weights (near-ties everywhere): see tests/test_predictor_gpu.py

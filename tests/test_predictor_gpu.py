@@ -9,8 +9,15 @@ Two weight sets are used:
     against the oracle run on the same in-memory weights; the 99.9 % bar applies.
   * "random-init" golden vectors (tests/golden/e2e_unet_r34.npz): softmax within
     0.004 of uniform, i.e. every voxel is on a decision boundary (reference margin
-    < 2e-2 everywhere); probability tolerance and the margin clause apply, the
-    agreement floor is 99 % and the measured value is printed.
+    < 2e-2 everywhere).  Probability tolerance and the margin clause apply in full.
+    The agreement measures the rounding noise of the 16-bit activation chain (logit
+    error about 1e-4 on logits of magnitude 0.07): measured 99.87 % single axis,
+    99.83 % 3-way, 99.79 % 12-way (profiles/r01_gpu_tests_v4.log) -- BELOW the 99.9 %
+    north_star asks for, and stated as such in DESIGN.md; RANDOM_INIT_FLOOR only keeps
+    it from regressing.
+For 3-way and 12-way results the margin clause uses the reference's margin between the
+winning label and the best competing label over all merged directions
+(OraclePredictor.class_best_over_directions).
 Plus the dtype / shape contract of the reference's own GPU tests
 (tests/test_vol_seg_2d_predictor.py:14-81, test_vol_seg_prediction_manager.py)."""
 from pathlib import Path
@@ -26,6 +33,8 @@ from oracle.make_golden import structured_volume
 pytestmark = pytest.mark.gpu
 
 PROB_TOL = 2e-2
+TRAINED_FLOOR = 0.999      # north_star
+RANDOM_INIT_FLOOR = 0.997  # every voxel a near-tie: see the module docstring
 SETTINGS = dict(quality="medium", output_probs=False, clip_data=False, st_dev_factor=2.575,
                 data_hdf5_path="/data", cuda_device=0, downsample=False, one_hot=False, prediction_axis="Z")
 
@@ -96,23 +105,29 @@ def test_trained_single_axis(trained, axis_name):
     want_l, want_p, full = oracle.predict_single_axis(vol, True, axis.value, return_full=True)
     top2 = np.sort(full, axis=1)[:, -2:]
     margin = po.rotate_array_to_axis(top2[:, 1] - top2[:, 0], axis.value)
-    _check(f"trained {axis_name}", labels, probs, np.ascontiguousarray(want_l), np.ascontiguousarray(want_p), 0.999, margin)
+    _check(f"trained {axis_name}", labels, probs, np.ascontiguousarray(want_l), np.ascontiguousarray(want_p),
+           TRAINED_FLOOR, margin)
     labels2, none = pred._predict_single_axis(vol, output_probs=False, axis=axis)
     assert none is None and np.array_equal(labels2, labels)
+
+
+def _merged_margin(oracle, vol, dirs):
+    cb = np.sort(oracle.class_best_over_directions(vol, dirs), axis=0)
+    return cb[-1] - cb[-2]
 
 
 def test_trained_three_ways(trained):
     pred, oracle, vol = trained
     labels, probs = pred._predict_3_ways_max_probs(vol)
     want_l, want_p = oracle.predict_3_ways_max_probs(vol)
-    _check("trained 3-way", labels, probs, want_l, want_p, 0.999)
+    _check("trained 3-way", labels, probs, want_l, want_p, TRAINED_FLOOR, _merged_margin(oracle, vol, range(3)))
 
 
 def test_trained_twelve_ways_and_one_hot(trained):
     pred, oracle, vol = trained
     labels, probs = pred._predict_12_ways_max_probs(vol)
     want_l, want_p = oracle.predict_12_ways_max_probs(vol)
-    _check("trained 12-way", labels, probs, want_l, want_p, 0.999)
+    _check("trained 12-way", labels, probs, want_l, want_p, TRAINED_FLOOR, _merged_margin(oracle, vol, range(12)))
     votes = pred._predict_12_ways_one_hot(vol)
     want = oracle.predict_12_ways_one_hot(vol)
     assert votes.dtype == np.uint8 and votes.ndim == 4 and votes.shape == want.shape
@@ -129,14 +144,18 @@ def test_golden_single_axis(predictor, golden):
     full = golden["full_probs_d1"]  # [S,C,H,W] slice space of direction 1 = (Y; Z, X)
     top2 = np.sort(full, axis=1)[:, -2:]
     margin = (top2[:, 1] - top2[:, 0]).swapaxes(0, 1)
-    _check("random-init Y", labels, probs, golden["low_y_labels"], golden["low_y_probs"], 0.99, margin)
+    _check("random-init Y", labels, probs, golden["low_y_labels"], golden["low_y_probs"], RANDOM_INIT_FLOOR, margin)
 
 
-def test_golden_three_and_twelve_ways(predictor, golden):
-    labels, probs = predictor._predict_3_ways_max_probs(golden["volume"])
-    _check("random-init 3-way", labels, probs, golden["medium_labels"], golden["medium_probs"], 0.99)
-    labels, probs = predictor._predict_12_ways_max_probs(golden["volume"])
-    _check("random-init 12-way", labels, probs, golden["high_labels"], golden["high_probs"], 0.99)
+def test_golden_three_and_twelve_ways(predictor, golden, unet_r34):
+    oracle = po.OraclePredictor(unet_r34[0], 4)  # the weights the golden file was generated from
+    vol = golden["volume"]
+    labels, probs = predictor._predict_3_ways_max_probs(vol)
+    _check("random-init 3-way", labels, probs, golden["medium_labels"], golden["medium_probs"], RANDOM_INIT_FLOOR,
+           _merged_margin(oracle, vol, range(3)))
+    labels, probs = predictor._predict_12_ways_max_probs(vol)
+    _check("random-init 12-way", labels, probs, golden["high_labels"], golden["high_probs"], RANDOM_INIT_FLOOR,
+           _merged_margin(oracle, vol, range(12)))
 
 
 def test_manager_quality_dispatch(model_path, golden):
@@ -146,12 +165,12 @@ def test_manager_quality_dispatch(model_path, golden):
     mgr = VolSeg2DPredictionManager(str(model_path), golden["volume"].astype(np.int64), SimpleNamespace(**SETTINGS))
     out = mgr.predict_volume_to_path(None, Quality.MEDIUM)
     assert out.shape == golden["volume"].shape and out.dtype == np.uint8
-    assert (out == golden["medium_labels"]).mean() >= 0.99
+    assert (out == golden["medium_labels"]).mean() >= RANDOM_INIT_FLOOR
     s = dict(SETTINGS, prediction_axis="y")
     mgr = VolSeg2DPredictionManager(str(model_path), golden["volume"], SimpleNamespace(**s))
     out = mgr.predict_volume_to_path(None, Quality.LOW)
     assert out.shape == golden["volume"].shape  # reference tests/test_vol_seg_prediction_manager.py:40-64
-    assert (out == golden["low_y_labels"]).mean() >= 0.99
+    assert (out == golden["low_y_labels"]).mean() >= RANDOM_INIT_FLOOR
     one_hot = VolSeg2DPredictionManager(str(model_path), golden["volume"], SimpleNamespace(**dict(SETTINGS, one_hot=True)))
     votes = one_hot.predict_volume_to_path(None, Quality.LOW)
     assert votes.dtype == np.uint8 and votes.ndim == 4 and (votes.sum(0) == 1).all()
@@ -190,8 +209,44 @@ def test_kernel_variants_agree(engine, unet_r34, golden):
     assert dp < 2e-3 and (results["default"][0] == results["pertap"][0]).mean() > 0.99
 
 
-def test_non_uint8_volumes_are_refused_loudly(predictor):
-    with pytest.raises(NotImplementedError):
+def test_unsliceable_dtypes_are_refused_with_the_remedy(predictor):
+    """float64 / float16 volumes fail in the reference too (double batch into float32 weights)."""
+    with pytest.raises(TypeError, match="float32"):
         predictor._predict_single_axis(np.random.rand(8, 32, 32))
-    with pytest.raises(NotImplementedError):
-        predictor._predict_single_axis(np.full((8, 32, 32), 1000, np.int32))
+    with pytest.raises(ValueError, match="int32"):
+        predictor._predict_single_axis(np.full((8, 32, 32), 2**40, np.int64))
+
+
+def test_two_checkpoints_one_engine(tmp_path, unet_r34, trained_unet_r34, golden):
+    """a second predictor on the same engine, and weights changed in place, must never
+    run the previous plan (the plan key is the module object + a per-tensor version fingerprint)."""
+    from volume_segmantics.model.operations.vol_seg_2d_predictor import VolSeg2dPredictor
+
+    vol = golden["volume"]
+    pa = VolSeg2dPredictor(str(_save(unet_r34[0], tmp_path / "a.pytorch")), SimpleNamespace(**SETTINGS))
+    pb = VolSeg2dPredictor(str(_save(trained_unet_r34[0], tmp_path / "b.pytorch")), SimpleNamespace(**SETTINGS))
+    la, _ = pa._predict_single_axis(vol)
+    lb, _ = pb._predict_single_axis(vol)
+    la2, _ = pa._predict_single_axis(vol)
+    assert np.array_equal(la, la2) and not np.array_equal(la, lb)
+    pa.model.load_state_dict(trained_unet_r34[0].state_dict())  # in place, same module object
+    la3, _ = pa._predict_single_axis(vol)
+    assert np.array_equal(la3, lb)
+
+
+def test_one_hot_class_count_change_on_one_shape(engine, golden):
+    """the vote volume is sized by the class count of the loaded plan."""
+    from volume_segmantics_b200.plan import B200SegmentationModel
+
+    vol = golden["volume"]
+    for classes in (2, 6, 3):
+        torch.manual_seed(classes)
+        model = B200SegmentationModel("U_NET", "resnet34", classes)
+        engine.load_model(model)
+        engine.set_volume(vol)
+        engine.set_vote_mode(True)
+        engine.reset()
+        engine.predict(0b111, skip_duplicates=False)
+        votes = engine.fetch_votes()
+        engine.set_vote_mode(False)
+        assert votes.shape == (classes,) + vol.shape and (votes.sum(0) == 3).all()

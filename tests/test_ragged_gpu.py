@@ -45,9 +45,15 @@ def test_three_ways_on_ragged_shapes(pair, shape):
     assert labels.shape == shape and labels.dtype == np.uint8 and probs.dtype == np.float16
     perr = np.abs(probs.astype(np.float32) - want_p.astype(np.float32)).max()
     agree = (labels == want_l).mean()
-    print(f"[ragged {shape}] agreement {agree:.5f} max prob err {perr:.5f}")
+    cb = np.sort(oracle.class_best_over_directions(vol, range(3)), axis=0)
+    margin = cb[-1] - cb[-2]
+    bad = labels != want_l
+    worst = margin[bad].max() if bad.any() else 0.0
+    print(f"[ragged {shape}] agreement {agree:.5f} max prob err {perr:.5f} largest margin at a disagreement {worst:.5f}")
     assert perr < PROB_TOL
-    assert agree >= 0.995  # tiny volumes: a handful of boundary voxels weigh more than at scale
+    assert worst < PROB_TOL  # the margin clause of BASELINE.json
+    # volumes of a few thousand voxels: one flipped near-tie voxel is already 0.03 %
+    assert agree >= (0.999 if vol.size >= 20000 else 0.995)
 
 
 def test_single_axis_each_direction_on_a_ragged_shape(pair):
@@ -61,12 +67,16 @@ def test_single_axis_each_direction_on_a_ragged_shape(pair):
         eng.predict(1 << d, skip_duplicates=False)
         lab, prb = eng.fetch()
         sl = np.ascontiguousarray(po.direction_slices(vol, d))
-        l_s, p_s = oracle.predict_single_axis(sl, True, po.AXIS_Z)  # slice space of direction d
+        l_s, p_s, full = oracle.predict_single_axis(sl, True, po.AXIS_Z, return_full=True)  # slice space of direction d
         want_l = po.direction_to_volume(l_s, d)
         want_p = po.direction_to_volume(p_s, d)
+        top2 = np.sort(full, axis=1)[:, -2:]
+        margin = po.direction_to_volume(top2[:, 1] - top2[:, 0], d)
         perr = np.abs(prb.astype(np.float32) - want_p.astype(np.float32)).max()
+        bad = lab != want_l
         assert perr < PROB_TOL, f"direction {d}: prob error {perr}"
-        assert (lab == want_l).mean() >= 0.99, f"direction {d}"
+        assert not bad.any() or margin[bad].max() < PROB_TOL, f"direction {d}: disagreement outside the margin"
+        assert 1 - bad.mean() >= 0.999, f"direction {d}: agreement {1 - bad.mean():.5f}"
 
 
 def test_one_hot_votes_all_qualities(pair):
