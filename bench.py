@@ -1,37 +1,42 @@
 #!/usr/bin/env python
 """Benchmark of the prediction hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg1..cfg5]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Metric: voxels/sec of a 12-direction ('high' quality) U-Net/ResNet-34, 4-class
-prediction of a synthetic 1024^3 uint8 volume (BASELINE.json configs[2], the
-configuration the metric is quoted on; it fits one B200).  One "step" = one
-full prediction of the volume.  The same volume is sharded over N GPUs
-(strong scaling): work items = (direction, slice range), one NCCL max-reduce of
-the packed keys, rank 0 unpacks.
+Default workload = BASELINE.json configs[2] ("cfg3"), the configuration the metric is quoted on:
+12-direction ('high' quality) U-Net/ResNet-34, 4 classes, synthetic 1024^3 uint8 volume (fits one B200).
+--config selects the other BASELINE configurations (architecture, classes, quality, shape):
+  cfg1 U-Net/R34 low C=2 256^3 | cfg2 U-Net/R34 medium C=4 512^3 | cfg4 U-Net++/ResNeXt-50 high C=6 512^3 |
+  cfg5 DeepLabV3+/R50 medium C=4 (2048,2048,512).
+One "step" = one full prediction of the volume.  The same volume is sharded over N GPUs (strong
+scaling): work items = (direction, slice range), one exchange of the packed keys.
 
-  value : volume already resident in HBM -> label + fp16 probability volumes in
-          HBM (CUDA events on the engine's stream, max over ranks).
-  e2e   : VolSeg2dPredictor._predict_12_ways_max_probs(host ndarray) -> host
-          ndarrays; pinned H2D of the volume and D2H of labels + probs inside
-          the timed region (N = 1: through the reference-facing API itself).
-  roofline : the tcgen05 convolution kernel; achieved = algorithmic conv FLOPs
-          of the launches / their summed CUDA-event durations.
-  cpu_baseline : the CPU oracle (restatement of the reference path) on a bounded
-          sample, extrapolated; a reported baseline, not a target.
+  value : volume already resident in HBM -> label + fp16 probability volumes in HBM (CUDA events on
+          the engine's stream, max over ranks).
+  e2e   : host ndarray -> host ndarrays, copies inside the timed region.  N = 1: the reference-facing call
+          itself, VolSeg2dPredictor(model file)._predict_*(ndarray).  N > 1 (one process per GPU): every
+          rank uploads 1/N of the volume from pinned memory, the parts are all-gathered over NVLink, and
+          every rank downloads ITS shard of labels + probabilities into one shared page-locked result.
+  roofline : the tcgen05 convolution class (achieved = algorithmic conv FLOPs / summed CUDA-event
+          durations of its launches); `roofline_classes` adds the HBM-bound classes (slicer, stem + pool,
+          head + merge) the same way.
+  cpu_baseline : the CPU oracle (restatement of the reference path) on a bounded sample, extrapolated
+          (cfg1: timed in full); a reported baseline, not a target.
+  result_sha256 : SHA-256 of the label + probability volumes of the e2e leg (identical at every N).
 
---impl reference runs ONLY the CPU oracle port (the reference itself cannot be
-imported in this image: h5py / segmentation_models_pytorch / albumentations are
-absent) with all host threads on the same config.
+--impl reference runs ONLY the CPU oracle port (the reference itself cannot be imported in this image:
+h5py / segmentation_models_pytorch / albumentations are absent) with all host threads.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import time
 from pathlib import Path
 
@@ -40,25 +45,62 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-ARCH, ENCODER, CLASSES = "U_NET", "resnet34", 4
-DIR_MASK = (1 << 12) - 1
-METRIC = "voxels/sec, 12-direction U-Net prediction of a 1024^3 volume"
+# BASELINE.json `configs`, in order (cfg3 = the one the metric is quoted on)
+CONFIGS = {
+    "cfg1": dict(arch="U_NET", oracle_arch="unet", encoder="resnet34", classes=2, quality="low", shape=(256, 256, 256),
+                 name="U-Net/ResNet-34, low quality (1 direction), 2 classes, synthetic 256^3 uint8 volume"),
+    "cfg2": dict(arch="U_NET", oracle_arch="unet", encoder="resnet34", classes=4, quality="medium", shape=(512, 512, 512),
+                 name="U-Net/ResNet-34, medium quality (3 directions), 4 classes, synthetic 512^3 uint8 volume"),
+    "cfg3": dict(arch="U_NET", oracle_arch="unet", encoder="resnet34", classes=4, quality="high", shape=(1024, 1024, 1024),
+                 name="U-Net/ResNet-34, high quality (12 directions), 4 classes, synthetic 1024^3 uint8 volume"),
+    "cfg4": dict(arch="U_NET_PLUS_PLUS", oracle_arch="unetplusplus", encoder="resnext50_32x4d", classes=6, quality="high",
+                 shape=(512, 512, 512),
+                 name="U-Net++/ResNeXt-50_32x4d, high quality (12 directions), 6 classes, synthetic 512^3 uint8 volume"),
+    "cfg5": dict(arch="DEEPLABV3_PLUS", oracle_arch="deeplabv3plus", encoder="resnet50", classes=4, quality="medium",
+                 shape=(2048, 2048, 512),
+                 name="DeepLabV3+/ResNet-50, medium quality (3 directions), 4 classes, synthetic (2048,2048,512) uint8 volume"),
+}
+QUALITY_MASK = {"low": 0b001, "medium": 0b111, "high": (1 << 12) - 1}
+QUALITY_DIRS = {"low": 1, "medium": 3, "high": 12}
+METRIC_CFG3 = "voxels/sec, 12-direction U-Net prediction of a 1024^3 volume"
 
 
 def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
-def synth_volume(size):
+def resolve_config(args):
+    cfg = dict(CONFIGS[args.config])
+    if args.size:  # development aid: a smaller cube of the same configuration
+        cfg["shape"] = (args.size,) * 3
+        cfg["name"] = cfg["name"].split(", synthetic")[0] + f", synthetic {args.size}^3 uint8 volume"
+    cfg["key"] = args.config
+    cfg["dir_mask"] = QUALITY_MASK[cfg["quality"]]
+    cfg["n_dirs"] = QUALITY_DIRS[cfg["quality"]]
+    if args.config == "cfg3" and not args.size:
+        cfg["metric"] = METRIC_CFG3
+    else:
+        z, y, x = cfg["shape"]
+        cfg["metric"] = f"voxels/sec, {cfg['n_dirs']}-direction {cfg['name'].split(',')[0]} prediction of a {z}x{y}x{x} volume"
+    return cfg
+
+
+def config_dict(cfg):
+    """Identical for both arms (the driver compares them textually)."""
+    return {"workload": cfg["name"], "baseline_config": cfg["key"],
+            "weights": "random init of the named architecture (seed 0), BN statistics randomised"}
+
+
+def synth_volume(shape):
     # SURVEY.md 8d: integers(0, 256) uint8 volume, fixed seed
-    return np.random.default_rng(20240).integers(0, 256, size=(size, size, size), dtype=np.uint8)
+    return np.random.default_rng(20240).integers(0, 256, size=shape, dtype=np.uint8)
 
 
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, sustained bf16)"
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json: sustained bf16, HBM copy)"
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
@@ -99,55 +141,94 @@ class ClockSampler:
         return out
 
 
+def make_models(cfg, want_oracle=False):
+    """Random init of the named architecture with randomised BN statistics."""
+    import torch
+
+    from volume_segmantics_b200.plan import B200SegmentationModel
+
+    torch.manual_seed(0)
+    model = B200SegmentationModel(cfg["arch"], cfg["encoder"], cfg["classes"])
+    g = torch.Generator().manual_seed(1)
+    sd = model.state_dict()
+    for key, (shape, (role, _)) in model.spec.param_shapes().items():
+        if role in ("bn_w", "bn_var"):
+            sd[key].copy_(torch.rand(shape, generator=g) + 0.5)
+        elif role in ("bn_b", "bn_mean"):
+            sd[key].copy_(torch.randn(shape, generator=g) * 0.1)
+    return model
+
+
 # ----------------------------------------------------------------------------- CPU oracle leg
-def cpu_oracle_sample(size, slices, threads):
-    """Time the oracle on `slices` Z-slices of a size^2 image + one merge sample;
-    extrapolate to the full 12-direction prediction.  Returns (voxels/s, detail)."""
+def cpu_oracle_sample(cfg, threads, per_axis):
+    """Time the oracle (a) in full for cfg1, else (b) on `per_axis` slices of every AXIS orientation
+    the configuration slices along (strided views included, as the reference gathers them) + one merge
+    sample, extrapolated linearly.  Returns (voxels/s, sample description)."""
     import torch
 
     from oracle import predict_oracle as po
     from oracle.smp_models import make_random_model
 
     torch.set_num_threads(threads)
-    model = make_random_model("unet", ENCODER, CLASSES, seed=0)
-    pred = po.OraclePredictor(model, CLASSES, batch_size=4)
-    vol = np.random.default_rng(1).integers(0, 256, size=(slices, size, size), dtype=np.uint8)
-    t0 = time.perf_counter()
-    pred.predict_single_axis(vol, True, po.AXIS_Z)
-    t_slice = (time.perf_counter() - t0) / slices
-    mz = max(1, min(size, (32 << 20) // (size * size)))
-    pc = np.random.default_rng(2).random((2, mz, size, size)).astype(np.float16)
-    lc = np.zeros((2, mz, size, size), np.uint8)
-    t0 = time.perf_counter()
-    po.merge_vols_in_mem(pc, lc)
-    t_merge_vox = (time.perf_counter() - t0) / (mz * size * size)
-    nvox = size ** 3
-    total = 12 * size * t_slice + 11 * nvox * t_merge_vox
-    return nvox / total, {"s_per_slice": t_slice, "s_per_merge_voxel": t_merge_vox}
+    model = make_random_model(cfg["oracle_arch"], cfg["encoder"], cfg["classes"], seed=0)
+    pred = po.OraclePredictor(model, cfg["classes"], batch_size=4)
+    Z, Y, X = cfg["shape"]
+    nvox = Z * Y * X
+    if cfg["key"] == "cfg1" and nvox <= 256 ** 3:
+        vol = synth_volume(cfg["shape"])
+        t0 = time.perf_counter()
+        pred.predict_single_axis(vol, True, po.AXIS_Z)
+        dt = time.perf_counter() - t0
+        return nvox / dt, f"the whole {Z}x{Y}x{X} volume, single axis, batch 4 (timed in full: {dt:.1f} s)"
+    rng = np.random.default_rng(1)
+    axes = (0,) if cfg["quality"] == "low" else (0, 1, 2)
+    total, parts = 0.0, []
+    for a in axes:
+        # a slab thick enough for `per_axis` slices along axis a, full size in the slice plane
+        shp = [Z, Y, X]
+        shp[a] = per_axis
+        slab = rng.integers(0, 256, size=shp, dtype=np.uint8)
+        t0 = time.perf_counter()
+        pred.predict_single_axis(slab, True, a)
+        t_slice = (time.perf_counter() - t0) / per_axis
+        n_slices = (Z, Y, X)[a] * (cfg["n_dirs"] // len(axes))  # rot90 variants slice the same planes (transposed)
+        total += n_slices * t_slice
+        parts.append(f"axis {'ZYX'[a]} {t_slice:.3f} s/slice")
+    n_merges = cfg["n_dirs"] - 1
+    t_merge_vox = 0.0
+    if n_merges:
+        mz = max(1, min(Z, (32 << 20) // (Y * X)))
+        pc = rng.random((2, mz, Y, X)).astype(np.float16)
+        lc = np.zeros((2, mz, Y, X), np.uint8)
+        t0 = time.perf_counter()
+        po.merge_vols_in_mem(pc, lc)
+        t_merge_vox = (time.perf_counter() - t0) / (mz * Y * X)
+        total += n_merges * nvox * t_merge_vox
+    sample = (f"{per_axis} slices per axis orientation ({', '.join(parts)}) through the fp32 CPU oracle (batch 4) + one "
+              f"fp16 merge sample ({t_merge_vox * 1e9:.1f} ns/voxel), extrapolated linearly to {cfg['n_dirs']} directions "
+              f"+ {n_merges} merges")
+    return nvox / total, sample
 
 
-def run_reference(args):
-    rank = env_int("RANK", 0)
-    if rank != 0:
+def run_reference(args, cfg):
+    if env_int("RANK", 0) != 0:
         return
     threads = os.cpu_count() or 1
-    size = args.size
-    slices = 4
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, _ = cpu_oracle_sample(size, slices, threads)
-        if i >= args.warmup:
+    vals, sample = [], ""
+    warm, steps = args.warmup, args.steps
+    if cfg["key"] == "cfg1":  # timed in full (tens of seconds per step): bound the run
+        warm, steps = min(warm, 1), min(steps, 3)
+    for i in range(warm + steps):
+        v, sample = cpu_oracle_sample(cfg, threads, 2)
+        if i >= warm:
             vals.append(v)
     value = float(np.mean(vals))
-    sample = (f"{slices} Z-slices of {size}x{size} through the fp32 CPU oracle (batch 4) + one "
-              f"(2,{max(1, min(size, (32 << 20) // (size * size)))},{size},{size}) fp16 merge per step, "
-              f"extrapolated linearly to 12 directions x {size} slices + 11 merges")
+    nvox = int(np.prod(cfg["shape"]))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * size ** 3 / value,
+        "impl": "reference", "metric": cfg["metric"], "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * nvox / value,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": f"U-Net/ResNet-34, high quality (12 directions), {CLASSES} classes, synthetic {size}^3 uint8 volume",
-                   "weights": "random init (seed 0), BN statistics randomised"},
+        "config": config_dict(cfg),
         "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -156,13 +237,13 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- GPU leg
-def run_ours(args):
+def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
 
     from volume_segmantics_b200 import _lib, sharding
-    from volume_segmantics_b200.engine import Engine
-    from volume_segmantics_b200.plan import B200SegmentationModel, conv_macs_per_pixel
+    from volume_segmantics_b200.engine import get_engine
+    from volume_segmantics_b200.plan import conv_macs_per_pixel
 
     world, rank, local = env_int("WORLD_SIZE", 1), env_int("RANK", 0), env_int("LOCAL_RANK", 0)
     if world > 1:
@@ -171,21 +252,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    size = args.size
-    nvox = size ** 3
+    shape = tuple(cfg["shape"])
+    nvox = int(np.prod(shape))
 
-    torch.manual_seed(0)
-    model = B200SegmentationModel(ARCH, ENCODER, CLASSES)  # random init of the named architecture
-    g = torch.Generator().manual_seed(1)
-    sd = model.state_dict()
-    for key, (shape, (role, _)) in model.spec.param_shapes().items():  # randomise BN
-        if role in ("bn_w", "bn_var"):
-            sd[key].copy_(torch.rand(shape, generator=g) + 0.5)
-        elif role in ("bn_b", "bn_mean"):
-            sd[key].copy_(torch.randn(shape, generator=g) * 0.1)
-
-    vol_host = torch.from_numpy(synth_volume(size)).pin_memory()
-    eng = Engine(local)
+    model = make_models(cfg)
+    vol_host = torch.from_numpy(synth_volume(shape)).pin_memory()
+    eng = get_engine(local)
     stream = torch.cuda.Stream(device=dev)
     eng.set_stream(stream.cuda_stream)
     eng.load_model(model)
@@ -193,9 +265,9 @@ def run_ours(args):
         eng.set_batch(args.batch)
     vol_dev = vol_host.to(dev)
     torch.cuda.synchronize()
-    eng.set_volume_device(vol_dev.data_ptr(), (size, size, size))
-    dirs = sharding.direction_list(DIR_MASK, skip_duplicates=True)
-    items = sharding.partition((size, size, size), dirs, world, granule=8)[rank]
+    eng.set_volume_device(vol_dev.data_ptr(), shape)
+    dirs = sharding.direction_list(cfg["dir_mask"], skip_duplicates=True)
+    items = sharding.partition(shape, dirs, world, granule=8)[rank]
 
     # ---- the one exchange step --------------------------------------------
     # "peer": fused max-reduce + unpack of this rank's voxel shard, reading the other ranks'
@@ -223,7 +295,8 @@ def run_ours(args):
         eng.bind_keys(keys.data_ptr())
     shards = sharding.voxel_shards(nvox, world)
     v0, v1 = shards[rank]
-    out_n = nvox if exchange != "peer" else shards[0][1] - shards[0][0]
+    per = shards[0][1] - shards[0][0]
+    out_n = nvox if exchange != "peer" else per
     labels_dev = torch.empty(out_n, dtype=torch.uint8, device=dev)
     probs_dev = torch.empty(out_n, dtype=torch.float16, device=dev)
     tick = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -272,7 +345,7 @@ def run_ours(args):
         return e0.elapsed_time(e1)
 
     # pass 1 (the reported value): no per-launch events.  pass 2: the same K steps with every
-    # kernel launch bracketed by CUDA events, for the roofline of the conv kernels.
+    # kernel launch bracketed by CUDA events, for the rooflines of the kernel classes.
     sampler = ClockSampler(local) if rank == 0 else None
     ms = timed_pass(False)
     launches = eng.launch_count()  # own kernels only (NCCL kernels are not counted)
@@ -286,16 +359,18 @@ def run_ours(args):
     ms_step = float(t.item()) / args.steps
     value = nvox / (ms_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (tcgen05 conv), this rank's launches ----
+    # ---- rooflines, this rank's launches -------------------------------------------------------
     peak_tf, peak_gbs, peak_src = measured_peaks()
-    macs_px = conv_macs_per_pixel(model.spec) - 49 * 64 / 4.0  # the 7x7 stem is timed in its own class
+    stem_macs = 49 * 64 / 4.0  # the 7x7 stem is timed in its own (HBM-bound) class
+    macs_px = conv_macs_per_pixel(model.spec) - stem_macs
     padded_px = sum(it.cost for it in items)
+    C = cfg["classes"]
     conv_ms, conv_n = stages["conv_tc"]
     conv_flops = 2.0 * macs_px * padded_px * args.steps
     roofline = None
     traffic = None  # DRAM bytes per conv launch from the committed ncu capture of one batch (profiles/)
     tpath = ROOT / "profiles" / "r01_conv_traffic.json"
-    if tpath.exists() and size == 1024:
+    if tpath.exists() and cfg["key"] == "cfg3" and not args.size:
         traffic = json.loads(tpath.read_text()).get("dram_bytes_per_conv_launch")
     if conv_ms > 0:
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
@@ -310,101 +385,144 @@ def run_ours(args):
                     "measured": "second pass of the same K steps with per-launch CUDA events "
                                 f"({ms_prof / args.steps:.1f} ms/step with events vs {ms / args.steps:.1f} without)",
                     "other_stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items() if k != "conv_tc"}}
+    # HBM-bound classes: algorithmic bytes per padded pixel / event time
+    head_factor = model.spec.layers[-1].factor
+    per_px = {
+        "slicer": (3.0, "1 B volume read + 2 B activation written"),
+        "stem": (2.0 + 32.0 + 8.0, "stem 7x7/2 + fused 3x3/2 max-pool: 2 B in + 64 ch x 2 B / 4 out + 64 ch x 2 B / 16 pooled"),
+        "head": (4.0 * C / (head_factor ** 2) + 16.0, f"{C} fp32 logits (at 1/{head_factor} resolution) + 8 B key read + 8 B key written"),
+    }
+    classes = {}
+    for name, (bpp, what) in per_px.items():
+        ms_c, n_c = stages[name]
+        if name == "stem":
+            ms_c += stages["pool"][0]
+        if ms_c > 0:
+            gbs = bpp * padded_px * args.steps / (ms_c * 1e-3) / 1e9
+            classes[name] = {"bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
+                             "bytes_per_padded_pixel": bpp, "what": what, "ms_per_step": ms_c / args.steps, "launches": n_c}
 
     # ---- e2e through the public API with host buffers ------------------------------
-    e2e = None
-    if rank == 0 or world > 1:
-        e2e = run_e2e(args, eng, model, vol_host, stream, world, rank, items, keys, dev, exchange, shards)
+    e2e, digest = run_e2e(args, cfg, eng, model, vol_host, stream, world, rank, items, keys, dev, exchange, shards)
 
     # ---- CPU baseline: bounded sample on rank 0, N = 1 only -------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        v, detail = cpu_oracle_sample(size, 8 if size >= 1024 else 16, threads)
-        cpu = {"value": v, "unit": "voxels/s", "cores": threads, "kind": "port",
-               "sample": f"{8 if size >= 1024 else 16} slices of {size}^2 through the fp32 CPU oracle + one fp16 merge sample, "
-                         f"extrapolated to 12 directions x {size} slices + 11 merges ({detail['s_per_slice']:.3f} s/slice, "
-                         f"{detail['s_per_merge_voxel'] * 1e9:.1f} ns/merge-voxel)"}
+        v, sample = cpu_oracle_sample(cfg, threads, 2)
+        cpu = {"value": v, "unit": "voxels/s", "cores": threads, "kind": "port", "sample": sample}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": cfg["metric"], "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "fp16" if _lib.act_dtype() == torch.float16 else "bf16", "data": "synthetic",
-            "config": {"workload": f"U-Net/ResNet-34, high quality (12 directions), {CLASSES} classes, synthetic {size}^3 uint8 volume",
-                       "weights": "random init of the named architecture (seed 0), BN statistics randomised",
-                       "directions_computed": len(dirs),
-                       "note": "directions 3,6,9,10 duplicate 1,4,7,0 image-for-image and can never win the first-max merge "
-                               "(SURVEY.md 3.3); they are skipped and NOT counted in the roofline FLOPs",
-                       "l2": "inputs larger than L2 (1 GiB volume + 8 GiB keys per step)",
-                       "accumulate": "fp32", "parallelism": f"slice-range sharding over {world} GPU(s)",
-                       "exchange": {"none": "single GPU: unpack only",
-                                    "peer": "fused max-reduce + unpack of each rank's voxel shard over NVLink peer memory (CUDA IPC); result sharded over ranks",
-                                    "nccl": "ncclAllReduce(max) of the 8 B/voxel key volume, rank 0 unpacks"}[exchange]},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "config": config_dict(cfg),
+            "details": {"directions_computed": len(dirs),
+                        "note": "directions 3,6,9,10 duplicate 1,4,7,0 image-for-image and can never win the first-max merge "
+                                "(SURVEY.md 3.3); they are skipped and NOT counted in the roofline FLOPs",
+                        "l2": f"inputs larger than L2 ({nvox >> 20} MiB volume + {nvox >> 17} MiB keys per step)",
+                        "accumulate": "fp32", "parallelism": f"slice-range sharding over {world} GPU(s)",
+                        "exchange": {"none": "single GPU: unpack only",
+                                     "peer": "fused max-reduce + unpack of each rank's voxel shard over NVLink peer memory (CUDA IPC); result sharded over ranks",
+                                     "nccl": "ncclAllReduce(max) of the 8 B/voxel key volume, rank 0 unpacks"}[exchange]},
+            "roofline": roofline, "roofline_classes": classes, "cpu_baseline": cpu, "e2e": e2e, "result_sha256": digest,
+            "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_e2e(args, eng, model, vol_host, stream, world, rank, items, keys, dev, exchange, shards):
-    """Host ndarray in -> host ndarrays out, copies inside the timed region."""
+def sha256_arrays(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(memoryview(np.ascontiguousarray(a)).cast("B"))
+    return h.hexdigest()
+
+
+def run_e2e(args, cfg, eng, model, vol_host, stream, world, rank, items, keys, dev, exchange, shards):
+    """Host ndarray in -> host ndarrays out, copies inside the timed region.  Returns (e2e dict, sha256)."""
     import torch
     import torch.distributed as dist
 
-    size = args.size
-    nvox = size ** 3
+    shape = tuple(cfg["shape"])
+    nvox = int(np.prod(shape))
     vol_np = vol_host.numpy()
-    steps = max(1, min(args.steps, 2))
+    steps = max(1, args.steps)
     if world == 1:
-        # exactly the call a user of the reference makes
+        # exactly what a user of the reference does: a .pytorch file, VolSeg2dPredictor, one _predict_* call
         from types import SimpleNamespace
 
-        from volume_segmantics_b200.host.predictor import VolSeg2dPredictor
+        import volume_segmantics.utilities.base_data_utils as utils
+        from volume_segmantics.model.operations.vol_seg_2d_predictor import VolSeg2dPredictor
 
-        pred = VolSeg2dPredictor.__new__(VolSeg2dPredictor)
-        pred.settings = SimpleNamespace(cuda_device=eng.device)
-        pred.model_device_num, pred.model, pred.num_labels, pred.label_codes = eng.device, model, CLASSES, {}
-        pred._engine = eng
-        eng.bind_keys(0)
-        eng.set_stream(0)
-        pred._predict_12_ways_max_probs(vol_np)  # warm-up (allocations)
+        struc = {"type": utils.ModelType[cfg["arch"]], "encoder_name": cfg["encoder"], "encoder_weights": None,
+                 "in_channels": 1, "classes": cfg["classes"]}
+        with tempfile.TemporaryDirectory() as tmp:
+            path = Path(tmp) / "bench_model.pytorch"
+            torch.save({"model_state_dict": model.state_dict(), "model_struc_dict": struc, "label_codes": {}}, path)
+            eng.bind_keys(0)
+            eng.set_stream(0)
+            pred = VolSeg2dPredictor(str(path), SimpleNamespace(cuda_device=eng.device))
+        call = {"low": lambda v: pred._predict_single_axis(v), "medium": pred._predict_3_ways_max_probs,
+                "high": pred._predict_12_ways_max_probs}[cfg["quality"]]
+        call(vol_np)  # warm-up (weights lowered for this module, allocations)
         labels = probs = None
         t0 = time.perf_counter()
         for _ in range(steps):
             labels = probs = None  # the caller is done with the previous result: its pinned block is reused
-            labels, probs = pred._predict_12_ways_max_probs(vol_np)
+            labels, probs = call(vol_np)
         dt = (time.perf_counter() - t0) / steps
         assert labels.shape == vol_np.shape and probs.dtype == np.float16
-        return {"value": nvox / dt, "unit": "voxels/s", "h2d_bytes_per_step": nvox, "d2h_bytes_per_step": 3 * nvox,
-                "api": "VolSeg2dPredictor._predict_12_ways_max_probs(ndarray) -> (uint8, float16) ndarrays"}
-    # N > 1: every rank uploads the (replicated) volume, rank 0 downloads the result
-    labels_h = torch.empty(nvox, dtype=torch.uint8).pin_memory() if rank == 0 else None
-    probs_h = torch.empty(nvox, dtype=torch.float16).pin_memory() if rank == 0 else None
-    vol_dev = torch.empty(nvox, dtype=torch.uint8, device=dev)
+        fn = {"low": "_predict_single_axis", "medium": "_predict_3_ways_max_probs", "high": "_predict_12_ways_max_probs"}[cfg["quality"]]
+        return ({"value": nvox / dt, "unit": "voxels/s", "h2d_bytes_per_step": nvox, "d2h_bytes_per_step": 3 * nvox, "steps": steps,
+                 "api": f"VolSeg2dPredictor(<model>.pytorch, settings).{fn}(ndarray) -> (uint8, float16) ndarrays; "
+                        "model file loading and weight lowering happen once, before the timed calls"},
+                sha256_arrays(labels, probs))
+
+    # ---- N > 1: one process per GPU ---------------------------------------------------------
     per = shards[0][1] - shards[0][0]
     v0, v1 = shards[rank]
+    # ONE page-locked result shared by all ranks (a /dev/shm mapping registered with the CUDA driver in
+    # every process): each rank downloads its own shard over its own PCIe link
+    tag = os.environ.get("MASTER_PORT", "0")
+    lab_path, prb_path = f"/dev/shm/vsb200_bench_{tag}_labels", f"/dev/shm/vsb200_bench_{tag}_probs"
+    if rank == 0:
+        for p, n in ((lab_path, nvox), (prb_path, 2 * nvox)):
+            with open(p, "wb") as f:
+                f.truncate(n)
+    dist.barrier()
+    labels_h = torch.from_file(lab_path, shared=True, size=nvox, dtype=torch.uint8)
+    probs_h = torch.from_file(prb_path, shared=True, size=nvox, dtype=torch.float16)
+    rt = torch.cuda.cudart()
+    for tsr in (labels_h, probs_h):
+        rc = rt.cudaHostRegister(tsr.data_ptr(), tsr.numel() * tsr.element_size(), 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister failed: {rc}")
+    vol_dev = torch.empty(per * world, dtype=torch.uint8, device=dev)  # all-gather output (>= nvox)
+    vol_flat = vol_host.view(-1)
     n_out = nvox if exchange == "nccl" else per
     labels_dev = torch.empty(n_out, dtype=torch.uint8, device=dev)
     probs_dev = torch.empty(n_out, dtype=torch.float16, device=dev)
-    lab_all = torch.empty(per * world, dtype=torch.uint8, device=dev) if (exchange == "peer" and rank == 0) else None
-    prb_all = torch.empty(per * world, dtype=torch.float16, device=dev) if (exchange == "peer" and rank == 0) else None
     tick = torch.zeros(1, dtype=torch.int32, device=dev)
     eng.set_stream(stream.cuda_stream)
     if exchange == "peer":
-        eng.close_peers()  # set_volume_device re-creates nothing (same size), but remap to be safe
-    eng.set_volume_device(vol_dev.data_ptr(), (size, size, size))
+        eng.close_peers()
+    eng.set_volume_device(vol_dev.data_ptr(), shape)
     if exchange == "nccl":
         eng.bind_keys(keys.data_ptr())
     else:
         handles = [None] * world
         dist.all_gather_object(handles, eng.keys_ipc_handle())
         eng.open_peers(handles, rank)
+    my = vol_dev[rank * per:(rank + 1) * per]
 
     def one():
         with torch.cuda.stream(stream):
-            vol_dev.copy_(vol_host.view(-1), non_blocking=True)
+            if v1 > v0:
+                my[: v1 - v0].copy_(vol_flat[v0:v1], non_blocking=True)  # 1/N of the volume over this rank's PCIe link
+            dist.all_gather_into_tensor(vol_dev, my)  # the other parts over NVLink
             if exchange == "nccl":
                 keys.zero_()
             else:
@@ -413,19 +531,17 @@ def run_e2e(args, eng, model, vol_host, stream, world, rank, items, keys, dev, e
                 eng.predict_range(it.d, it.s0, it.s1)
             if exchange == "nccl":
                 dist.all_reduce(keys, op=dist.ReduceOp.MAX)
-                if rank == 0:
-                    eng.unpack_device(labels_dev.data_ptr(), probs_dev.data_ptr())
-                    labels_h.copy_(labels_dev, non_blocking=True)
-                    probs_h.copy_(probs_dev, non_blocking=True)
+                eng.unpack_device(labels_dev.data_ptr(), probs_dev.data_ptr())
+                if v1 > v0:
+                    labels_h[v0:v1].copy_(labels_dev[v0:v1], non_blocking=True)
+                    probs_h[v0:v1].copy_(probs_dev[v0:v1], non_blocking=True)
             else:
                 dist.all_reduce(tick)
                 eng.reduce_unpack_shard(v0, v1, labels_dev.data_ptr(), probs_dev.data_ptr())
                 dist.all_reduce(tick)
-                dist.gather(labels_dev, list(lab_all.split(per)) if rank == 0 else None, dst=0)
-                dist.gather(probs_dev, list(prb_all.split(per)) if rank == 0 else None, dst=0)
-                if rank == 0:
-                    labels_h.copy_(lab_all[:nvox], non_blocking=True)
-                    probs_h.copy_(prb_all[:nvox], non_blocking=True)
+                if v1 > v0:
+                    labels_h[v0:v1].copy_(labels_dev[: v1 - v0], non_blocking=True)
+                    probs_h[v0:v1].copy_(probs_dev[: v1 - v0], non_blocking=True)
         torch.cuda.synchronize()
 
     one()
@@ -433,14 +549,30 @@ def run_e2e(args, eng, model, vol_host, stream, world, rank, items, keys, dev, e
     t0 = time.perf_counter()
     for _ in range(steps):
         one()
-    dist.barrier()
+    dist.barrier()  # every shard of the last result is in the shared host buffer
     t = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    digest = None
+    if rank == 0:
+        digest = sha256_arrays(labels_h.numpy().reshape(shape), probs_h.numpy().reshape(shape))
+    dist.barrier()
+    for tsr in (labels_h, probs_h):
+        rt.cudaHostUnregister(tsr.data_ptr())
     if exchange == "peer":
         eng.close_peers()
-    return {"value": nvox / float(t.item()), "unit": "voxels/s", "h2d_bytes_per_step": nvox * world,
-            "d2h_bytes_per_step": 3 * nvox,
-            "api": f"Engine.predict_range per rank + {exchange} exchange, host ndarray in/out"}
+    dist.barrier()
+    if rank == 0:
+        for p in (lab_path, prb_path):
+            try:
+                os.unlink(p)
+            except OSError:
+                pass
+    return ({"value": nvox / float(t.item()), "unit": "voxels/s", "h2d_bytes_per_step": nvox, "d2h_bytes_per_step": 3 * nvox,
+             "steps": steps,
+             "api": f"one process per GPU: 1/{world} of the volume uploaded per rank + NCCL all-gather over NVLink, "
+                    f"Engine.predict_range per work item, {exchange} exchange, every rank downloads its shard of labels + "
+                    "fp16 probabilities into one shared page-locked host result"},
+            digest)
 
 
 def main():
@@ -449,17 +581,19 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=1024, help="edge of the cubic synthetic volume (BASELINE: 1024)")
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS), help="BASELINE.json configuration (default cfg3)")
+    ap.add_argument("--size", type=int, default=0, help="development aid: edge of a smaller cubic volume of the same configuration")
     ap.add_argument("--batch", type=int, default=0, help="slices per launch (0 = engine default)")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with CUDA events")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU key exchange: fused NVLink peer reduce+unpack (default) or NCCL all-reduce")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline sample")
     args = ap.parse_args()
+    cfg = resolve_config(args)
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, cfg)
     else:
-        run_ours(args)
+        run_ours(args, cfg)
 
 
 if __name__ == "__main__":

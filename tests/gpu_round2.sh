@@ -1,0 +1,59 @@
+#!/bin/bash
+# Round-2 validation on ONE B200 (gpurun --timeout 3000 -- 'bash tests/gpu_round2.sh [stage ...]').
+# Stages: tests bench configs layers ncu.  Artefacts land in gpurun_out/ (copied to profiles/ by hand).
+mkdir -p gpurun_out
+STAGES="${@:-tests bench configs layers ncu}"
+nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader
+for st in $STAGES; do
+case $st in
+tests)
+  echo "== gpu tests"; timeout 2400 python -m pytest tests -m gpu -q -s -p no:cacheprovider > gpurun_out/r02_gpu_tests.log 2>&1
+  echo "pytest rc=$?"; grep -E "passed|failed|error" gpurun_out/r02_gpu_tests.log | tail -3; grep -E "^FAILED|^ERROR" gpurun_out/r02_gpu_tests.log | head -20
+  echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/r02_smoke.log
+  ;;
+bench)
+  echo "== bench cfg3"; timeout 1500 python bench.py --steps 3 --warmup 3 > gpurun_out/r02_bench_cfg3.json 2> gpurun_out/r02_bench_cfg3.err
+  echo "rc=$?"; tail -3 gpurun_out/r02_bench_cfg3.err
+  python - <<'PY'
+import json
+try:
+    d=json.loads(open('gpurun_out/r02_bench_cfg3.json').read().strip().splitlines()[-1])
+    print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks','result_sha256')}, d['e2e']['value'], d['roofline']['frac'], d['roofline']['other_stage_ms_per_step'])
+    print({k:(round(v['frac'],3), round(v['ms_per_step'],1)) for k,v in d['roofline_classes'].items()})
+except Exception as e: print('bench parse failed', e)
+PY
+  ;;
+configs)
+  for c in cfg2 cfg4 cfg5; do
+    echo "== bench $c"; timeout 1500 python bench.py --config $c --steps 2 --warmup 3 --no-cpu > gpurun_out/r02_bench_$c.json 2> gpurun_out/r02_bench_$c.err
+    echo "rc=$?"; tail -3 gpurun_out/r02_bench_$c.err
+    python - $c <<'PY'
+import json,sys
+try:
+    d=json.loads(open(f'gpurun_out/r02_bench_{sys.argv[1]}.json').read().strip().splitlines()[-1])
+    print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'], d['roofline']['other_stage_ms_per_step'])
+except Exception as e: print('bench parse failed', e)
+PY
+  done
+  ;;
+layers)
+  echo "== per-layer table"; timeout 600 python tests/layer_profile.py 1024 64 > gpurun_out/r02_layers.txt 2>&1; tail -2 gpurun_out/r02_layers.txt
+  echo "== other architectures"; timeout 900 python tests/arch_timing.py > gpurun_out/r02_arch_timing.txt 2>&1; tail -6 gpurun_out/r02_arch_timing.txt
+  ;;
+ncu)
+  # only after the identical plain command exited 0
+  echo "== ncu stem / b3.conv1 / conv_tc"
+  timeout 300 python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_plain.log 2>&1 && \
+  timeout 900 ncu --set full --import-source on --clock-control none -k 'regex:conv_halo2_kernel<1' -s 1 -c 1 -f -o gpurun_out/r02_stem \
+      python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_stem.log 2>&1
+  echo "ncu stem rc=$?"
+  timeout 900 ncu --set full --import-source on --clock-control none -k 'regex:conv_halo2_kernel<0, 64, 2' -s 5 -c 1 -f -o gpurun_out/r02_b3conv1 \
+      python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_b3.log 2>&1
+  echo "ncu b3 rc=$?"
+  timeout 900 ncu --set full --import-source on --clock-control none -k 'regex:conv_tc_kernel<128' -s 6 -c 2 -f -o gpurun_out/r02_convtc \
+      python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_convtc.log 2>&1
+  echo "ncu conv_tc rc=$?"
+  ls -la gpurun_out/*.ncu-rep | tail -5
+  ;;
+esac
+done
