@@ -39,18 +39,21 @@ PY
 layers)
   echo "== per-layer table"; timeout 600 python tests/layer_profile.py 1024 64 > gpurun_out/r02_layers.txt 2>&1; tail -2 gpurun_out/r02_layers.txt
   echo "== other architectures"; timeout 900 python tests/arch_timing.py > gpurun_out/r02_arch_timing.txt 2>&1; tail -6 gpurun_out/r02_arch_timing.txt
+  echo "== per-layer, DeepLabV3+/R50 at 2048x2048 (cfg5 x-plane slices) and U-Net++/ResNeXt-50 at 512x512"
+  timeout 600 python tests/layer_profile.py 2048 32 0 DEEPLABV3_PLUS resnet50 4 > gpurun_out/r02_layers_deeplab.txt 2>&1; tail -3 gpurun_out/r02_layers_deeplab.txt
+  timeout 600 python tests/layer_profile.py 512 128 0 U_NET_PLUS_PLUS resnext50_32x4d 6 > gpurun_out/r02_layers_unetpp.txt 2>&1; tail -3 gpurun_out/r02_layers_unetpp.txt
   ;;
 ncu)
   # only after the identical plain command exited 0
   echo "== ncu stem / b3.conv1 / conv_tc"
   timeout 300 python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_plain.log 2>&1 && \
-  timeout 900 ncu --set full --import-source on --clock-control none -k 'regex:conv_halo2_kernel<1' -s 1 -c 1 -f -o gpurun_out/r02_stem \
+  timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k 'regex:conv_halo2_kernel<1' -s 1 -c 1 -f -o gpurun_out/r02_stem \
       python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_stem.log 2>&1
   echo "ncu stem rc=$?"
-  timeout 900 ncu --set full --import-source on --clock-control none -k 'regex:conv_halo2_kernel<0, 64, 2' -s 5 -c 1 -f -o gpurun_out/r02_b3conv1 \
+  timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k 'regex:conv_halo2_kernel<0, 64, 2' -s 5 -c 1 -f -o gpurun_out/r02_b3conv1 \
       python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_b3.log 2>&1
   echo "ncu b3 rc=$?"
-  timeout 900 ncu --set full --import-source on --clock-control none -k 'regex:conv_tc_kernel<128' -s 6 -c 2 -f -o gpurun_out/r02_convtc \
+  timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k 'regex:conv_tc_kernel<128' -s 6 -c 2 -f -o gpurun_out/r02_convtc \
       python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_convtc.log 2>&1
   echo "ncu conv_tc rc=$?"
   ls -la gpurun_out/*.ncu-rep | tail -5

@@ -14,7 +14,10 @@ from volume_segmantics_b200.plan import B200SegmentationModel  # noqa: E402
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 nslices = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 batch = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-model = B200SegmentationModel("U_NET", "resnet34", 4)
+arch = sys.argv[4] if len(sys.argv) > 4 else "U_NET"
+encoder = sys.argv[5] if len(sys.argv) > 5 else "resnet34"
+classes = int(sys.argv[6]) if len(sys.argv) > 6 else 4
+model = B200SegmentationModel(arch, encoder, classes)
 eng = Engine(0)
 eng.load_model(model)
 if batch:
@@ -37,9 +40,16 @@ tot_ms = tot_fl = 0
 print(f"size {size} slices {nslices} batch {batch or 'auto'}")
 print(f"{'layer':38s} {'Cin':>5s} {'Cout':>5s} k s {'res':>5s} {'ms':>8s} {'TFLOP/s':>8s} {'GB/s':>7s} {'launch':>6s}")
 for L, (ms, n) in zip(spec.layers, times):
-    if L.kind not in ("conv", "maxpool") or n == 0:
+    if L.kind not in ("conv", "maxpool", "gap", "upsample") or n == 0:
         continue
     ds = spec.tensors[L.out].ds_log2
+    if L.kind in ("gap", "upsample"):
+        t_in = spec.tensors[L.srcs[0][0]]
+        by = t_in.channels * 2 * (px / 4 ** t_in.ds_log2 if t_in.ds_log2 >= 0 else nslices)
+        by += spec.tensors[L.out].channels * 2 * (px / 4 ** ds if ds >= 0 else nslices)
+        tot_ms += ms
+        print(f"{L.kind:38s} {t_in.channels:5d} {spec.tensors[L.out].channels:5d} - - {'1/' + str(2 ** ds) if ds >= 0 else '1x1':5s} {ms:8.3f} {0.0:8.1f} {by / ms / 1e6:7.0f} {n:6d}")
+        continue
     opx = px / 4 ** ds
     if L.kind == "conv":
         fl = 2.0 * L.k * L.k * (L.cin // L.groups) * L.cout * opx

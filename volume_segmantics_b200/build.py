@@ -15,7 +15,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libvsb200.so"          # fp16 activations/weights (default)
 LIB_BF16 = HERE / "libvsb200_bf16.so"  # bfloat16 variant (VSB200_VARIANT=bf16)
-SOURCES = ["engine.cu", "conv_tc.cu", "conv_halo.cu", "kernels_simple.cu", "kernels_head.cu", "kernels_ingest.cu"]
+SOURCES = ["engine.cu", "conv_tc.cu", "conv_halo.cu", "conv_stem.cu", "kernels_simple.cu", "kernels_head.cu", "kernels_ingest.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -145,6 +145,24 @@ struct ConvHalo2Params {
   int32_t mma_warps;  // 2: two MMA issuing warps on alternate tiles (MODE 0, resident weights, even a_stages >= 4)
   FastDiv div_n_tiles, div_tx, div_ty;  // set by the launcher
 };
+// Stem 7x7/2 + fused 3x3/2 max-pool, pool computed inside the CTA (conv_stem.cu).
+struct ConvStemParams {
+  const uint16_t* in;       // network input [NB, 2H, 2W] 16-bit (tensor 0)
+  const uint8_t* wpacked;   // [64][128 B] SW128 rows: K index = ky * 8 + (kx + 1)
+  const float* bias;        // [64]
+  const TmaDesc* out_map;   // conv output [NB, H, W, 64]: box {64, 14, 1, 16, 1}, SWIZZLE_128B
+  const TmaDesc* pool_map;  // pooled output [NB, H/2, W/2, 64]: box {64, 7, 1, 8, 1}, SWIZZLE_128B
+  int32_t NB, H, W;         // conv output size
+  int32_t n_base;
+  int32_t tiles_x, tiles_y; // blocks of 8 x 7 pooled pixels
+  int32_t a_stages;         // 2..4 im2col stages of 32 KB
+  FastDiv div_tx, div_ty;   // set by the launcher
+};
+size_t conv_stem_smem_bytes(const ConvStemParams& p);
+void conv_stem_tiles(int Hc, int Wc, int* tiles_x, int* tiles_y);
+cudaError_t conv_stem_configure();
+cudaError_t launch_conv_stem(const ConvStemParams& p, int num_sms, cudaStream_t st);
+
 constexpr int HALO2_LOAD_WARPS = 4;
 constexpr int HALO2_MMA2_WARP = HALO2_LOAD_WARPS + 2 + 8;  // second MMA issuer (mma_warps == 2)
 constexpr int HALO2_THREADS = 32 * (HALO2_LOAD_WARPS + 2 + 8 + 1);

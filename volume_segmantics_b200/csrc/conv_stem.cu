@@ -1,0 +1,392 @@
+// Stem of the ResNet encoders: conv 7x7 / stride 2 / pad 3, 1 -> 64 channels, folded BN + ReLU,
+// FUSED with the 3x3 / stride 2 / pad 1 max-pool that follows it (smp ResNetEncoder conv1 + bn1 +
+// relu + maxpool [ext]; reached from vol_seg_2d_predictor.py:44).  HBM-bound: per conv output
+// pixel 4 x 2 B in, 128 B out (the /2 skip tensor), 32 B pooled.
+//
+// A CTA owns a block of 8 x 7 POOLED pixels.  The pooling windows of that block cover conv rows
+// [2*py0 - 1, 2*py0 + 16) and conv columns [2*px0 - 1, 2*px0 + 14): 17 x 15 = 255 conv pixels = the
+// 256 rows of two M = 128 tcgen05 tiles (one dummy row).  The one conv row / column above / left of
+// the 16 x 14 pixels this CTA OWNS is recomputed (14 % more MMA rows, which are not the limit) so the
+// pool needs no exchange between CTAs, no atomics and no zero-initialised output:
+//   warps 0..3   loaders: raw input window (39 rows x 48 px, 16-byte cp.async, zero-filled outside
+//                the image, two tiles ahead) -> im2col rows in the SW128 K-major A layout:
+//                K chunk ky (16 bytes) = input columns 2*cx-4 .. 2*cx+3 of row 2*cy+ky-3; column
+//                2*cx-4 lies outside the 7x7 window and meets a zero weight; K padded 49 -> 64
+//   warp 4       TMEM allocator + MMA issuer: 2 tiles x 4 K-steps, N = 64, accumulators in 4 stages
+//   warp 5       weights (8 KB, once), then TMA-store issuer: the owned 16 x 14 conv pixels and the
+//                8 x 7 pooled pixels leave as one cp.async.bulk.tensor store each (clipped at the
+//                image edge by TMA)
+//   warps 6..13  epilogue: tcgen05.ld (thread = conv pixel, 64 channels), + bias, ReLU, 16-bit pack
+//                -> swizzled staging tile; then the 3x3 max over the staged tile -> pooled staging.
+// Pixels outside the image (the halo row / column of border tiles, the dummy row) are staged as 0,
+// the identity of max over ReLU outputs -- every pooling window holds at least one real pixel.
+#include "conv_halo.cuh"
+
+#include "conv_epilogue.cuh"
+#include "kernels.h"
+
+namespace vsb {
+
+namespace {
+
+constexpr int ST_PH = 8, ST_PW = 7;                  // pooled block
+constexpr int ST_RH = 2 * ST_PH + 1, ST_RW = 2 * ST_PW + 1;  // conv region 17 x 15
+constexpr int ST_OH = 2 * ST_PH, ST_OW = 2 * ST_PW;  // owned conv block 16 x 14
+constexpr int ST_RAW_ROWS = 2 * (ST_RH - 1) + 7;     // 39 input rows
+constexpr int ST_RAW_PITCH = 96;                     // bytes per raw row: 48 fp16 pixels
+constexpr int ST_RAW_BYTES = 3840;                   // >= 39 * 96, multiple of 128
+constexpr int ST_RAW_RING = 4;
+constexpr int ST_A_STAGE = 2 * 128 * 128;            // two M tiles of 128 rows x 128 B
+constexpr int ST_OWNED_BYTES = ST_OH * ST_OW * 128;  // 28672
+constexpr int ST_HALO_BYTES = 4096;                  // 31 halo pixels x 128 B
+constexpr int ST_POOL_BYTES = ST_PH * ST_PW * 128;   // 7168
+constexpr int ST_OUT_BUF = ST_OWNED_BYTES + ST_HALO_BYTES + ST_POOL_BYTES;  // 39936 (multiple of 1024)
+constexpr int ST_LOAD_WARPS = 4, ST_EPI_WARPS = 8;
+constexpr int ST_THREADS = 32 * (ST_LOAD_WARPS + 2 + ST_EPI_WARPS);
+constexpr int ST_MAX_A = 4;
+
+struct StemCtl {
+  uint64_t a_full[ST_MAX_A];
+  uint64_t a_empty[ST_MAX_A];
+  uint64_t w_full;
+  uint64_t acc_full[4];
+  uint64_t acc_empty[4];
+  uint64_t out_full[2];
+  uint64_t out_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad[3];
+};
+
+__device__ __forceinline__ void st_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint4 st_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t st_max2(uint32_t a, uint32_t b) {
+  uint32_t r;
+#if VSB_ACT_F16
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+#else
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+#endif
+  return r;
+}
+__device__ __forceinline__ uint64_t st_desc(uint32_t addr) {  // SW128 K-major, 8-row groups 1024 B apart
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// byte offset of chunk `j` (16 B) of conv-region pixel (ry, rx) inside one staging buffer
+__device__ __forceinline__ uint32_t st_px_off(int ry, int rx) {
+  if (ry >= 1 && rx >= 1) return (uint32_t)((ry - 1) * ST_OW + (rx - 1)) * 128u;              // owned block, TMA box order
+  return (uint32_t)ST_OWNED_BYTES + (uint32_t)(ry == 0 ? rx : ST_RW - 1 + ry) * 128u;          // halo row 0, then halo column 0
+}
+__device__ __forceinline__ uint32_t st_chunk(uint32_t px_off, int j) {  // Swizzle<3,4,3> on the address bits
+  return px_off + ((uint32_t)(j ^ (int)((px_off >> 7) & 7u)) << 4);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(ST_THREADS, 1) stem_pool_kernel(const __grid_constant__ ConvStemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* a_ring = smem;                                                   // a_stages x 32 KB
+  uint8_t* out_stage = a_ring + (size_t)p.a_stages * ST_A_STAGE;            // 2 x 39 KB
+  uint8_t* b_area = out_stage + 2 * ST_OUT_BUF;                             // 8 KB weights
+  uint8_t* raw_ring = b_area + 64 * 128;                                    // 4 x 3840 B
+  StemCtl* ctl = reinterpret_cast<StemCtl*>(raw_ring + ST_RAW_RING * ST_RAW_BYTES);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + 512);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.NB;
+  const int Hc = p.H, Wc = p.W;            // conv output (= stem tensor) size
+  const int Hin = 2 * Hc, Win = 2 * Wc;    // network input size
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.a_stages; ++i) {
+      mbar_init(&ctl->a_full[i], 32 * ST_LOAD_WARPS);
+      mbar_init(&ctl->a_empty[i], 1);
+    }
+    mbar_init(&ctl->w_full, 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&ctl->acc_full[i], 1);
+      mbar_init(&ctl->acc_empty[i], ST_EPI_WARPS);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->out_full[i], ST_EPI_WARPS);
+      mbar_init(&ctl->out_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+  if (warp == ST_LOAD_WARPS) tmem_alloc<512>(&ctl->tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  auto decode = [&](int t, int& px0, int& py0, int& n) {
+    auto fdiv = [](uint32_t v, const FastDiv& f) { return f.m ? __umulhi(v, f.m) : v; };
+    const uint32_t q = fdiv((uint32_t)t, p.div_tx);
+    const int tx = (int)((uint32_t)t - q * p.div_tx.d);
+    const uint32_t q2 = fdiv(q, p.div_ty);
+    const int ty = (int)(q - q2 * p.div_ty.d);
+    n = (int)q2 + p.n_base;
+    px0 = tx * ST_PW;
+    py0 = ty * ST_PH;
+  };
+
+  if (warp < ST_LOAD_WARPS) {
+    // ===================== loaders =====================
+    const int ptid = threadIdx.x;  // 0..127
+    const uint32_t raw0 = smem_u32(raw_ring), ring_addr = smem_u32(a_ring);
+    auto fetch_raw = [&](int tt, int slot) {
+      if (tt < total_tiles) {
+        int px2, py2, n2;
+        decode(tt, px2, py2, n2);
+        const uint16_t* img = p.in + (int64_t)n2 * Hin * Win;
+        const int iy0 = 4 * py2 - 5, ix0 = (4 * px2 - 8) & ~7;  // 16-byte aligned window origin
+        const uint32_t dst0 = raw0 + (uint32_t)slot * ST_RAW_BYTES;
+        for (int i = ptid; i < ST_RAW_ROWS * 6; i += 32 * ST_LOAD_WARPS) {
+          const int rr = i / 6, cc = i - rr * 6;
+          const int iy = iy0 + rr, ix = ix0 + 8 * cc;
+          const bool ok = iy >= 0 && iy < Hin && ix >= 0 && ix < Win;  // Win % 8 == 0: a chunk is all in or all out
+          const uint16_t* g = ok ? img + (int64_t)iy * Win + ix : p.in;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + rr * ST_RAW_PITCH + cc * 16), "l"(g),
+                       "r"(ok ? 16u : 0u)
+                       : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // this thread builds row `ptid` of both M tiles: conv-region pixels q = ptid and q = 128 + ptid
+    int ryA, rxA, ryB, rxB;
+    ryA = ptid / ST_RW;
+    rxA = ptid - ryA * ST_RW;
+    ryB = (128 + ptid) / ST_RW;
+    rxB = (128 + ptid) - ryB * ST_RW;
+    const bool dummyB = 128 + ptid >= ST_RH * ST_RW;
+    int as = 0;
+    uint32_t aph = 0;
+    int k = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
+      if (k == 0) {
+        fetch_raw(t, 0);
+        fetch_raw(t + (int)gridDim.x, 1);
+      }
+      fetch_raw(t + 2 * (int)gridDim.x, (k + 2) % ST_RAW_RING);
+      asm volatile("cp.async.wait_group 2;" ::: "memory");  // this tile's window has landed
+      st_bar_sync(5, 32 * ST_LOAD_WARPS);                    // ... for every loader thread
+      int px0, py0, n;
+      decode(t, px0, py0, n);
+      const int xoff = (4 * px0 - 8) - ((4 * px0 - 8) & ~7);  // 0 or 4 pixels
+      const uint32_t raw = raw0 + (uint32_t)(k % ST_RAW_RING) * ST_RAW_BYTES + (uint32_t)(xoff + 2) * 2u;
+      uint32_t va[28], vb[28];
+#pragma unroll
+      for (int ky = 0; ky < 7; ++ky) {
+        const uint32_t ra = raw + (uint32_t)(2 * ryA + ky) * ST_RAW_PITCH + (uint32_t)rxA * 4u;
+        const uint32_t rb = raw + (uint32_t)(2 * ryB + ky) * ST_RAW_PITCH + (uint32_t)rxB * 4u;
+#pragma unroll
+        for (int wq = 0; wq < 4; ++wq) {
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(va[ky * 4 + wq]) : "r"(ra + wq * 4));
+          if (!dummyB) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(vb[ky * 4 + wq]) : "r"(rb + wq * 4));
+          else vb[ky * 4 + wq] = 0u;
+        }
+      }
+      mbar_wait(&ctl->a_empty[as], aph ^ 1);
+      const uint32_t rowA = ring_addr + (uint32_t)as * ST_A_STAGE + (uint32_t)ptid * 128u;
+      const uint32_t rowB = rowA + 128u * 128u;
+      const int sw = ptid & 7;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        st_sts128(rowA + ((uint32_t)(j ^ sw) << 4), make_uint4(va[4 * j], va[4 * j + 1], va[4 * j + 2], va[4 * j + 3]));
+        st_sts128(rowB + ((uint32_t)(j ^ sw) << 4), make_uint4(vb[4 * j], vb[4 * j + 1], vb[4 * j + 2], vb[4 * j + 3]));
+      }
+      st_sts128(rowA + ((uint32_t)(7 ^ sw) << 4), make_uint4(0u, 0u, 0u, 0u));
+      st_sts128(rowB + ((uint32_t)(7 ^ sw) << 4), make_uint4(0u, 0u, 0u, 0u));
+      fence_proxy_async_smem();
+      mbar_arrive(&ctl->a_full[as]);
+      if (++as == p.a_stages) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp == ST_LOAD_WARPS) {
+    // ===================== MMA issuer =====================
+    int as = 0, acc = 0;
+    uint32_t aph = 0, acc_phase = 0;
+    const uint32_t idesc = umma_idesc_act(128, 64);
+    const uint64_t a_desc0 = st_desc(smem_u32(a_ring));
+    const uint64_t b_desc0 = st_desc(smem_u32(b_area));
+    mbar_wait(&ctl->w_full, 0);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      mbar_wait(&ctl->acc_empty[acc], acc_phase ^ 1);
+      mbar_wait(&ctl->a_full[as], aph);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t d0 = tmem_base + (uint32_t)acc * 128u;
+        const uint32_t a_units = (uint32_t)(as * ST_A_STAGE) >> 4;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const uint64_t ad = (a_desc0 & 0xffffffff00000000ull) | (uint32_t)((uint32_t)a_desc0 + a_units + m * (16384u >> 4));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16_ss(d0 + (uint32_t)m * 64u, (ad & 0xffffffff00000000ull) | (uint32_t)((uint32_t)ad + 2 * ks),
+                         (b_desc0 & 0xffffffff00000000ull) | (uint32_t)((uint32_t)b_desc0 + 2 * ks), idesc, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&ctl->a_empty[as]);
+        umma_commit(&ctl->acc_full[acc]);
+      }
+      __syncwarp();
+      if (++as == p.a_stages) {
+        as = 0;
+        aph ^= 1;
+      }
+      if (++acc == 4) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp == ST_LOAD_WARPS + 1) {
+    // ===================== weights, then TMA-store issuer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&ctl->w_full, 64 * 128);
+      bulk_load_1d(b_area, p.wpacked, 64 * 128, &ctl->w_full);
+      int ob = 0;
+      uint32_t oph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int px0, py0, n;
+        decode(t, px0, py0, n);
+        mbar_wait(&ctl->out_full[ob], oph);
+        uint8_t* buf = out_stage + (size_t)ob * ST_OUT_BUF;
+        tma_store_5d(p.out_map, buf, 0, 2 * px0, 0, 2 * py0, n);
+        tma_store_5d(p.pool_map, buf + ST_OWNED_BYTES + ST_HALO_BYTES, 0, px0, 0, py0, n);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(&ctl->out_empty[ob]);
+        if (++ob == 2) {
+          ob = 0;
+          oph ^= 1;
+        }
+      }
+      tma_store_wait_all<0>();
+    }
+  } else {
+    // ===================== epilogue + pool =====================
+    const int ew = warp - (ST_LOAD_WARPS + 2);     // 0..7
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
+    const int mtile = ew >> 2;                     // warps 6..9 -> tile 0, 10..13 -> tile 1 (6 & 3 = 2: quarters differ per warp, all four covered)
+    const int q = mtile * 128 + quarter * 32 + lane;  // conv-region pixel of this thread
+    const int ry = q / ST_RW, rx = q - ry * ST_RW;
+    const bool dummy = q >= ST_RH * ST_RW;
+    const uint32_t my_off = dummy ? 0u : st_px_off(ry, rx);
+    const int et = ew * 32 + lane;  // 0..255
+    const uint32_t stage0 = smem_u32(out_stage);
+    int acc = 0, ob = 0;
+    uint32_t acc_phase = 0, oph = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int px0, py0, n;
+      decode(t, px0, py0, n);
+      const int cy = 2 * py0 - 1 + ry, cx = 2 * px0 - 1 + rx;
+      const bool valid = !dummy && cy >= 0 && cy < Hc && cx >= 0 && cx < Wc;
+      mbar_wait(&ctl->acc_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * 128u + (uint32_t)mtile * 64u + ((uint32_t)(quarter * 32) << 16);
+      uint32_t v[2][32];
+      tmem_ld_32x32b_x32(taddr, v[0]);
+      tmem_ld_32x32b_x32(taddr + 32, v[1]);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->acc_empty[acc]);
+      mbar_wait(&ctl->out_empty[ob], oph ^ 1);  // TMA has read the previous tile out of this buffer
+      const uint32_t stage = stage0 + (uint32_t)ob * ST_OUT_BUF;
+      if (!dummy) {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h2 * 32 + qq * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h2 * 32 + qq * 8 + 4);
+              pk.x = pack2<true>(__uint_as_float(v[h2][qq * 8 + 0]) + b0.x, __uint_as_float(v[h2][qq * 8 + 1]) + b0.y);
+              pk.y = pack2<true>(__uint_as_float(v[h2][qq * 8 + 2]) + b0.z, __uint_as_float(v[h2][qq * 8 + 3]) + b0.w);
+              pk.z = pack2<true>(__uint_as_float(v[h2][qq * 8 + 4]) + b1.x, __uint_as_float(v[h2][qq * 8 + 5]) + b1.y);
+              pk.w = pack2<true>(__uint_as_float(v[h2][qq * 8 + 6]) + b1.z, __uint_as_float(v[h2][qq * 8 + 7]) + b1.w);
+            }
+            st_sts128(stage + st_chunk(my_off, h2 * 4 + qq), pk);
+          }
+      }
+      st_bar_sync(1, 32 * ST_EPI_WARPS);  // the whole 17 x 15 region is staged
+      // pooled block: 56 pooled pixels x 8 channel chunks
+      for (int i = et; i < ST_PH * ST_PW * 8; i += 32 * ST_EPI_WARPS) {
+        const int ch = i & 7, pp = i >> 3;
+        const int pyl = pp / ST_PW, pxl = pp - pyl * ST_PW;
+        uint4 m = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint4 val = st_lds128(stage + st_chunk(st_px_off(2 * pyl + dy, 2 * pxl + dx), ch));
+            m.x = st_max2(m.x, val.x);
+            m.y = st_max2(m.y, val.y);
+            m.z = st_max2(m.z, val.z);
+            m.w = st_max2(m.w, val.w);
+          }
+        st_sts128(stage + (uint32_t)(ST_OWNED_BYTES + ST_HALO_BYTES) + st_chunk((uint32_t)pp * 128u, ch), m);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->out_full[ob]);  // the buffer is restaged only after TMA has read it (out_empty)
+      if (++acc == 4) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+      if (++ob == 2) {
+        ob = 0;
+        oph ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == ST_LOAD_WARPS) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+size_t conv_stem_smem_bytes(const ConvStemParams& p) {
+  return (size_t)p.a_stages * ST_A_STAGE + 2 * ST_OUT_BUF + 64 * 128 + ST_RAW_RING * ST_RAW_BYTES + 1024 + 1024;
+}
+
+cudaError_t conv_stem_configure() {
+  return cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+void conv_stem_tiles(int Hc, int Wc, int* tiles_x, int* tiles_y) {
+  *tiles_x = (Wc / 2 + ST_PW - 1) / ST_PW;
+  *tiles_y = (Hc / 2 + ST_PH - 1) / ST_PH;
+}
+
+cudaError_t launch_conv_stem(const ConvStemParams& p0, int num_sms, cudaStream_t st) {
+  ConvStemParams p = p0;
+  const int64_t total = (int64_t)p.tiles_x * p.tiles_y * p.NB;
+  const int64_t dmax = p.tiles_x > p.tiles_y ? p.tiles_x : p.tiles_y;
+  if (total * dmax >= (1ll << 32)) return cudaErrorInvalidValue;  // FastDiv exactness bound
+  p.div_tx = make_fastdiv((uint32_t)p.tiles_x);
+  p.div_ty = make_fastdiv((uint32_t)p.tiles_y);
+  const int grid = total < num_sms ? (int)total : num_sms;
+  stem_pool_kernel<<<grid, ST_THREADS, conv_stem_smem_bytes(p), st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace vsb

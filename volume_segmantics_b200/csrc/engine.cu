@@ -100,6 +100,8 @@ struct ConvPlan {
   bool stem_tc = false;   // 7x7/2 single-channel stem on tensor cores (halo2 kernel, MODE 1)
   int pool_op = -1;       // stem: index of the MAXPOOL op fused into its epilogue (per workspace), or -1
   bool fused_away = false;  // MAXPOOL: computed by the preceding stem launch
+  bool use_stem2 = false;   // stem + pool by the in-CTA pooling kernel (conv_stem.cu), per workspace
+  vsb::ConvStemParams sparams{};
   bool halo2_ok = false, use_halo2 = false;  // cp.async-assembled halo (concat / up-sampled / narrow sources)
   vsb::ConvHalo2Params h2params{};
   // spatial-size dependent
@@ -156,6 +158,8 @@ struct vsb_engine {
   size_t arena_bytes = 0;
   bool keep_all = false;
   bool ws_keep = false;
+  float* d_gap_scratch = nullptr;  // fp32 partials of the two-phase global average pool
+  size_t gap_scratch_bytes = 0;
 
   int batch_override = 0;
   int conv_impl = 0;
@@ -164,6 +168,7 @@ struct vsb_engine {
   int halo_a_stages_max = 8;     // vsb_set_flag("halo_a_stages", n)
   bool sync_each = false;        // vsb_set_flag("sync_each", 1): synchronise after every op and name the one that failed
   bool no_fuse_pool = false;     // vsb_set_flag("fuse_pool", 0): separate max-pool kernel after the stem
+  bool no_stem2 = false;         // vsb_set_flag("stem_v2", 0): stem + pool by the red.global.max variant of conv_halo2_kernel
   int halo_ab_override = 0;      // vsb_set_flag("halo_ab", a*10+b): ring depths of streamed-weight launches (tuning aid)
   int halo_mt_max_bn = 128;      // vsb_set_flag("halo_mt_bn", n): largest BN that gets two tiles per stage
   bool no_halo_mt = false;       // vsb_set_flag("halo_mt", 1): one tile per stage in streamed-weight conv_halo launches
@@ -850,6 +855,30 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
           cp.pool_op = i + 1;
           h.pool_out = (uint16_t*)e->tens[nx.out].ptr;
           e->conv[i + 1].fused_away = true;
+          cp.use_stem2 = false;
+          if (!e->no_stem2 && !e->no_tma_epilogue && (ot.W & 1) == 0) {
+            // in-CTA pooling kernel: two TMA-store maps (conv output, pooled output)
+            if (!cp.d_maps) CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * 2 * VSB_MAX_SRC));
+            TmaDesc m2[2];
+            int rc = make_tensor_map(e, &m2[0], ot, nb, false, 64, 14, 16, 1);
+            if (rc) return rc;
+            rc = make_tensor_map(e, &m2[1], e->tens[nx.out], nb, false, 64, 7, 8, 1);
+            if (rc) return rc;
+            CK(cudaMemcpy(cp.d_maps + 2, m2, sizeof(m2), cudaMemcpyHostToDevice));
+            vsb::ConvStemParams& sp = cp.sparams;
+            sp = vsb::ConvStemParams{};
+            sp.in = (const uint16_t*)st.ptr;
+            sp.wpacked = cp.d_whalo;
+            sp.bias = cp.d_bias_pad;
+            sp.out_map = cp.d_maps + 2;
+            sp.pool_map = cp.d_maps + 3;
+            sp.NB = nb;
+            sp.H = ot.H;
+            sp.W = ot.W;
+            sp.a_stages = 3;
+            vsb::conv_stem_tiles(ot.H, ot.W, &sp.tiles_x, &sp.tiles_y);
+            cp.use_stem2 = true;
+          }
           if (!e->no_tma_epilogue) {
             if (!cp.d_maps) CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * 2 * VSB_MAX_SRC));
             TmaDesc m;
@@ -1142,6 +1171,14 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
     }
     return VSB_OK;
   }
+  if (cp.stem_tc && cp.use_stem2 && cp.pool_op >= 0 && e->conv_impl == 0 && !e->no_halo) {
+    vsb::ConvStemParams sp = cp.sparams;
+    sp.NB = nb;
+    sp.n_base = n0;
+    ProfScope ps(e, PC_STEM, oi);
+    CK(vsb::launch_conv_stem(sp, e->num_sms, e->stream));
+    return VSB_OK;
+  }
   if (cp.stem_tc && e->conv_impl == 0 && !e->no_halo) {
     vsb::ConvHalo2Params h = cp.h2params;
     h.NB = nb;
@@ -1267,16 +1304,26 @@ int run_op(vsb_engine* e, int i, int n0, int nb) {
     case VSB_OP_GAP: {
       const TensorBuf& s = e->tens[op.src[0]];
       const TensorBuf& o = e->tens[op.out];
-      ProfScope ps(e, PC_OTHER);
+      const size_t need = vsb::gap_scratch_bytes(nb, s.C);
+      if (need > e->gap_scratch_bytes) {
+        CK(cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_gap_scratch);
+        e->d_gap_scratch = nullptr;
+        e->gap_scratch_bytes = 0;
+        CK(cudaMalloc(&e->d_gap_scratch, need));
+        e->gap_scratch_bytes = need;
+      }
+      ProfScope ps(e, PC_OTHER, i);
+      e->launches += 1;  // two kernels: partial sums + finish
       vsb::launch_gap((const uint16_t*)s.ptr + (size_t)n0 * s.H * s.W * s.C, nb, s.H, s.W, s.C,
-                      (uint16_t*)o.ptr + (size_t)n0 * o.C, e->stream);
+                      (uint16_t*)o.ptr + (size_t)n0 * o.C, e->d_gap_scratch, e->stream);
       CK(cudaGetLastError());
       return VSB_OK;
     }
     case VSB_OP_UPSAMPLE: {
       const TensorBuf& s = e->tens[op.src[0]];
       const TensorBuf& o = e->tens[op.out];
-      ProfScope ps(e, PC_OTHER);
+      ProfScope ps(e, PC_OTHER, i);
       vsb::launch_upsample((const uint16_t*)s.ptr + (size_t)n0 * s.H * s.W * s.C, nb, s.H, s.W, s.C, o.H, o.W,
                            op.mode, (uint16_t*)o.ptr + (size_t)n0 * o.H * o.W * o.C, e->stream);
       CK(cudaGetLastError());
@@ -1473,6 +1520,7 @@ int vsb_create(int device, vsb_engine** out) {
   e->encode = (EncodeTiledFn)fn;
   CK(vsb::conv_tc_configure());
   CK(vsb::conv_halo_configure());
+  CK(vsb::conv_stem_configure());
   {
     // the slicer normalises with one FMA per pixel; it must reproduce the reference formula for all 256 inputs
     const int bad = vsb::slicer_norm_selfcheck(e->stream);
@@ -1521,6 +1569,7 @@ void vsb_destroy(vsb_engine* e) {
   free_plan(e);
   close_peers(e);
   cudaFree(e->d_vol_owned);
+  cudaFree(e->d_gap_scratch);
   cudaFree(e->d_raw);
   cudaFree(e->d_keys_owned);
   cudaFree(e->d_votes);
@@ -1828,6 +1877,7 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
   }
   else if (n == "sync_each") e->sync_each = value != 0;
   else if (n == "fuse_pool") { e->no_fuse_pool = value == 0; free_workspace(e); }
+  else if (n == "stem_v2") { e->no_stem2 = value == 0; free_workspace(e); }
   else if (n == "halo_ab") { e->halo_ab_override = value; free_workspace(e); }
   else if (n == "halo_mt_bn") { e->halo_mt_max_bn = value; free_workspace(e); }
   else if (n == "halo_mt") { e->no_halo_mt = value < 2; free_workspace(e); }

@@ -484,35 +484,113 @@ void launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------
-// Global average pool (smp ASPPPooling AdaptiveAvgPool2d(1) [ext]).
-// One block per (image, 64-channel group); fp32 accumulation.
+// Global average pool (smp ASPPPooling AdaptiveAvgPool2d(1) [ext]), two phases with a fixed
+// reduction order: (1) a block sums one of GAP_CHUNKS pixel ranges of one image for 8 channels
+// per thread (16-byte loads, a warp reads 512 contiguous bytes) into fp32 partials;
+// (2) the partials of a channel are added in chunk order and scaled by 1 / (H * W).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gap_kernel(const uint16_t* __restrict__ in, int H, int W,
-                                                  int C, uint16_t* __restrict__ out) {
-  __shared__ float red[4][64];
-  const int n = blockIdx.y, cg = blockIdx.x;
-  const int c = cg * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
-  float s = 0.f;
-  const int64_t hw = (int64_t)H * W;
-  if (c < C)
-    for (int64_t p = part; p < hw; p += 4) s += act_to_float(in[((int64_t)n * hw + p) * C + c]);
-  red[part][threadIdx.x & 63] = s;
+constexpr int GAP_CHUNKS = 32;
+__global__ void __launch_bounds__(256) gap_partial_kernel(const uint16_t* __restrict__ in, int64_t hw, int C,
+                                                          float* __restrict__ partial) {
+  // grid: (C / 8 / 32 rounded up, GAP_CHUNKS, NB); block: 32 channel-octets x 8 pixel lanes
+  const int oct = blockIdx.x * 32 + (threadIdx.x & 31), lanep = threadIdx.x >> 5;
+  const int chunk = blockIdx.y, n = blockIdx.z;
+  const int64_t p0 = hw * chunk / GAP_CHUNKS, p1 = hw * (chunk + 1) / GAP_CHUNKS;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (oct * 8 < C) {
+    const uint16_t* base = in + (int64_t)n * hw * C + oct * 8;
+    for (int64_t p = p0 + lanep; p < p1; p += 8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + p * C));
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_act2(w4[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+  }
+  __shared__ float red[8][32][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[lanep][threadIdx.x & 31][j] = acc[j];
   __syncthreads();
-  if (part == 0 && c < C) {
-    s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
-    out[(int64_t)n * C + c] = float_to_act(s / (float)hw);
+  if (lanep == 0 && oct * 8 < C) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += red[q][threadIdx.x][j];
+      partial[((int64_t)n * GAP_CHUNKS + chunk) * C + oct * 8 + j] = s;
+    }
   }
 }
-void launch_gap(const uint16_t* in, int NB, int H, int W, int C, uint16_t* out, cudaStream_t st) {
-  dim3 grid((C + 63) / 64, NB);
-  gap_kernel<<<grid, 256, 0, st>>>(in, H, W, C, out);
+__global__ void __launch_bounds__(256) gap_finish_kernel(const float* __restrict__ partial, int NB, int C, float inv_hw,
+                                                         uint16_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NB * C) return;
+  const int n = i / C, c = i - n * C;
+  float s = 0.f;
+  for (int q = 0; q < GAP_CHUNKS; ++q) s += partial[((int64_t)n * GAP_CHUNKS + q) * C + c];
+  out[i] = float_to_act(s * inv_hw);
+}
+size_t gap_scratch_bytes(int NB, int C) { return (size_t)NB * GAP_CHUNKS * C * sizeof(float); }
+void launch_gap(const uint16_t* in, int NB, int H, int W, int C, uint16_t* out, float* scratch, cudaStream_t st) {
+  dim3 grid((C / 8 + 31) / 32, GAP_CHUNKS, NB);
+  gap_partial_kernel<<<grid, 256, 0, st>>>(in, (int64_t)H * W, C, scratch);
+  gap_finish_kernel<<<(NB * C + 255) / 256, 256, 0, st>>>(scratch, NB, C, 1.0f / (float)((int64_t)H * W), out);
 }
 
-// Bilinear align_corners=True up-sampling (nn.UpsamplingBilinear2d [ext]) or
-// broadcast of a 1x1 map (bilinear interpolation of a single pixel).
+// Bilinear align_corners=True up-sampling (nn.UpsamplingBilinear2d [ext]) or broadcast of a
+// 1x1 map (bilinear interpolation of a single pixel).  One thread = one output pixel x 8
+// channels (16-byte loads and stores); the interpolation arithmetic per element is the scalar
+// formula (1-ly)*((1-lx)*v00 + lx*v01) + ly*((1-lx)*v10 + lx*v11) in fp32.
 __global__ void __launch_bounds__(256) upsample_kernel(const uint16_t* __restrict__ in, int NB,
                                                        int Hin, int Win, int C, int Hout, int Wout,
                                                        int mode, uint16_t* __restrict__ out) {
+  const int C8 = C >> 3;
+  const int64_t total = (int64_t)NB * Hout * Wout * C8;
+  const float sy = (Hout > 1) ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
+  const float sx = (Wout > 1) ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const int ox = (int)((i / C8) % Wout);
+    const int oy = (int)((i / ((int64_t)C8 * Wout)) % Hout);
+    const int64_t n = i / ((int64_t)C8 * Wout * Hout);
+    uint4 o;
+    if (mode == 1) {
+      o = __ldg(reinterpret_cast<const uint4*>(in + n * C + c8 * 8));
+    } else {
+      const float fy = sy * oy, fx = sx * ox;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = min(y0 + 1, Hin - 1), x1 = min(x0 + 1, Win - 1);
+      const float ly = fy - y0, lx = fx - x0;
+      const uint16_t* b = in + n * (int64_t)Hin * Win * C + c8 * 8;
+      const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(b + ((int64_t)y0 * Win + x0) * C));
+      const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(b + ((int64_t)y0 * Win + x1) * C));
+      const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(b + ((int64_t)y1 * Win + x0) * C));
+      const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(b + ((int64_t)y1 * Win + x1) * C));
+      const uint32_t a00[4] = {q00.x, q00.y, q00.z, q00.w}, a01[4] = {q01.x, q01.y, q01.z, q01.w};
+      const uint32_t a10[4] = {q10.x, q10.y, q10.z, q10.w}, a11[4] = {q11.x, q11.y, q11.z, q11.w};
+      uint32_t r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 v00 = unpack_act2(a00[j]), v01 = unpack_act2(a01[j]), v10 = unpack_act2(a10[j]), v11 = unpack_act2(a11[j]);
+        const float lo = (1.f - ly) * ((1.f - lx) * v00.x + lx * v01.x) + ly * ((1.f - lx) * v10.x + lx * v11.x);
+        const float hi = (1.f - ly) * ((1.f - lx) * v00.y + lx * v01.y) + ly * ((1.f - lx) * v10.y + lx * v11.y);
+        r[j] = pack_act2(lo, hi);
+      }
+      o = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = o;
+  }
+}
+// scalar fallback for channel counts that are not a multiple of 8
+__global__ void __launch_bounds__(256) upsample_scalar_kernel(const uint16_t* __restrict__ in, int NB,
+                                                              int Hin, int Win, int C, int Hout, int Wout,
+                                                              int mode, uint16_t* __restrict__ out) {
   const int64_t total = (int64_t)NB * Hout * Wout * C;
   const float sy = (Hout > 1) ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
   const float sx = (Wout > 1) ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
@@ -542,10 +620,12 @@ __global__ void __launch_bounds__(256) upsample_kernel(const uint16_t* __restric
 }
 void launch_upsample(const uint16_t* in, int NB, int Hin, int Win, int C, int Hout, int Wout,
                      int mode, uint16_t* out, cudaStream_t st) {
-  const int64_t total = (int64_t)NB * Hout * Wout * C;
+  const bool vec = (C & 7) == 0;
+  const int64_t total = (int64_t)NB * Hout * Wout * (vec ? C / 8 : C);
   const int64_t blocks = (total + 255) / 256;
   const int grid = (int)(blocks < 148 * 32 ? blocks : 148 * 32);
-  upsample_kernel<<<grid, 256, 0, st>>>(in, NB, Hin, Win, C, Hout, Wout, mode, out);
+  if (vec) upsample_kernel<<<grid, 256, 0, st>>>(in, NB, Hin, Win, C, Hout, Wout, mode, out);
+  else upsample_scalar_kernel<<<grid, 256, 0, st>>>(in, NB, Hin, Win, C, Hout, Wout, mode, out);
 }
 
 // ---------------------------------------------------------------------------

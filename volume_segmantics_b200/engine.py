@@ -68,9 +68,7 @@ class Engine:
         self._plan = plan
         self._plan_model = weakref.ref(model)
         self._plan_version = weights_version(model)
-        self.classes = plan.classes
-        self.shape = None
-        self.resident = None
+        self.classes = plan.classes  # (the resident volume and its residency token are independent of the plan)
 
     def ensure_model(self, model: B200SegmentationModel) -> None:
         """Re-lower unless `model` is the very module that was lowered last AND none of its
