@@ -46,14 +46,22 @@ class OracleEncoder(ResNet):
         if in_channels != 3:
             self.conv1 = nn.Conv2d(in_channels, 64, 7, 2, 3, bias=False)
 
-    def make_dilated_os16(self):
-        # smp `replace_strides_with_dilation(layer4, 2)`: EVERY Conv2d of layer4
-        for mod in self.layer4.modules():
+    def _dilate(self, layer, rate):
+        # smp `replace_strides_with_dilation(layer, rate)`: EVERY Conv2d of the stage
+        for mod in layer.modules():
             if isinstance(mod, nn.Conv2d):
                 mod.stride = (1, 1)
-                mod.dilation = (2, 2)
+                mod.dilation = (rate, rate)
                 kh, _ = mod.kernel_size
-                mod.padding = ((kh // 2) * 2, (kh // 2) * 2)
+                mod.padding = ((kh // 2) * rate, (kh // 2) * rate)
+
+    def make_dilated_os16(self):
+        self._dilate(self.layer4, 2)
+
+    def make_dilated_os8(self):
+        # smp DeepLabV3: encoder.make_dilated(stage_list=[4, 5], dilation_list=[2, 4])
+        self._dilate(self.layer3, 2)
+        self._dilate(self.layer4, 4)
 
     def forward(self, x):
         f1 = self.relu(self.bn1(self.conv1(x)))
@@ -170,13 +178,13 @@ class _ASPPPool(nn.Sequential):
 
 
 class _ASPP(nn.Module):
-    def __init__(self, cin, cout, rates):
+    def __init__(self, cin, cout, rates, separable=True):
         super().__init__()
         mods = [nn.Sequential(nn.Conv2d(cin, cout, 1, bias=False), nn.BatchNorm2d(cout), nn.ReLU())]
         for r in rates:
-            mods.append(
-                nn.Sequential(_separable(cin, cout, 3, r, r), nn.BatchNorm2d(cout), nn.ReLU())
-            )
+            # smp ASPPSeparableConv (DeepLabV3+) / ASPPConv (DeepLabV3): conv, BN, ReLU
+            conv = _separable(cin, cout, 3, r, r) if separable else nn.Conv2d(cin, cout, 3, padding=r, dilation=r, bias=False)
+            mods.append(nn.Sequential(conv, nn.BatchNorm2d(cout), nn.ReLU()))
         mods.append(_ASPPPool(cin, cout))
         self.convs = nn.ModuleList(mods)
         self.project = nn.Sequential(
@@ -211,8 +219,23 @@ class _DeepLabV3PlusDecoder(nn.Module):
         return self.block2(torch.cat([a, h], dim=1))
 
 
+class _DeepLabV3Decoder(nn.Sequential):
+    """smp DeepLabV3Decoder(nn.Sequential) [ext]: ASPP (plain atrous 3x3), conv3x3, BN, ReLU on the last feature."""
+
+    def __init__(self, cin, out_ch=256, rates=(12, 24, 36)):
+        super().__init__(
+            _ASPP(cin, out_ch, rates, separable=False),
+            nn.Conv2d(out_ch, out_ch, 3, padding=1, bias=False),
+            nn.BatchNorm2d(out_ch),
+            nn.ReLU(),
+        )
+
+    def forward(self, feats):
+        return super().forward(feats[-1])
+
+
 class OracleSegModel(nn.Module):
-    """``arch`` in {"unet", "unetplusplus", "deeplabv3plus"}."""
+    """``arch`` in {"unet", "unetplusplus", "deeplabv3plus", "deeplabv3"}."""
 
     def __init__(self, arch: str, encoder_name: str, classes: int, in_channels: int = 1):
         super().__init__()
@@ -231,6 +254,12 @@ class OracleSegModel(nn.Module):
             self.segmentation_head = nn.Sequential(
                 nn.Conv2d(256, classes, 1), nn.UpsamplingBilinear2d(scale_factor=4)
             )
+        elif arch == "deeplabv3":
+            self.encoder.make_dilated_os8()
+            self.decoder = _DeepLabV3Decoder(ch[-1])
+            self.segmentation_head = nn.Sequential(
+                nn.Conv2d(256, classes, 1), nn.UpsamplingBilinear2d(scale_factor=8)
+            )
         else:
             raise ValueError(arch)
 
@@ -243,6 +272,7 @@ ARCH_OF_MODELTYPE = {
     "U_NET": "unet",
     "U_NET_PLUS_PLUS": "unetplusplus",
     "DEEPLABV3_PLUS": "deeplabv3plus",
+    "DEEPLABV3": "deeplabv3",
 }
 
 

@@ -47,16 +47,33 @@ ncu)
   # only after the identical plain command exited 0
   echo "== ncu stem / b3.conv1 / conv_tc"
   timeout 300 python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_plain.log 2>&1 && \
-  timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k 'regex:conv_halo2_kernel<1' -s 1 -c 1 -f -o gpurun_out/r02_stem \
+  timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k 'regex:stem_pool_kernel' -s 1 -c 1 -f -o gpurun_out/r02_stem \
       python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_stem.log 2>&1
   echo "ncu stem rc=$?"
-  timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k 'regex:conv_halo2_kernel<0, 64, 2' -s 5 -c 1 -f -o gpurun_out/r02_b3conv1 \
+  timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k 'regex:conv_halo2_kernel<\(int\)0, \(int\)64, \(int\)2>' -s 5 -c 1 -f -o gpurun_out/r02_b3conv1 \
       python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_b3.log 2>&1
   echo "ncu b3 rc=$?"
-  timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k 'regex:conv_tc_kernel<128' -s 6 -c 2 -f -o gpurun_out/r02_convtc \
+  timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k 'regex:conv_tc_kernel' -s 6 -c 2 -f -o gpurun_out/r02_convtc \
       python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_convtc.log 2>&1
   echo "ncu conv_tc rc=$?"
   ls -la gpurun_out/*.ncu-rep | tail -5
+  ;;
+deeplab)
+  timeout 600 python tests/layer_profile.py 2048 32 0 DEEPLABV3_PLUS resnet50 4 > gpurun_out/r02_layers_deeplab.txt 2>&1; tail -3 gpurun_out/r02_layers_deeplab.txt
+  ;;
+multi)
+  # needs gpurun --gpus N (N >= 2)
+  N=$(nvidia-smi -L | wc -l); echo "== multi-GPU on $N GPUs"
+  timeout 1200 python -m pytest tests/test_multi_gpu.py -m gpu -q -s -p no:cacheprovider 2>&1 | tail -15 | tee gpurun_out/r02_multi_gpu_tests_${N}gpu.log
+  timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29711 bench.py --gpus $N --steps 2 --warmup 3 > gpurun_out/r02_bench_cfg3_${N}gpu.json 2> gpurun_out/r02_bench_cfg3_${N}gpu.err
+  echo "bench rc=$?"; tail -5 gpurun_out/r02_bench_cfg3_${N}gpu.err
+  python - $N <<'PY'
+import json,sys
+try:
+    d=json.loads(open(f'gpurun_out/r02_bench_cfg3_{sys.argv[1]}gpu.json').read().strip().splitlines()[-1])
+    print({k:d[k] for k in ('value','ms_per_step','gpu_launches','result_sha256')}, d['e2e'])
+except Exception as e: print('bench parse failed', e)
+PY
   ;;
 esac
 done

@@ -50,12 +50,13 @@ for L, (ms, n) in zip(spec.layers, times):
         tot_ms += ms
         print(f"{L.kind:38s} {t_in.channels:5d} {spec.tensors[L.out].channels:5d} - - {'1/' + str(2 ** ds) if ds >= 0 else '1x1':5s} {ms:8.3f} {0.0:8.1f} {by / ms / 1e6:7.0f} {n:6d}")
         continue
-    opx = px / 4 ** ds
+    opx = px / 4 ** ds if ds >= 0 else nslices
     if L.kind == "conv":
         fl = 2.0 * L.k * L.k * (L.cin // L.groups) * L.cout * opx
         by = 0
         for t, up in L.srcs:
-            by += spec.tensors[t].channels * 2 * px / 4 ** spec.tensors[t].ds_log2
+            tds = spec.tensors[t].ds_log2
+            by += spec.tensors[t].channels * 2 * (px / 4 ** tds if tds >= 0 else nslices)
         by += L.cout * (4 if spec.tensors[L.out].dtype else 2) * opx
         if L.res >= 0:
             by += L.cout * 2 * opx
@@ -63,6 +64,7 @@ for L, (ms, n) in zip(spec.layers, times):
         fl, by = 0, spec.tensors[L.srcs[0][0]].channels * 2 * px / 4 ** (ds - 1) * 1.25
     tot_ms += ms
     tot_fl += fl
-    print(f"{(L.name or L.kind):38s} {L.cin:5d} {L.cout:5d} {L.k} {L.stride} 1/{2**ds:<3d} {ms:8.3f} {fl / ms / 1e9:8.1f} {by / ms / 1e6:7.0f} {n:6d}")
+    res = f"1/{2 ** ds}" if ds >= 0 else "1x1"
+    print(f"{(L.name or L.kind):38s} {L.cin:5d} {L.cout:5d} {L.k} {L.stride} {res:5s} {ms:8.3f} {fl / ms / 1e9:8.1f} {by / ms / 1e6:7.0f} {n:6d}")
 print(f"total conv+pool ms {tot_ms:.2f}  ->  {tot_fl / tot_ms / 1e9:.1f} TFLOP/s ; per slice {tot_ms / nslices * 1e3:.1f} us")
 print({k: (round(v[0], 2), v[1]) for k, v in eng.stage_times().items()})

@@ -7,8 +7,8 @@ flat list of layer records over numbered activation tensors.  The same list
 file loads unchanged, and (2) is lowered -- after BatchNorm folding -- into the
 ``vsb_op`` table that libvsb200 executes (``plan.py``).
 
-Supported: Unet / UnetPlusPlus / DeepLabV3Plus decoders on ResNet-18/34/50/101
-and ResNeXt-50_32x4d encoders (BASELINE.json configs 1-5).
+Supported: Unet / UnetPlusPlus / DeepLabV3Plus (BASELINE.json configs 1-5) and DeepLabV3 decoders on
+ResNet-18/34/50/101 and ResNeXt-50_32x4d encoders.
 """
 from __future__ import annotations
 
@@ -122,8 +122,14 @@ class NetSpec:
 # ---------------------------------------------------------------------------
 # Encoders (torchvision ResNet trunk as wrapped by smp ResNetEncoder [ext])
 # ---------------------------------------------------------------------------
-def _encoder(net: NetSpec, name: str, dilate_layer4: bool = False):
-    """Returns the feature tensors [f1 (/2), f2 (/4), f3 (/8), f4 (/16), f5 (/32 or /16)]."""
+def _encoder(net: NetSpec, name: str, dilate_layer4: bool = False, dilations=None):
+    """Returns the feature tensors [f1 (/2), f2 (/4), f3 (/8), f4 (/16), f5 (/32 or /16)].
+    `dilations` {stage: rate} = smp `encoder.make_dilated(stage_list, dilation_list)` in ResNet stage
+    numbering (layer3 = 3, layer4 = 4): every Conv2d of the stage gets stride 1, dilation `rate`,
+    padding (k // 2) * rate."""
+    dilations = dict(dilations or {})
+    if dilate_layer4:
+        dilations[4] = 2
     if name not in ENCODER_CFG:
         raise ValueError(f"encoder {name!r} is not supported by the B200 engine; options: {sorted(ENCODER_CFG)}")
     kind, blocks, groups, wpg = ENCODER_CFG[name]
@@ -135,10 +141,10 @@ def _encoder(net: NetSpec, name: str, dilate_layer4: bool = False):
     for stage, (planes, nblk) in enumerate(zip((64, 128, 256, 512), blocks), start=1):
         stage_stride = 1 if stage == 1 else 2
         dil = 1
-        if stage == 4 and dilate_layer4:
-            # smp replace_strides_with_dilation: every conv of layer4 -> stride 1,
-            # dilation 2, padding (k // 2) * 2
-            stage_stride, dil = 1, 2
+        if stage in dilations:
+            # smp replace_strides_with_dilation: every conv of the stage -> stride 1,
+            # dilation r, padding (k // 2) * r
+            stage_stride, dil = 1, dilations[stage]
         for b in range(nblk):
             p = f"encoder.layer{stage}.{b}"
             stride = stage_stride if b == 0 else 1
@@ -244,8 +250,31 @@ def build_deeplabv3plus(encoder: str, classes: int, in_channels: int = 1) -> Net
     return net
 
 
+def build_deeplabv3(encoder: str, classes: int, in_channels: int = 1) -> NetSpec:
+    """smp.DeepLabV3 [ext]: encoder at output stride 8 (make_dilated(stage_list=[4, 5], dilation_list=[2, 4]) in smp's
+    stage numbering = layer3 dilation 2, layer4 dilation 4), DeepLabV3Decoder = Sequential(ASPP with plain 3x3 atrous
+    convolutions at rates 12 / 24 / 36, conv3x3 + BN + ReLU), head = conv1x1 + bilinear x8 (align_corners=True)."""
+    net = NetSpec("deeplabv3", encoder, classes, in_channels)
+    f = _encoder(net, encoder, dilations={3: 2, 4: 4})
+    top = f[-1]
+    a = "decoder.0"
+    branches = [net.conv(f"{a}.convs.0.0", [top], 256, 1, bn=f"{a}.convs.0.1", relu=True, init="decoder")]
+    for i, rate in enumerate((12, 24, 36), start=1):
+        branches.append(net.conv(f"{a}.convs.{i}.0", [top], 256, 3, pad=rate, dil=rate, bn=f"{a}.convs.{i}.1", relu=True,
+                                 init="decoder"))
+    pooled = net.gap(top)
+    pc = net.conv(f"{a}.convs.4.1", [pooled], 256, 1, bn=f"{a}.convs.4.2", relu=True, init="decoder")
+    branches.append(net.upsample(pc, net.tensors[top].ds_log2, mode=1))
+    proj = net.conv(f"{a}.project.0", branches, 256, 1, bn=f"{a}.project.1", relu=True, init="decoder")
+    y = net.conv("decoder.1", [proj], 256, 3, pad=1, bn="decoder.2", relu=True, init="decoder")
+    logits = net.conv("segmentation_head.0", [y], classes, 1, bias=True, init="head", out_dtype=1)
+    net.head(logits, factor=8)
+    return net
+
+
 BUILDERS = {
     "U_NET": build_unet,
+    "DEEPLABV3": build_deeplabv3,
     "U_NET_PLUS_PLUS": build_unetplusplus,
     "DEEPLABV3_PLUS": build_deeplabv3plus,
 }
