@@ -213,7 +213,10 @@ int vsb_set_conv_impl(vsb_engine* e, int32_t impl);
  *   "halo_a_stages" (8)   maximum depth of the halo ring, 2..8
  *   "halo2_tma" (1)       non-up-sampled sources of the cp.async halo kernel fetched by TMA; 0: by the loader warps
  *   "halo2_mma2" (0)      second MMA warp in the cp.async halo kernel (measured neutral)
- *   "fuse_pool" (1)       3x3/2 max-pool inside the stem's epilogue; 0: separate kernel
+ *   "fuse_pool" (1)       3x3/2 max-pool inside the stem's launch; 0: separate kernel
+ *   "stem" (3)            stem + pool kernel: 3 = raw input window read in place by shifted no-swizzle descriptors, pool
+ *                         computed inside the CTA; 2 = im2col rows built by loader warps, pool inside the CTA;
+ *                         1 = im2col + pooling by red.global.max into a zeroed tensor (round-1 kernel)
  *   "fuse_head" (0)       softmax/argmax/merge inside the last conv's epilogue (bit-identical, measured slower)
  *   "sub_batch_mb" (0)    L2 budget for depth-first sub-batches, 0 = off
  * Debugging aids: "sync_each" (synchronise after every op and name the one that failed), "halo_prof" (per-launch

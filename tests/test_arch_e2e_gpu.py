@@ -31,6 +31,10 @@ ARCHS = [
     ("U_NET_PLUS_PLUS", "unetplusplus", "resnext50_32x4d", 6, (20, 45, 70)),
     ("DEEPLABV3_PLUS", "deeplabv3plus", "resnet50", 4, (19, 70, 100)),
     ("U_NET", "unet", "resnet50", 2, (12, 33, 61)),
+    # the first of the remaining smp model types (model_2d.py:21-38), plain atrous ASPP at
+    # output stride 8, head bilinear x8 -- runs on the existing kernel classes
+    ("DEEPLABV3", "deeplabv3", "resnet34", 3, (14, 70, 100)),
+    ("DEEPLABV3", "deeplabv3", "resnet50", 2, (9, 45, 64)),
 ]
 
 

@@ -73,6 +73,8 @@ def test_model_file_roundtrip(tmp_path):
     ("U_NET", "unet", "resnet34", 2, 117808),
     ("U_NET_PLUS_PLUS", "unetplusplus", "resnext50_32x4d", 6, 878448),
     ("DEEPLABV3_PLUS", "deeplabv3plus", "resnet50", 4, 137948),
+    ("DEEPLABV3", "deeplabv3", "resnet34", 3, 415004),
+    ("DEEPLABV3", "deeplabv3", "resnet50", 3, 622364),
 ])
 def test_state_dict_keys_and_mac_counts(mt, arch, enc, c, macs):
     """smp key names == oracle key names; MAC/px equals SURVEY.md 8a-T."""
@@ -144,3 +146,38 @@ def test_key_packing_reproduces_first_max_rule():
     assert np.array_equal(got_l, lab[idx, np.arange(n)])
     assert np.array_equal(got_p, p16[idx, np.arange(n)])
     assert (keys < np.uint64(1) << np.uint64(63)).all()
+
+
+def test_weights_version_tracks_in_place_updates_and_new_modules():
+    """the plan key must change when weights are loaded / trained in place and must not
+    depend on id() (CPython reuses ids after garbage collection)."""
+    from volume_segmantics_b200.engine import weights_version
+
+    a = B200SegmentationModel("U_NET", "resnet34", 2)
+    v0 = weights_version(a)
+    assert weights_version(a) == v0
+    a.load_state_dict({k: t.clone() for k, t in a.state_dict().items()})
+    v1 = weights_version(a)
+    assert v1 != v0
+    with torch.no_grad():
+        next(a.parameters()).mul_(1.0)
+    assert weights_version(a) != v1
+    b = B200SegmentationModel("U_NET", "resnet34", 2)
+    assert weights_version(b) != weights_version(a)
+
+
+def test_in_channels_other_than_one_is_refused():
+    with pytest.raises(NotImplementedError, match="single-channel"):
+        B200SegmentationModel("U_NET", "resnet34", 2, in_channels=3)
+
+
+def test_unsupported_volume_dtypes_are_named():
+    from volume_segmantics_b200.host.predictor import _as_engine_volume
+
+    assert _as_engine_volume(np.zeros((2, 4, 4), np.uint16)).dtype == np.uint16
+    assert _as_engine_volume(np.zeros((2, 4, 4), np.int64)).dtype == np.int32
+    assert _as_engine_volume(np.zeros((2, 4, 4), np.float32)).dtype == np.float32
+    with pytest.raises(TypeError, match="float32"):
+        _as_engine_volume(np.zeros((2, 4, 4), np.float64))
+    with pytest.raises(ValueError, match="3-D"):
+        _as_engine_volume(np.zeros((4, 4), np.uint8))

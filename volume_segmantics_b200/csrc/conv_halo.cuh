@@ -150,16 +150,20 @@ struct ConvStemParams {
   const uint16_t* in;       // network input [NB, 2H, 2W] 16-bit (tensor 0)
   const uint8_t* wpacked;   // [64][128 B] SW128 rows: K index = ky * 8 + (kx + 1)
   const float* bias;        // [64]
-  const TmaDesc* out_map;   // conv output [NB, H, W, 64]: box {64, 14, 1, 16, 1}, SWIZZLE_128B
-  const TmaDesc* pool_map;  // pooled output [NB, H/2, W/2, 64]: box {64, 7, 1, 8, 1}, SWIZZLE_128B
+  int32_t version;          // 2: im2col by loader warps (stem_pool_kernel); 3: raw window read in place (stem_pool_v3_kernel)
+  // v2: conv output [NB, H, W, 64]: box {64, 14, 1, 16, 1}; pooled [NB, H/2, W/2, 64]: box {64, 7, 1, 8, 1}; SWIZZLE_128B
+  // v3: conv output viewed as (c, x / 4, x % 4, y, n): box {64, 8, 1, 14, 1}; pooled: box {64, 15, 1, 7, 1}; SWIZZLE_128B
+  const TmaDesc* out_map;
+  const TmaDesc* pool_map;
+  const TmaDesc* in_map;    // v3: network input as (x, y, n) 16-bit, box {64, 38, 1}, no swizzle, zero fill
   int32_t NB, H, W;         // conv output size
   int32_t n_base;
   int32_t tiles_x, tiles_y; // blocks of 8 x 7 pooled pixels
-  int32_t a_stages;         // 2..4 im2col stages of 32 KB
+  int32_t a_stages;         // v2: 2..4 im2col stages of 32 KB; v3: 2..3 window stages of 20 KB
   FastDiv div_tx, div_ty;   // set by the launcher
 };
 size_t conv_stem_smem_bytes(const ConvStemParams& p);
-void conv_stem_tiles(int Hc, int Wc, int* tiles_x, int* tiles_y);
+void conv_stem_tiles(int version, int Hc, int Wc, int* tiles_x, int* tiles_y);
 cudaError_t conv_stem_configure();
 cudaError_t launch_conv_stem(const ConvStemParams& p, int num_sms, cudaStream_t st);
 

@@ -364,17 +364,300 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_pool_kernel(const __grid_c
   }
 }
 
+// =====================================================================================
+// Stem v3: the same fused stem + pool WITHOUT an im2col pass.
+//
+// The A operand of tcgen05.mma may be any "K-major, no swizzle" arrangement of 8-row x 16-byte
+// core matrices: rows of a core matrix 16 bytes apart, core matrices LBO apart along K and SBO
+// apart along M.  For a stride-2, single-channel convolution the K chunk (filter row ky) of
+// output pixel cx is the 16 bytes  in[2*cy + ky - 3][2*cx - 4 .. 2*cx + 3]  -- so the chunks of the
+// output pixels cx, cx + 4, cx + 8, ... lie 16 bytes apart IN THE RAW IMAGE ROW.  Eight of them
+// are one core matrix = 128 contiguous bytes of one input row; the next filter row is the next
+// input row (LBO = row pitch) and the next output row two input rows further (SBO = 2 pitches).
+// One MMA (M = 128) therefore covers 16 output rows x 8 output pixels of one "phase"
+// r = cx mod 4, reading the raw window in place; the four phases need the window shifted by
+// 0 / 2 / 4 / 6 pixels so that every core matrix starts on a 16-byte boundary -- four TMA box
+// loads of the same 38 x 64-pixel window at shifted x coordinates (TMA zero-fills outside the
+// image = the convolution's zero padding).  No loader warps, no shared-memory traffic for A
+// besides TMA's writes: v2 was bound by the LSU wavefronts of its im2col (ncu: l1tex 75 %).
+//
+// A CTA tile is a 16 x 32 block of conv pixels (four phases x 128 rows, 256 TMEM columns):
+// conv rows [2*py0 - 1, 2*py0 + 15), columns [2*px0 - 1, 2*px0 + 31).  It yields the 7 x 15 pooled
+// pixels whose windows it contains and stores conv rows 1..14; columns are stored per phase (the
+// staging order [row][i] of a phase makes the epilogue's shared-memory stores conflict-free), all
+// 32 of them -- columns 0 and 31 duplicate the neighbour tiles' identical values.
+//   warp 0      TMA producer (4 boxes per tile) + weights     warp 1   MMA issuer (16 MMAs per tile)
+//   warp 2      TMA-store issuer (4 + 1 stores per tile)       warp 3   idle
+//   warps 4..11 epilogue: thread = (row, i) of two phases; bias, ReLU, pack, stage; 3x3 max
+// =====================================================================================
+namespace {
+constexpr int S3_PH = 7, S3_PW = 15;                 // pooled block
+constexpr int S3_ROWS = 16, S3_COLS = 32;            // conv region
+constexpr int S3_RAW_ROWS = 2 * (S3_ROWS - 1) + 8;   // 38 input rows (7 filter rows + the zero-weight 8th)
+constexpr int S3_COPY_BYTES = S3_RAW_ROWS * 128;     // 4864: one phase-shifted window, 64 px x 2 B per row
+constexpr int S3_A_STAGE = 20 * 1024;                // 4 copies (19456 B), 1024-aligned
+constexpr int S3_PHASE_STAGE = S3_ROWS * 8 * 128;    // 16 KB: staged conv pixels of one phase
+constexpr int S3_POOL_BYTES = 14 * 1024;             // 105 pooled pixels x 128 B (13440), 1024-aligned
+constexpr int S3_OUT_BUF = 4 * S3_PHASE_STAGE + S3_POOL_BYTES;  // 78 KB
+constexpr int S3_THREADS = 32 * 12;
+constexpr int S3_EPI_WARPS = 8;
+
+__device__ __forceinline__ uint64_t s3_desc_a(uint32_t addr) {  // K-major, no swizzle: LBO = 128 B, SBO = 256 B
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tma_load_3d_plain(const void* desc, uint64_t* bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// staged conv pixel (ry, rx) of a buffer: phase r = rx & 3, i = rx >> 2, row index ry * 8 + i inside the phase
+__device__ __forceinline__ uint32_t s3_px_off(int ry, int rx) {
+  return (uint32_t)(rx & 3) * S3_PHASE_STAGE + (uint32_t)(ry * 8 + (rx >> 2)) * 128u;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __grid_constant__ ConvStemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* a_ring = smem;                                          // a_stages x 20 KB
+  uint8_t* out_stage = a_ring + (size_t)p.a_stages * S3_A_STAGE;   // 2 x 78 KB
+  uint8_t* b_area = out_stage + 2 * S3_OUT_BUF;                    // 8 KB weights
+  StemCtl* ctl = reinterpret_cast<StemCtl*>(b_area + 64 * 128);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + 512);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.NB;
+  const int Hc = p.H, Wc = p.W;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.a_stages; ++i) {
+      mbar_init(&ctl->a_full[i], 1);
+      mbar_init(&ctl->a_empty[i], 1);
+    }
+    mbar_init(&ctl->w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->acc_full[i], 1);
+      mbar_init(&ctl->acc_empty[i], S3_EPI_WARPS);
+      mbar_init(&ctl->out_full[i], S3_EPI_WARPS);
+      mbar_init(&ctl->out_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+  if (warp == 1) tmem_alloc<512>(&ctl->tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  auto decode = [&](int t, int& px0, int& py0, int& n) {
+    auto fdiv = [](uint32_t v, const FastDiv& f) { return f.m ? __umulhi(v, f.m) : v; };
+    const uint32_t q = fdiv((uint32_t)t, p.div_tx);
+    const int tx = (int)((uint32_t)t - q * p.div_tx.d);
+    const uint32_t q2 = fdiv(q, p.div_ty);
+    const int ty = (int)(q - q2 * p.div_ty.d);
+    n = (int)q2 + p.n_base;
+    px0 = tx * S3_PW;
+    py0 = ty * S3_PH;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&ctl->w_full, 64 * 128);
+      bulk_load_1d(b_area, p.wpacked, 64 * 128, &ctl->w_full);
+      int as = 0;
+      uint32_t aph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int px0, py0, n;
+        decode(t, px0, py0, n);
+        mbar_wait(&ctl->a_empty[as], aph ^ 1);
+        mbar_arrive_expect_tx(&ctl->a_full[as], 4 * S3_COPY_BYTES);
+        const uint32_t dst = smem_u32(a_ring) + (uint32_t)as * S3_A_STAGE;
+        // phase r: window of output pixel rx = r starts at input column 2 * (2 * px0 - 1 + r) - 4
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          tma_load_3d_plain(p.in_map, &ctl->a_full[as], dst + r * S3_COPY_BYTES, 4 * px0 - 6 + 2 * r, 4 * py0 - 5, n);
+        if (++as == p.a_stages) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int as = 0, acc = 0;
+    uint32_t aph = 0, acc_phase = 0;
+    const uint32_t idesc = umma_idesc_act(128, 64);
+    const uint64_t a_desc0 = s3_desc_a(smem_u32(a_ring));
+    const uint64_t b_desc0 = st_desc(smem_u32(b_area));
+    mbar_wait(&ctl->w_full, 0);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      mbar_wait(&ctl->acc_empty[acc], acc_phase ^ 1);
+      mbar_wait(&ctl->a_full[as], aph);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t d0 = tmem_base + (uint32_t)acc * 256u;
+        const uint32_t a_units = (uint32_t)(as * S3_A_STAGE) >> 4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            // filter rows 2ks, 2ks + 1 = input rows +2ks, +2ks+1 of the window: 256 bytes further per K-step
+            const uint32_t a_off = a_units + (uint32_t)((r * S3_COPY_BYTES + ks * 256) >> 4);
+            umma_bf16_ss(d0 + (uint32_t)r * 64u, (a_desc0 & 0xffffffff00000000ull) | (uint32_t)((uint32_t)a_desc0 + a_off),
+                         (b_desc0 & 0xffffffff00000000ull) | (uint32_t)((uint32_t)b_desc0 + 2 * ks), idesc, ks != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&ctl->a_empty[as]);
+        umma_commit(&ctl->acc_full[acc]);
+      }
+      __syncwarp();
+      if (++as == p.a_stages) {
+        as = 0;
+        aph ^= 1;
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== TMA-store issuer =====================
+    if (lane == 0) {
+      int ob = 0;
+      uint32_t oph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int px0, py0, n;
+        decode(t, px0, py0, n);
+        mbar_wait(&ctl->out_full[ob], oph);
+        uint8_t* buf = out_stage + (size_t)ob * S3_OUT_BUF;
+        const int cx0 = 2 * px0 - 1, cy0 = 2 * py0 - 1;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int x = cx0 + r;                       // conv column of this phase's first pixel (may be -1)
+          const int xi = (x + 4) / 4 - 1, xr = x - 4 * xi;  // floor division
+          // rows 1..14 of the phase: 14 x 8 pixels, starting one staged row (8 x 128 B) into the phase
+          tma_store_5d(p.out_map, buf + r * S3_PHASE_STAGE + 8 * 128, 0, xr, xi, cy0 + 1, n);  // map dims (c, x % 4, x / 4, y, n)
+        }
+        tma_store_5d(p.pool_map, buf + 4 * S3_PHASE_STAGE, 0, px0, 0, py0, n);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(&ctl->out_empty[ob]);
+        if (++ob == 2) {
+          ob = 0;
+          oph ^= 1;
+        }
+      }
+      tma_store_wait_all<0>();
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue + pool =====================
+    const int ew = warp - 4;          // 0..7
+    const int quarter = warp & 3;     // TMEM lane quarter
+    const int pg = ew >> 2;           // phases 2*pg, 2*pg + 1
+    const int m = quarter * 32 + lane;
+    const int ry = m >> 3, i = m & 7;
+    const int et = ew * 32 + lane;    // 0..255
+    const uint32_t stage0 = smem_u32(out_stage);
+    int acc = 0, ob = 0;
+    uint32_t acc_phase = 0, oph = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int px0, py0, n;
+      decode(t, px0, py0, n);
+      const int cy = 2 * py0 - 1 + ry;
+      const bool row_ok = cy >= 0 && cy < Hc;
+      mbar_wait(&ctl->acc_full[acc], acc_phase);
+      tc_fence_after_sync();
+      mbar_wait(&ctl->out_empty[ob], oph ^ 1);  // TMA has read the previous tile out of this buffer
+      const uint32_t stage = stage0 + (uint32_t)ob * S3_OUT_BUF;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = 2 * pg + rr;
+        const int cx = 2 * px0 - 1 + r + 4 * i;
+        const bool valid = row_ok && cx >= 0 && cx < Wc;
+        const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + (uint32_t)r * 64u + ((uint32_t)(quarter * 32) << 16);
+        uint32_t v[2][32];
+        tmem_ld_32x32b_x32(taddr, v[0]);
+        tmem_ld_32x32b_x32(taddr + 32, v[1]);
+        tmem_ld_wait();
+        const uint32_t row_addr = stage + (uint32_t)r * S3_PHASE_STAGE + (uint32_t)m * 128u;  // m = ry * 8 + i
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h2 * 32 + qq * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h2 * 32 + qq * 8 + 4);
+              pk.x = pack2<true>(__uint_as_float(v[h2][qq * 8 + 0]) + b0.x, __uint_as_float(v[h2][qq * 8 + 1]) + b0.y);
+              pk.y = pack2<true>(__uint_as_float(v[h2][qq * 8 + 2]) + b0.z, __uint_as_float(v[h2][qq * 8 + 3]) + b0.w);
+              pk.z = pack2<true>(__uint_as_float(v[h2][qq * 8 + 4]) + b1.x, __uint_as_float(v[h2][qq * 8 + 5]) + b1.y);
+              pk.w = pack2<true>(__uint_as_float(v[h2][qq * 8 + 6]) + b1.z, __uint_as_float(v[h2][qq * 8 + 7]) + b1.w);
+            }
+            st_sts128(row_addr + ((uint32_t)((h2 * 4 + qq) ^ i) << 4), pk);  // SW128: chunk ^ (row index & 7), row index & 7 == i
+          }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->acc_empty[acc]);
+      st_bar_sync(1, 32 * S3_EPI_WARPS);  // the whole 16 x 32 region is staged
+      for (int it = et; it < S3_PH * S3_PW * 8; it += 32 * S3_EPI_WARPS) {
+        const int ch = it & 7, pp = it >> 3;
+        const int pyl = pp / S3_PW, pxl = pp - pyl * S3_PW;
+        uint4 mx = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const int wx = 2 * pxl + dx;
+            const uint4 val = st_lds128(stage + s3_px_off(2 * pyl + dy, wx) + ((uint32_t)(ch ^ (wx >> 2)) << 4));
+            mx.x = st_max2(mx.x, val.x);
+            mx.y = st_max2(mx.y, val.y);
+            mx.z = st_max2(mx.z, val.z);
+            mx.w = st_max2(mx.w, val.w);
+          }
+        st_sts128(stage + 4u * S3_PHASE_STAGE + (uint32_t)pp * 128u + ((uint32_t)(ch ^ (pp & 7)) << 4), mx);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->out_full[ob]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+      if (++ob == 2) {
+        ob = 0;
+        oph ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 size_t conv_stem_smem_bytes(const ConvStemParams& p) {
+  if (p.version == 3) return (size_t)p.a_stages * S3_A_STAGE + 2 * S3_OUT_BUF + 64 * 128 + 1024 + 1024;
   return (size_t)p.a_stages * ST_A_STAGE + 2 * ST_OUT_BUF + 64 * 128 + ST_RAW_RING * ST_RAW_BYTES + 1024 + 1024;
 }
 
 cudaError_t conv_stem_configure() {
-  return cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_pool_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  return e;
 }
 
-void conv_stem_tiles(int Hc, int Wc, int* tiles_x, int* tiles_y) {
-  *tiles_x = (Wc / 2 + ST_PW - 1) / ST_PW;
-  *tiles_y = (Hc / 2 + ST_PH - 1) / ST_PH;
+void conv_stem_tiles(int version, int Hc, int Wc, int* tiles_x, int* tiles_y) {
+  const int pw = version == 3 ? S3_PW : ST_PW, ph = version == 3 ? S3_PH : ST_PH;
+  *tiles_x = (Wc / 2 + pw - 1) / pw;
+  *tiles_y = (Hc / 2 + ph - 1) / ph;
 }
 
 cudaError_t launch_conv_stem(const ConvStemParams& p0, int num_sms, cudaStream_t st) {
@@ -385,7 +668,8 @@ cudaError_t launch_conv_stem(const ConvStemParams& p0, int num_sms, cudaStream_t
   p.div_tx = make_fastdiv((uint32_t)p.tiles_x);
   p.div_ty = make_fastdiv((uint32_t)p.tiles_y);
   const int grid = total < num_sms ? (int)total : num_sms;
-  stem_pool_kernel<<<grid, ST_THREADS, conv_stem_smem_bytes(p), st>>>(p);
+  if (p.version == 3) stem_pool_v3_kernel<<<grid, S3_THREADS, conv_stem_smem_bytes(p), st>>>(p);
+  else stem_pool_kernel<<<grid, ST_THREADS, conv_stem_smem_bytes(p), st>>>(p);
   return cudaGetLastError();
 }
 

@@ -168,7 +168,8 @@ struct vsb_engine {
   int halo_a_stages_max = 8;     // vsb_set_flag("halo_a_stages", n)
   bool sync_each = false;        // vsb_set_flag("sync_each", 1): synchronise after every op and name the one that failed
   bool no_fuse_pool = false;     // vsb_set_flag("fuse_pool", 0): separate max-pool kernel after the stem
-  bool no_stem2 = false;         // vsb_set_flag("stem_v2", 0): stem + pool by the red.global.max variant of conv_halo2_kernel
+  int stem_version = 3;          // vsb_set_flag("stem", v): 3 = raw window read in place (no im2col), 2 = im2col by loader warps,
+                                 // 1 = conv_halo2_kernel variant with red.global.max pooling
   int halo_ab_override = 0;      // vsb_set_flag("halo_ab", a*10+b): ring depths of streamed-weight launches (tuning aid)
   int halo_mt_max_bn = 128;      // vsb_set_flag("halo_mt_bn", n): largest BN that gets two tiles per stage
   bool no_halo_mt = false;       // vsb_set_flag("halo_mt", 1): one tile per stage in streamed-weight conv_halo launches
@@ -635,6 +636,21 @@ int make_tensor_map(vsb_engine* e, TmaDesc* out_host, const TensorBuf& t, int nb
   return VSB_OK;
 }
 
+// Tensor map with caller-chosen dimensions (16-bit elements): the stem's raw-window loads and its
+// phase-wise stores (conv_stem.cu, v3).  strides[i] = byte stride of dimension i + 1.
+int make_custom_map(vsb_engine* e, TmaDesc* out_host, void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                    const cuuint32_t* box, bool swizzle128) {
+  CUtensorMap m;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapDataType dt = VSB_ACT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUresult r = e->encode(&m, dt, (cuuint32_t)rank, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VSB_ERR_CUDA, "cuTensorMapEncodeTiled (custom, rank %d) failed (%d)", rank, (int)r);
+  memcpy(out_host, &m, sizeof(m));
+  return VSB_OK;
+}
+
 // Shared-memory epilogue + pipeline depth of one conv_halo launch.  `h` holds BN, n_tiles,
 // ncs, b_bytes, a_stage_bytes; decides out/res staging, accumulator stages, resident vs
 // streamed weights and the A / B ring depths inside the 227 KB of one SM.
@@ -856,27 +872,49 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
           h.pool_out = (uint16_t*)e->tens[nx.out].ptr;
           e->conv[i + 1].fused_away = true;
           cp.use_stem2 = false;
-          if (!e->no_stem2 && !e->no_tma_epilogue && (ot.W & 1) == 0) {
-            // in-CTA pooling kernel: two TMA-store maps (conv output, pooled output)
+          if (e->stem_version >= 2 && !e->no_tma_epilogue && (ot.W & 3) == 0) {
+            // in-CTA pooling kernels (conv_stem.cu): TMA-store maps of the conv output and the pooled output
             if (!cp.d_maps) CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * 2 * VSB_MAX_SRC));
-            TmaDesc m2[2];
-            int rc = make_tensor_map(e, &m2[0], ot, nb, false, 64, 14, 16, 1);
-            if (rc) return rc;
-            rc = make_tensor_map(e, &m2[1], e->tens[nx.out], nb, false, 64, 7, 8, 1);
-            if (rc) return rc;
-            CK(cudaMemcpy(cp.d_maps + 2, m2, sizeof(m2), cudaMemcpyHostToDevice));
+            const int ver = e->stem_version >= 3 ? 3 : 2;
+            TmaDesc m3[3];
+            memset(m3, 0, sizeof(m3));
+            int rc;
+            if (ver == 3) {
+              // conv output viewed as (c, x % 4, x / 4, y, n): one store per column phase
+              const cuuint64_t od[5] = {64, 4, (cuuint64_t)ot.W / 4, (cuuint64_t)ot.H, (cuuint64_t)nb};
+              const cuuint64_t os[4] = {128, 512, (cuuint64_t)ot.W * 128, (cuuint64_t)ot.H * ot.W * 128};
+              const cuuint32_t ob[5] = {64, 1, 8, 14, 1};
+              rc = make_custom_map(e, &m3[0], ot.ptr, 5, od, os, ob, true);
+              if (rc) return rc;
+              rc = make_tensor_map(e, &m3[1], e->tens[nx.out], nb, false, 64, 15, 7, 1);
+              if (rc) return rc;
+              // network input as (x, y, n): the raw window of a tile, zero-filled outside the image
+              const cuuint64_t id[3] = {(cuuint64_t)st.W, (cuuint64_t)st.H, (cuuint64_t)nb};
+              const cuuint64_t is[2] = {(cuuint64_t)st.W * 2, (cuuint64_t)st.H * st.W * 2};
+              const cuuint32_t ib[3] = {64, 38, 1};
+              rc = make_custom_map(e, &m3[2], st.ptr, 3, id, is, ib, false);
+              if (rc) return rc;
+            } else {
+              rc = make_tensor_map(e, &m3[0], ot, nb, false, 64, 14, 16, 1);
+              if (rc) return rc;
+              rc = make_tensor_map(e, &m3[1], e->tens[nx.out], nb, false, 64, 7, 8, 1);
+              if (rc) return rc;
+            }
+            CK(cudaMemcpy(cp.d_maps + 2, m3, sizeof(m3), cudaMemcpyHostToDevice));
             vsb::ConvStemParams& sp = cp.sparams;
             sp = vsb::ConvStemParams{};
+            sp.version = ver;
             sp.in = (const uint16_t*)st.ptr;
             sp.wpacked = cp.d_whalo;
             sp.bias = cp.d_bias_pad;
             sp.out_map = cp.d_maps + 2;
             sp.pool_map = cp.d_maps + 3;
+            sp.in_map = cp.d_maps + 4;
             sp.NB = nb;
             sp.H = ot.H;
             sp.W = ot.W;
             sp.a_stages = 3;
-            vsb::conv_stem_tiles(ot.H, ot.W, &sp.tiles_x, &sp.tiles_y);
+            vsb::conv_stem_tiles(ver, ot.H, ot.W, &sp.tiles_x, &sp.tiles_y);
             cp.use_stem2 = true;
           }
           if (!e->no_tma_epilogue) {
@@ -1877,7 +1915,7 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
   }
   else if (n == "sync_each") e->sync_each = value != 0;
   else if (n == "fuse_pool") { e->no_fuse_pool = value == 0; free_workspace(e); }
-  else if (n == "stem_v2") { e->no_stem2 = value == 0; free_workspace(e); }
+  else if (n == "stem") { e->stem_version = value; free_workspace(e); }
   else if (n == "halo_ab") { e->halo_ab_override = value; free_workspace(e); }
   else if (n == "halo_mt_bn") { e->halo_mt_max_bn = value; free_workspace(e); }
   else if (n == "halo_mt") { e->no_halo_mt = value < 2; free_workspace(e); }
