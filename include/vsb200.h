@@ -207,6 +207,7 @@ int vsb_set_conv_impl(vsb_engine* e, int32_t impl);
  * checks that the pipeline switches give bit-identical logits):
  *   "halo" (1)            halo-tile conv kernels; 0: per-tap TMA kernel everywhere
  *   "tma_epilogue" (1)    epilogue through shared memory + TMA store where weights stay resident; 0: per-thread stores
+ *   "tc_smem_epilogue" (1) the same for the per-tap kernel (1x1 and stride-2 convolutions); 0: per-thread stores
  *   "epi_groups" (1)      two epilogue groups on alternate tiles for BN <= 64; 0: one group
  *   "mma_warps" (2)       two MMA-issuing warps for resident-weight, one-slab launches; 1: one
  *   "halo_mt" (2)         two tiles per stage for streamed-weight launches with BN <= "halo_mt_bn" (128); 1: one

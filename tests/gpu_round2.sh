@@ -58,6 +58,12 @@ ncu)
   echo "ncu conv_tc rc=$?"
   ls -la gpurun_out/*.ncu-rep | tail -5
   ;;
+ncustem)
+  timeout 300 python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_plain.log 2>&1 && \
+  timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k 'regex:stem_pool' -s 1 -c 1 -f -o gpurun_out/r02_stem_v3 \
+      python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_stem.log 2>&1
+  echo "ncu stem rc=$?"
+  ;;
 deeplab)
   timeout 600 python tests/layer_profile.py 2048 32 0 DEEPLABV3_PLUS resnet50 4 > gpurun_out/r02_layers_deeplab.txt 2>&1; tail -3 gpurun_out/r02_layers_deeplab.txt
   ;;

@@ -26,7 +26,7 @@ def _inputs(shape=(2, 70, 100), seed=11):
 
 
 @pytest.mark.parametrize("flag,value", [("tma_epilogue", 0), ("mma_warps", 1), ("epi_groups", 0), ("fuse_pool", 0),
-                                        ("halo_a_stages", 2), ("halo2_mma2", 1), ("halo_mt", 1), ("halo2_tma", 0), ("stem", 2), ("stem", 1)])
+                                        ("halo_a_stages", 2), ("halo2_mma2", 1), ("halo_mt", 1), ("halo2_tma", 0), ("stem", 2), ("stem", 1), ("tc_smem_epilogue", 0)])
 def test_pipeline_switches_are_bit_identical(engine, unet_r34, flag, value):
     _, model = unet_r34
     x = _inputs()
@@ -36,7 +36,7 @@ def test_pipeline_switches_are_bit_identical(engine, unet_r34, flag, value):
         got = engine.forward_logits(model, x)
     finally:
         engine.set_flag(flag, {"tma_epilogue": 1, "mma_warps": 2, "epi_groups": 1, "fuse_pool": 1,
-                               "halo_a_stages": 8, "halo2_mma2": 0, "halo_mt": 2, "halo2_tma": 1, "stem": 3}[flag])
+                               "halo_a_stages": 8, "halo2_mma2": 0, "halo_mt": 2, "halo2_tma": 1, "stem": 3, "tc_smem_epilogue": 1}[flag])
     assert np.array_equal(got, want), f"{flag}={value}: max |diff| {np.abs(got - want).max()}"
 
 
@@ -94,3 +94,19 @@ def test_s2d_head_against_oracle_three_axes(engine, unet_r34):
     assert not bad.any() or (cb[-1] - cb[-2])[bad].max() < 2e-2  # margin clause
     print(f"[s2d head vs oracle] agreement {1 - bad.mean():.5f}")
     assert 1 - bad.mean() > 0.997  # random-init weights (near-ties everywhere): see tests/test_predictor_gpu.py
+
+
+@pytest.mark.parametrize("mt,arch,enc,classes", [("U_NET", "unet", "resnet50", 2), ("DEEPLABV3_PLUS", "deeplabv3plus", "resnet50", 4)])
+def test_per_tap_smem_epilogue_bit_identical_on_bottleneck_encoders(engine, mt, arch, enc, classes):
+    """Wide 1x1 convolutions with a residual (bottleneck conv3, downsample): TMA-store epilogue == direct epilogue."""
+    oracle = make_random_model(arch, enc, classes, seed=2)
+    model = B200SegmentationModel(mt, enc, classes)
+    model.load_state_dict(oracle.state_dict())
+    x = _inputs((3, 150, 200), 9)
+    want = engine.forward_logits(model, x)
+    engine.set_flag("tc_smem_epilogue", 0)
+    try:
+        got = engine.forward_logits(model, x)
+    finally:
+        engine.set_flag("tc_smem_epilogue", 1)
+    assert np.array_equal(got, want), f"max |diff| {np.abs(got - want).max()}"

@@ -156,10 +156,12 @@ struct ConvStemParams {
   const TmaDesc* out_map;
   const TmaDesc* pool_map;
   const TmaDesc* in_map;    // v3: network input as (x, y, n) 16-bit, box {64, 38, 1}, no swizzle, zero fill
+  const TmaDesc* out_map7;  // v3: as out_map with box {64, 1, 7, 14, 1} (phase 0 of the leftmost tiles)
   int32_t NB, H, W;         // conv output size
   int32_t n_base;
   int32_t tiles_x, tiles_y; // blocks of 8 x 7 pooled pixels
   int32_t a_stages;         // v2: 2..4 im2col stages of 32 KB; v3: 2..3 window stages of 20 KB
+  int32_t dbg;              // v3 bring-up only (results wrong): 1 no MMAs, 2 no TMA loads, 4 no TMA stores, 8 LBO / SBO swapped
   FastDiv div_tx, div_ty;   // set by the launcher
 };
 size_t conv_stem_smem_bytes(const ConvStemParams& p);

@@ -376,19 +376,23 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_pool_kernel(const __grid_c
 // input row (LBO = row pitch) and the next output row two input rows further (SBO = 2 pitches).
 // One MMA (M = 128) therefore covers 16 output rows x 8 output pixels of one "phase"
 // r = cx mod 4, reading the raw window in place; the four phases need the window shifted by
-// 0 / 2 / 4 / 6 pixels so that every core matrix starts on a 16-byte boundary -- four TMA box
-// loads of the same 38 x 64-pixel window at shifted x coordinates (TMA zero-fills outside the
-// image = the convolution's zero padding).  No loader warps, no shared-memory traffic for A
-// besides TMA's writes: v2 was bound by the LSU wavefronts of its im2col (ncu: l1tex 75 %).
+// 0 / 2 / 4 / 6 pixels so that every core matrix starts on a 16-byte boundary -- four copies of
+// the same 38 x 64-pixel window at shifted x positions.  TMA cannot make them: a tensor-map
+// coordinate whose byte offset in dimension 0 is not a multiple of 16 raises an illegal-instruction
+// fault (tests/micro/tma_plain_test.cu, measured on B200), so four loader warps issue cp.async
+// copies of 16 / 8 / 4 bytes -- whatever the phase's alignment allows -- with zero fill outside
+// the image (= the convolution's zero padding).  104 warp-level copy instructions per tile and no
+// shared-memory reads replace v2's im2col (700 LSU wavefronts per 224 pixels; ncu: l1tex 75 %).
 //
 // A CTA tile is a 16 x 32 block of conv pixels (four phases x 128 rows, 256 TMEM columns):
 // conv rows [2*py0 - 1, 2*py0 + 15), columns [2*px0 - 1, 2*px0 + 31).  It yields the 7 x 15 pooled
 // pixels whose windows it contains and stores conv rows 1..14; columns are stored per phase (the
 // staging order [row][i] of a phase makes the epilogue's shared-memory stores conflict-free), all
 // 32 of them -- columns 0 and 31 duplicate the neighbour tiles' identical values.
-//   warp 0      TMA producer (4 boxes per tile) + weights     warp 1   MMA issuer (16 MMAs per tile)
-//   warp 2      TMA-store issuer (4 + 1 stores per tile)       warp 3   idle
-//   warps 4..11 epilogue: thread = (row, i) of two phases; bias, ReLU, pack, stage; 3x3 max
+//   warps 0..3  loaders (cp.async, two tiles ahead)             warp 4   MMA issuer (16 MMAs per tile)
+//   warp 5      weights, then TMA-store issuer (4 + 1 stores per tile; TMA stores must not start at a
+//               negative coordinate either, see the shifted staging of the leftmost tiles)
+//   warps 6..13 epilogue: thread = (row, i) of two phases; bias, ReLU, pack, stage; 3x3 max
 // =====================================================================================
 namespace {
 constexpr int S3_PH = 7, S3_PW = 15;                 // pooled block
@@ -399,11 +403,13 @@ constexpr int S3_A_STAGE = 20 * 1024;                // 4 copies (19456 B), 1024
 constexpr int S3_PHASE_STAGE = S3_ROWS * 8 * 128;    // 16 KB: staged conv pixels of one phase
 constexpr int S3_POOL_BYTES = 14 * 1024;             // 105 pooled pixels x 128 B (13440), 1024-aligned
 constexpr int S3_OUT_BUF = 4 * S3_PHASE_STAGE + S3_POOL_BYTES;  // 78 KB
-constexpr int S3_THREADS = 32 * 12;
+constexpr int S3_LOAD_WARPS = 4;
 constexpr int S3_EPI_WARPS = 8;
+constexpr int S3_THREADS = 32 * (S3_LOAD_WARPS + 2 + S3_EPI_WARPS);
 
-__device__ __forceinline__ uint64_t s3_desc_a(uint32_t addr) {  // K-major, no swizzle: LBO = 128 B, SBO = 256 B
-  return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) | (1ull << 46);
+__device__ __forceinline__ uint64_t s3_desc_a(uint32_t addr, bool swap) {  // K-major, no swizzle: LBO = 128 B, SBO = 256 B
+  const uint64_t lbo = swap ? 256u : 128u, sbo = swap ? 128u : 256u;
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | ((lbo >> 4) << 16) | ((sbo >> 4) << 32) | (1ull << 46);
 }
 __device__ __forceinline__ void tma_load_3d_plain(const void* desc, uint64_t* bar, uint32_t dst, int c0, int c1, int c2) {
   asm volatile(
@@ -411,9 +417,10 @@ __device__ __forceinline__ void tma_load_3d_plain(const void* desc, uint64_t* ba
       "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// staged conv pixel (ry, rx) of a buffer: phase r = rx & 3, i = rx >> 2, row index ry * 8 + i inside the phase
-__device__ __forceinline__ uint32_t s3_px_off(int ry, int rx) {
-  return (uint32_t)(rx & 3) * S3_PHASE_STAGE + (uint32_t)(ry * 8 + (rx >> 2)) * 128u;
+// Phase 0 of the leftmost tiles (conv column -1 does not exist): pixels i = 1..7 of rows 1..14 are staged as a
+// dense 14 x 7 box at the start of the phase buffer (what its TMA store reads), rows 0 and 15 behind it.
+__device__ __forceinline__ int s3_row_shifted(int ry, int i) {
+  return (ry >= 1 && ry <= 14) ? (ry - 1) * 7 + (i - 1) : 98 + (ry == 0 ? 0 : 7) + (i - 1);
 }
 }  // namespace
 
@@ -433,7 +440,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __gri
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_stages; ++i) {
-      mbar_init(&ctl->a_full[i], 1);
+      mbar_init(&ctl->a_full[i], 32 * S3_LOAD_WARPS);
       mbar_init(&ctl->a_empty[i], 1);
     }
     mbar_init(&ctl->w_full, 1);
@@ -446,7 +453,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __gri
     fence_mbar_init();
   }
   if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias[threadIdx.x];
-  if (warp == 1) tmem_alloc<512>(&ctl->tmem_base);
+  if (warp == S3_LOAD_WARPS) tmem_alloc<512>(&ctl->tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -463,35 +470,76 @@ __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __gri
     py0 = ty * S3_PH;
   };
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&ctl->w_full, 64 * 128);
-      bulk_load_1d(b_area, p.wpacked, 64 * 128, &ctl->w_full);
-      int as = 0;
-      uint32_t aph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int px0, py0, n;
-        decode(t, px0, py0, n);
-        mbar_wait(&ctl->a_empty[as], aph ^ 1);
-        mbar_arrive_expect_tx(&ctl->a_full[as], 4 * S3_COPY_BYTES);
-        const uint32_t dst = smem_u32(a_ring) + (uint32_t)as * S3_A_STAGE;
-        // phase r: window of output pixel rx = r starts at input column 2 * (2 * px0 - 1 + r) - 4
+  if (warp < S3_LOAD_WARPS) {
+    // ===================== loaders: four phase-shifted copies of the raw window =====================
+    const int ptid = threadIdx.x;  // 0..127
+    const int Hin = 2 * Hc, Win = 2 * Wc;
+    const uint32_t ring = smem_u32(a_ring);
+    auto fetch = [&](int tt, int stage) {
+      if (tt < total_tiles && !(p.dbg & 2)) {
+        int px2, py2, n2;
+        decode(tt, px2, py2, n2);
+        const uint16_t* img = p.in + (int64_t)n2 * Hin * Win;
+        const int iy0 = 4 * py2 - 5;
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-          tma_load_3d_plain(p.in_map, &ctl->a_full[as], dst + r * S3_COPY_BYTES, 4 * px0 - 6 + 2 * r, 4 * py0 - 5, n);
-        if (++as == p.a_stages) {
-          as = 0;
-          aph ^= 1;
+        for (int r = 0; r < 4; ++r) {
+          // copy r: window of output pixel rx = r starts at input column 2 * (2 * px2 - 1 + r) - 4
+          const int ix0 = 4 * px2 - 6 + 2 * r;
+          const uint32_t dst0 = ring + (uint32_t)stage * S3_A_STAGE + (uint32_t)r * S3_COPY_BYTES;
+          const int al = (2 * ix0) & 15;  // byte alignment of the window start (rows are 16-byte aligned: Win % 8 == 0)
+          if (al == 0) {
+            for (int i = ptid; i < S3_RAW_ROWS * 8; i += 32 * S3_LOAD_WARPS) {
+              const int rr = i >> 3, cc = i & 7;
+              const int iy = iy0 + rr, ix = ix0 + 8 * cc;
+              const bool ok = iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+              const uint16_t* g = ok ? img + (int64_t)iy * Win + ix : p.in;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + rr * 128 + cc * 16), "l"(g), "r"(ok ? 16u : 0u) : "memory");
+            }
+          } else if (al == 8) {
+            for (int i = ptid; i < S3_RAW_ROWS * 16; i += 32 * S3_LOAD_WARPS) {
+              const int rr = i >> 4, cc = i & 15;
+              const int iy = iy0 + rr, ix = ix0 + 4 * cc;
+              const bool ok = iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+              const uint16_t* g = ok ? img + (int64_t)iy * Win + ix : p.in;
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst0 + rr * 128 + cc * 8), "l"(g), "r"(ok ? 8u : 0u) : "memory");
+            }
+          } else {
+            for (int i = ptid; i < S3_RAW_ROWS * 32; i += 32 * S3_LOAD_WARPS) {
+              const int rr = i >> 5, cc = i & 31;
+              const int iy = iy0 + rr, ix = ix0 + 2 * cc;
+              const bool ok = iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+              const uint16_t* g = ok ? img + (int64_t)iy * Win + ix : p.in;
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + rr * 128 + cc * 4), "l"(g), "r"(ok ? 4u : 0u) : "memory");
+            }
+          }
         }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // stage of the k-th tile of this CTA = k % a_stages; copies run two tiles ahead (a_stages >= 3)
+    int k = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
+      if (k == 0) {
+        fetch(t, 0);
+        fetch(t + (int)gridDim.x, 1 % p.a_stages);
+      }
+      {
+        const int k2 = k + 2, st2 = k2 % p.a_stages;
+        // the MMAs of the tile that used this stage last (k2 - a_stages) have completed
+        mbar_wait(&ctl->a_empty[st2], ((uint32_t)(k2 / p.a_stages) & 1u) ^ 1u);
+        fetch(t + 2 * (int)gridDim.x, st2);
+      }
+      asm volatile("cp.async.wait_group 2;" ::: "memory");  // this thread's copies of tile k have landed
+      fence_proxy_async_smem();
+      mbar_arrive(&ctl->a_full[k % p.a_stages]);
     }
-  } else if (warp == 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp == S3_LOAD_WARPS) {
     // ===================== MMA issuer =====================
     int as = 0, acc = 0;
     uint32_t aph = 0, acc_phase = 0;
     const uint32_t idesc = umma_idesc_act(128, 64);
-    const uint64_t a_desc0 = s3_desc_a(smem_u32(a_ring));
+    const uint64_t a_desc0 = s3_desc_a(smem_u32(a_ring), (p.dbg & 8) != 0);
     const uint64_t b_desc0 = st_desc(smem_u32(b_area));
     mbar_wait(&ctl->w_full, 0);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -502,7 +550,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __gri
         const uint32_t d0 = tmem_base + (uint32_t)acc * 256u;
         const uint32_t a_units = (uint32_t)(as * S3_A_STAGE) >> 4;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < ((p.dbg & 1) ? 0 : 4); ++r) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             // filter rows 2ks, 2ks + 1 = input rows +2ks, +2ks+1 of the window: 256 bytes further per K-step
@@ -524,9 +572,11 @@ __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __gri
         acc_phase ^= 1;
       }
     }
-  } else if (warp == 2) {
-    // ===================== TMA-store issuer =====================
+  } else if (warp == S3_LOAD_WARPS + 1) {
+    // ===================== weights, then TMA-store issuer =====================
     if (lane == 0) {
+      mbar_arrive_expect_tx(&ctl->w_full, 64 * 128);
+      bulk_load_1d(b_area, p.wpacked, 64 * 128, &ctl->w_full);
       int ob = 0;
       uint32_t oph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -535,14 +585,18 @@ __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __gri
         mbar_wait(&ctl->out_full[ob], oph);
         uint8_t* buf = out_stage + (size_t)ob * S3_OUT_BUF;
         const int cx0 = 2 * px0 - 1, cy0 = 2 * py0 - 1;
+        if (!(p.dbg & 4)) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int x = cx0 + r;                       // conv column of this phase's first pixel (may be -1)
-          const int xi = (x + 4) / 4 - 1, xr = x - 4 * xi;  // floor division
-          // rows 1..14 of the phase: 14 x 8 pixels, starting one staged row (8 x 128 B) into the phase
-          tma_store_5d(p.out_map, buf + r * S3_PHASE_STAGE + 8 * 128, 0, xr, xi, cy0 + 1, n);  // map dims (c, x % 4, x / 4, y, n)
+        for (int r = 0; r < ((p.dbg & 16) ? 0 : 4); ++r) {
+          const int x = cx0 + r;  // conv column of this phase's first pixel; -1 for phase 0 of the leftmost tiles
+          // rows 1..14 of the phase: 14 x 8 pixels, starting one staged row (8 x 128 B) into the phase.  TMA stores
+          // must not start at a negative coordinate (measured: the store never completes): the leftmost tiles stage
+          // phase 0 shifted by one pixel (column -1 does not exist) and store 7 pixels per row through a second map.
+          if (x < 0) tma_store_5d(p.out_map7, buf + r * S3_PHASE_STAGE, 0, 3, 0, cy0 + 1, n);
+          else tma_store_5d(p.out_map, buf + r * S3_PHASE_STAGE + 8 * 128, 0, x & 3, x >> 2, cy0 + 1, n);  // dims (c, x % 4, x / 4, y, n)
         }
-        tma_store_5d(p.pool_map, buf + 4 * S3_PHASE_STAGE, 0, px0, 0, py0, n);
+        if (!(p.dbg & 32)) tma_store_5d(p.pool_map, buf + 4 * S3_PHASE_STAGE, 0, px0, 0, py0, n);
+        }
         tma_store_commit();
         tma_store_wait_read<0>();
         mbar_arrive(&ctl->out_empty[ob]);
@@ -553,15 +607,31 @@ __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __gri
       }
       tma_store_wait_all<0>();
     }
-  } else if (warp >= 4) {
+  } else {
     // ===================== epilogue + pool =====================
-    const int ew = warp - 4;          // 0..7
+    // Epilogue: a warp owns one TMEM lane quarter (32 conv pixels per phase) and ONE HALF of the channels for all
+    // four phases, so its 32 bias values live in registers for the whole kernel (a float4 broadcast from shared
+    // memory costs four LSU wavefronts; ncu showed the bias reads as a third of this kernel's shared-memory traffic).
+    const int ew = warp - (S3_LOAD_WARPS + 2);  // 0..7
     const int quarter = warp & 3;     // TMEM lane quarter
-    const int pg = ew >> 2;           // phases 2*pg, 2*pg + 1
+    const int chalf = ew >> 2;        // channels 32 * chalf .. 32 * chalf + 31
     const int m = quarter * 32 + lane;
     const int ry = m >> 3, i = m & 7;
     const int et = ew * 32 + lane;    // 0..255
     const uint32_t stage0 = smem_u32(out_stage);
+    float bias_r[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bias_r[j] = bias_s[chalf * 32 + j];
+    // Pool: thread = (pooled column, 8-channel chunk, upper / lower half of the pooled rows); the 3-wide row maxima of
+    // 9 (or 7) consecutive conv rows are reduced in registers: 27 (21) loads for 4 (3) pooled pixels instead of 36 (27).
+    const int phalf = et >= 120 ? 1 : 0, pc = et - phalf * 120;
+    const int pxl = pc >> 3, pch = pc & 7;
+    uint32_t pcol[3];
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int wx = 2 * pxl + dx, slot = wx >> 2;
+      pcol[dx] = (uint32_t)(wx & 3) * S3_PHASE_STAGE + (uint32_t)slot * 128u + ((uint32_t)(pch ^ slot) << 4);
+    }
     int acc = 0, ob = 0;
     uint32_t acc_phase = 0, oph = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -569,57 +639,100 @@ __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __gri
       decode(t, px0, py0, n);
       const int cy = 2 * py0 - 1 + ry;
       const bool row_ok = cy >= 0 && cy < Hc;
+      const bool shift0 = px0 == 0;
       mbar_wait(&ctl->acc_full[acc], acc_phase);
       tc_fence_after_sync();
       mbar_wait(&ctl->out_empty[ob], oph ^ 1);  // TMA has read the previous tile out of this buffer
       const uint32_t stage = stage0 + (uint32_t)ob * S3_OUT_BUF;
+      const uint32_t tbase = tmem_base + (uint32_t)acc * 256u + (uint32_t)chalf * 32u + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int r = 2 * pg + rr;
-        const int cx = 2 * px0 - 1 + r + 4 * i;
-        const bool valid = row_ok && cx >= 0 && cx < Wc;
-        const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + (uint32_t)r * 64u + ((uint32_t)(quarter * 32) << 16);
+      for (int rp = 0; rp < 2; ++rp) {  // two phases per round: both TMEM loads in flight before the first is consumed
         uint32_t v[2][32];
-        tmem_ld_32x32b_x32(taddr, v[0]);
-        tmem_ld_32x32b_x32(taddr + 32, v[1]);
+        tmem_ld_32x32b_x32(tbase + (uint32_t)(2 * rp) * 64u, v[0]);
+        tmem_ld_32x32b_x32(tbase + (uint32_t)(2 * rp + 1) * 64u, v[1]);
         tmem_ld_wait();
-        const uint32_t row_addr = stage + (uint32_t)r * S3_PHASE_STAGE + (uint32_t)m * 128u;  // m = ry * 8 + i
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2)
+        for (int rr = 0; rr < 2; ++rr) {
+          const int r = 2 * rp + rr;
+          const int cx = 2 * px0 - 1 + r + 4 * i;
+          const bool valid = row_ok && cx >= 0 && cx < Wc;
+          // staged row of this pixel inside its phase: ry * 8 + i; phase 0 of the leftmost tiles is staged as the
+          // 7-pixel-wide box its store uses (s3_row_shifted)
+          const bool sh = r == 0 && shift0;
+          if (sh && i == 0) continue;  // conv column -1: outside the image
+          const int srow = sh ? s3_row_shifted(ry, i) : ry * 8 + i;
+          const uint32_t row_addr = stage + (uint32_t)r * S3_PHASE_STAGE + (uint32_t)srow * 128u;
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
             uint4 pk = make_uint4(0u, 0u, 0u, 0u);
             if (valid) {
-              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h2 * 32 + qq * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h2 * 32 + qq * 8 + 4);
-              pk.x = pack2<true>(__uint_as_float(v[h2][qq * 8 + 0]) + b0.x, __uint_as_float(v[h2][qq * 8 + 1]) + b0.y);
-              pk.y = pack2<true>(__uint_as_float(v[h2][qq * 8 + 2]) + b0.z, __uint_as_float(v[h2][qq * 8 + 3]) + b0.w);
-              pk.z = pack2<true>(__uint_as_float(v[h2][qq * 8 + 4]) + b1.x, __uint_as_float(v[h2][qq * 8 + 5]) + b1.y);
-              pk.w = pack2<true>(__uint_as_float(v[h2][qq * 8 + 6]) + b1.z, __uint_as_float(v[h2][qq * 8 + 7]) + b1.w);
+              pk.x = pack2<true>(__uint_as_float(v[rr][qq * 8 + 0]) + bias_r[qq * 8 + 0], __uint_as_float(v[rr][qq * 8 + 1]) + bias_r[qq * 8 + 1]);
+              pk.y = pack2<true>(__uint_as_float(v[rr][qq * 8 + 2]) + bias_r[qq * 8 + 2], __uint_as_float(v[rr][qq * 8 + 3]) + bias_r[qq * 8 + 3]);
+              pk.z = pack2<true>(__uint_as_float(v[rr][qq * 8 + 4]) + bias_r[qq * 8 + 4], __uint_as_float(v[rr][qq * 8 + 5]) + bias_r[qq * 8 + 5]);
+              pk.w = pack2<true>(__uint_as_float(v[rr][qq * 8 + 6]) + bias_r[qq * 8 + 6], __uint_as_float(v[rr][qq * 8 + 7]) + bias_r[qq * 8 + 7]);
             }
-            st_sts128(row_addr + ((uint32_t)((h2 * 4 + qq) ^ i) << 4), pk);  // SW128: chunk ^ (row index & 7), row index & 7 == i
+            st_sts128(row_addr + ((uint32_t)((chalf * 4 + qq) ^ (srow & 7)) << 4), pk);  // SW128: chunk ^ (staged row & 7)
           }
+        }
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->acc_empty[acc]);
       st_bar_sync(1, 32 * S3_EPI_WARPS);  // the whole 16 x 32 region is staged
-      for (int it = et; it < S3_PH * S3_PW * 8; it += 32 * S3_EPI_WARPS) {
-        const int ch = it & 7, pp = it >> 3;
-        const int pyl = pp / S3_PW, pxl = pp - pyl * S3_PW;
-        uint4 mx = make_uint4(0u, 0u, 0u, 0u);
+      const uint32_t pool_stage = stage + 4u * S3_PHASE_STAGE;
+      if (!shift0) {
+        if (et < 240) {
+          const int row0 = phalf ? 8 : 0, nrow = phalf ? 7 : 9;
+          uint4 h[9];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const int wx = 2 * pxl + dx;
-            const uint4 val = st_lds128(stage + s3_px_off(2 * pyl + dy, wx) + ((uint32_t)(ch ^ (wx >> 2)) << 4));
-            mx.x = st_max2(mx.x, val.x);
-            mx.y = st_max2(mx.y, val.y);
-            mx.z = st_max2(mx.z, val.z);
-            mx.w = st_max2(mx.w, val.w);
+          for (int q = 0; q < 9; ++q) {
+            if (q < nrow) {
+              const uint32_t ra = stage + (uint32_t)(row0 + q) * 1024u;
+              const uint4 a0 = st_lds128(ra + pcol[0]), a1 = st_lds128(ra + pcol[1]), a2 = st_lds128(ra + pcol[2]);
+              h[q].x = st_max2(st_max2(a0.x, a1.x), a2.x);
+              h[q].y = st_max2(st_max2(a0.y, a1.y), a2.y);
+              h[q].z = st_max2(st_max2(a0.z, a1.z), a2.z);
+              h[q].w = st_max2(st_max2(a0.w, a1.w), a2.w);
+            }
           }
-        st_sts128(stage + 4u * S3_PHASE_STAGE + (uint32_t)pp * 128u + ((uint32_t)(ch ^ (pp & 7)) << 4), mx);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (2 * j + 2 < nrow) {
+              uint4 mx;
+              mx.x = st_max2(st_max2(h[2 * j].x, h[2 * j + 1].x), h[2 * j + 2].x);
+              mx.y = st_max2(st_max2(h[2 * j].y, h[2 * j + 1].y), h[2 * j + 2].y);
+              mx.z = st_max2(st_max2(h[2 * j].z, h[2 * j + 1].z), h[2 * j + 2].z);
+              mx.w = st_max2(st_max2(h[2 * j].w, h[2 * j + 1].w), h[2 * j + 2].w);
+              const int pp = (phalf * 4 + j) * S3_PW + pxl;
+              st_sts128(pool_stage + (uint32_t)pp * 128u + ((uint32_t)(pch ^ (pp & 7)) << 4), mx);
+            }
+          }
+        }
+      } else {
+        // leftmost tiles: phase 0 is staged in the shifted 7-wide order (generic item loop)
+        for (int it = et; it < S3_PH * S3_PW * 8; it += 32 * S3_EPI_WARPS) {
+          const int ch = it & 7, pp = it >> 3;
+          const int pyl = pp / S3_PW, px_ = pp - pyl * S3_PW;
+          uint4 mx = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const int wx = 2 * px_ + dx;
+              int srow = (2 * pyl + dy) * 8 + (wx >> 2);
+              if ((wx & 3) == 0) {
+                if (wx == 0) continue;  // conv column -1: outside the image
+                srow = s3_row_shifted(2 * pyl + dy, wx >> 2);
+              }
+              const uint4 val = st_lds128(stage + (uint32_t)(wx & 3) * S3_PHASE_STAGE + (uint32_t)srow * 128u +
+                                          ((uint32_t)(ch ^ (srow & 7)) << 4));
+              mx.x = st_max2(mx.x, val.x);
+              mx.y = st_max2(mx.y, val.y);
+              mx.z = st_max2(mx.z, val.z);
+              mx.w = st_max2(mx.w, val.w);
+            }
+          st_sts128(pool_stage + (uint32_t)pp * 128u + ((uint32_t)(ch ^ (pp & 7)) << 4), mx);
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -637,7 +750,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __gri
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == S3_LOAD_WARPS) {
     tc_fence_after_sync();
     tmem_dealloc<512>(tmem_base);
   }

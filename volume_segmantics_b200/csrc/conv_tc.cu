@@ -34,6 +34,7 @@ struct SmemCtl {
   uint64_t empty[TC_MAX_STAGES];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
+  uint64_t res_full[2];
   uint32_t tmem_base;
   uint32_t pad[3];
 };
@@ -41,6 +42,19 @@ struct SmemCtl {
 constexpr int kCtlBytes = 1024;       // >= sizeof(SmemCtl)
 constexpr int kBiasBytes = 2048 * 4;  // bias for up to 2048 output channels
 constexpr int kRunBytes = TC_MAX_RUNS * (int)sizeof(TcRun);
+constexpr int kEpiBuf = 16384;  // one staged 64-channel group: 128 rows x 128 B (SW128)
+
+__device__ __forceinline__ void tc_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint4 tc_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void tc_sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int t, int& n_tile, int& X0,
                                             int& Y0, int& N0) {
@@ -65,7 +79,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* stages = smem;
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + (size_t)p.num_stages * p.stage_bytes);
+  const bool smem_epi = p.out_map != nullptr;
+  // staging of the shared-memory epilogue: 2 output + 2 residual buffers, 1024-aligned behind the ring
+  uint8_t* epi_stage = smem + (((size_t)p.num_stages * p.stage_bytes + 1023) & ~(size_t)1023);
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_epi ? epi_stage + (p.res_map ? 4 : 2) * kEpiBuf
+                                                     : smem + (size_t)p.num_stages * p.stage_bytes);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + kCtlBytes);
   TcRun* runs_s = reinterpret_cast<TcRun*>(reinterpret_cast<uint8_t*>(bias_s) + kBiasBytes);
 
@@ -81,6 +99,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->acc_full[i], 1);
       mbar_init(&ctl->acc_empty[i], 32 * TC_EPI_WARPS);
+      mbar_init(&ctl->res_full[i], 1);
     }
     fence_mbar_init();
   }
@@ -172,6 +191,107 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
         acc_phase ^= 1;
       }
     }
+  } else if (smem_epi) {
+    // ================= epilogue through shared memory + TMA store =================
+    // Work unit j = (tile, 64-channel group g); buffers alternate with j.  One barrier per unit:
+    //   TMEM load -> (residual group landed) -> bias / residual / ReLU / pack -> swizzled staging
+    //   -> [thread 0: the store that last used the OTHER buffer has been read] -> barrier
+    //   -> [thread 0: TMA store of unit j; residual load of unit j + 2 into the buffer just consumed].
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    const int et = (warp - 2) * 32 + lane;
+    const bool has_res = p.res_map != nullptr;
+    const int groups = p.BN >> 6;
+    const uint32_t out0 = smem_u32(epi_stage), res0 = out0 + 2 * kEpiBuf;
+    // residual prefetch cursor (thread 0 only)
+    int pf_t = blockIdx.x, pf_g = 0, pf_j = 0;
+    auto prefetch_res = [&]() {
+      if (pf_t >= total_tiles) return;
+      int n_tile, X0, Y0, N0;
+      decode_tile(p, pf_t, n_tile, X0, Y0, N0);
+      uint64_t* bar = &ctl->res_full[pf_j & 1];
+      mbar_arrive_expect_tx(bar, kEpiBuf);
+      tma_load_5d(p.res_map, bar, epi_stage + (2 + (pf_j & 1)) * kEpiBuf, p.cout_off + n_tile * p.BN + pf_g * 64, X0, 0, Y0,
+                  N0 + p.n_base);
+      ++pf_j;
+      if (++pf_g == groups) {
+        pf_g = 0;
+        pf_t += gridDim.x;
+      }
+    };
+    if (has_res && et == 0) {
+      prefetch_res();
+      prefetch_res();
+    }
+    int j = 0;
+    uint32_t rph[2] = {0, 0};
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n_tile, X0, Y0, N0;
+      decode_tile(p, t, n_tile, X0, Y0, N0);
+      const int ch0 = p.cout_off + n_tile * p.BN;
+      const float* bt = bias_s + ch0;
+      mbar_wait(&ctl->acc_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
+      for (int g = 0; g < groups; ++g, ++j) {
+        const int ob = j & 1;
+        const int c = g * 64 + half * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c, v);
+        tmem_ld_wait();
+        if (g == groups - 1) {  // the accumulator stage is free as soon as every thread has its last columns
+          tc_fence_before_sync();
+          mbar_arrive(&ctl->acc_empty[acc]);
+        }
+        if (has_res) {
+          mbar_wait(&ctl->res_full[ob], rph[ob]);
+          rph[ob] ^= 1;
+        }
+        const uint32_t ost = out0 + (uint32_t)ob * kEpiBuf + (uint32_t)row * 128u;
+        const uint32_t rst = res0 + (uint32_t)ob * kEpiBuf + (uint32_t)row * 128u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t off = (uint32_t)((half * 4 + q) ^ (row & 7)) << 4;
+          const float4 b0 = *reinterpret_cast<const float4*>(bt + c + q * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bt + c + q * 8 + 4);
+          float f0 = __uint_as_float(v[q * 8 + 0]) + b0.x, f1 = __uint_as_float(v[q * 8 + 1]) + b0.y;
+          float f2 = __uint_as_float(v[q * 8 + 2]) + b0.z, f3 = __uint_as_float(v[q * 8 + 3]) + b0.w;
+          float f4 = __uint_as_float(v[q * 8 + 4]) + b1.x, f5 = __uint_as_float(v[q * 8 + 5]) + b1.y;
+          float f6 = __uint_as_float(v[q * 8 + 6]) + b1.z, f7 = __uint_as_float(v[q * 8 + 7]) + b1.w;
+          if (has_res) {
+            const uint4 rv = tc_lds128(rst + off);
+            float2 r;
+            r = unpack_act2(rv.x); f0 += r.x; f1 += r.y;
+            r = unpack_act2(rv.y); f2 += r.x; f3 += r.y;
+            r = unpack_act2(rv.z); f4 += r.x; f5 += r.y;
+            r = unpack_act2(rv.w); f6 += r.x; f7 += r.y;
+          }
+          uint4 pk;
+          if (p.relu) {
+            pk.x = pack2<true>(f0, f1); pk.y = pack2<true>(f2, f3); pk.z = pack2<true>(f4, f5); pk.w = pack2<true>(f6, f7);
+          } else {
+            pk.x = pack2<false>(f0, f1); pk.y = pack2<false>(f2, f3); pk.z = pack2<false>(f4, f5); pk.w = pack2<false>(f6, f7);
+          }
+          tc_sts128(ost + off, pk);
+        }
+        fence_proxy_async_smem();
+        if (et == 0) tma_store_wait_read<0>();  // the store of unit j - 1 (other buffer) has been read out
+        tc_bar_sync(1, 32 * TC_EPI_WARPS);
+        if (et == 0) {
+          tma_store_5d(p.out_map, epi_stage + ob * kEpiBuf, ch0 + g * 64, X0, 0, Y0, N0 + p.n_base);
+          tma_store_commit();
+          if (has_res) prefetch_res();  // unit j + 2 reuses the residual buffer every thread has just finished with
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (et == 0) tma_store_wait_all<0>();
   } else {
     // ============================ epilogue ================================
     int acc = 0;
@@ -228,8 +348,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   }
 }
 
+size_t conv_tc_epilogue_bytes(bool with_residual) { return (size_t)(with_residual ? 4 : 2) * kEpiBuf + 1024; }
+
 size_t conv_tc_smem_bytes(const ConvTcParams& p) {
-  return (size_t)p.num_stages * p.stage_bytes + kCtlBytes + kBiasBytes + kRunBytes + 1024;
+  return (size_t)p.num_stages * p.stage_bytes + (p.out_map ? conv_tc_epilogue_bytes(p.res_map != nullptr) : 0) + kCtlBytes +
+         kBiasBytes + kRunBytes + 1024;
 }
 
 cudaError_t conv_tc_configure() {

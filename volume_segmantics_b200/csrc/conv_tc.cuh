@@ -56,6 +56,13 @@ struct ConvTcParams {
   int32_t num_stages;
   int32_t stage_bytes;        // A (128 rows) + B (BN rows) of row_bytes, 1024-aligned
   int32_t a_bytes;            // 128 * row_bytes
+  // Shared-memory epilogue (out_map != null; 16-bit output, one pixel class, cout % 64 == 0, BN % 64 == 0):
+  // a finished 64-channel group of the tile (bias, residual, ReLU, pack) is staged in a swizzled 16 KB buffer
+  // and written by ONE cp.async.bulk.tensor store; the residual group arrives the same way.  The per-thread
+  // 16-byte global accesses of the direct epilogue touch 32 different lines per warp instruction -- for the
+  // wide 1x1 convolutions of the bottleneck encoders (K = 64..512, N = 256..2048, HBM-bound) that was the limit.
+  const TmaDesc* out_map;     // box {64, bw, 1, bh, nt} over the output tensor
+  const TmaDesc* res_map;     // same box over the residual tensor, or null
 };
 
 constexpr int TC_EPI_WARPS = 8;
@@ -64,6 +71,7 @@ constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_MAX_RUNS = 128;
 
 size_t conv_tc_smem_bytes(const ConvTcParams& p);
+size_t conv_tc_epilogue_bytes(bool with_residual);  // staging of the shared-memory epilogue
 cudaError_t launch_conv_tc(const ConvTcParams& p, int num_sms, cudaStream_t st);
 cudaError_t conv_tc_configure();  // cudaFuncSetAttribute(max dynamic smem)
 

@@ -168,6 +168,9 @@ struct vsb_engine {
   int halo_a_stages_max = 8;     // vsb_set_flag("halo_a_stages", n)
   bool sync_each = false;        // vsb_set_flag("sync_each", 1): synchronise after every op and name the one that failed
   bool no_fuse_pool = false;     // vsb_set_flag("fuse_pool", 0): separate max-pool kernel after the stem
+  bool no_tc_smem_epilogue = false;  // vsb_set_flag("tc_smem_epilogue", 0): per-thread global stores in the per-tap kernel
+  bool no_dw_tiled = false;      // vsb_set_flag("dw_tiled", 0): one output per thread in the depthwise kernel
+  int stem_dbg = 0;              // vsb_set_flag("stem_dbg", bits): bring-up experiments of the v3 stem (results wrong)
   int stem_version = 3;          // vsb_set_flag("stem", v): 3 = raw window read in place (no im2col), 2 = im2col by loader warps,
                                  // 1 = conv_halo2_kernel variant with red.global.max pooling
   int halo_ab_override = 0;      // vsb_set_flag("halo_ab", a*10+b): ring depths of streamed-weight launches (tuning aid)
@@ -876,7 +879,7 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
             // in-CTA pooling kernels (conv_stem.cu): TMA-store maps of the conv output and the pooled output
             if (!cp.d_maps) CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * 2 * VSB_MAX_SRC));
             const int ver = e->stem_version >= 3 ? 3 : 2;
-            TmaDesc m3[3];
+            TmaDesc m3[4];
             memset(m3, 0, sizeof(m3));
             int rc;
             if (ver == 3) {
@@ -886,13 +889,17 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
               const cuuint32_t ob[5] = {64, 1, 8, 14, 1};
               rc = make_custom_map(e, &m3[0], ot.ptr, 5, od, os, ob, true);
               if (rc) return rc;
+              const cuuint32_t ob7[5] = {64, 1, 7, 14, 1};
+              rc = make_custom_map(e, &m3[3], ot.ptr, 5, od, os, ob7, true);
+              if (rc) return rc;
               rc = make_tensor_map(e, &m3[1], e->tens[nx.out], nb, false, 64, 15, 7, 1);
               if (rc) return rc;
               // network input as (x, y, n): the raw window of a tile, zero-filled outside the image
-              const cuuint64_t id[3] = {(cuuint64_t)st.W, (cuuint64_t)st.H, (cuuint64_t)nb};
-              const cuuint64_t is[2] = {(cuuint64_t)st.W * 2, (cuuint64_t)st.H * st.W * 2};
-              const cuuint32_t ib[3] = {64, 38, 1};
-              rc = make_custom_map(e, &m3[2], st.ptr, 3, id, is, ib, false);
+              const cuuint64_t img = (cuuint64_t)st.H * st.W * 2;
+              const cuuint64_t id[5] = {(cuuint64_t)st.W, (cuuint64_t)st.H, (cuuint64_t)nb, 1, 1};
+              const cuuint64_t is[4] = {(cuuint64_t)st.W * 2, img, img * nb, img * nb};
+              const cuuint32_t ib[5] = {64, 38, 1, 1, 1};
+              rc = make_custom_map(e, &m3[2], st.ptr, 5, id, is, ib, false);
               if (rc) return rc;
             } else {
               rc = make_tensor_map(e, &m3[0], ot, nb, false, 64, 14, 16, 1);
@@ -910,6 +917,7 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
             sp.out_map = cp.d_maps + 2;
             sp.pool_map = cp.d_maps + 3;
             sp.in_map = cp.d_maps + 4;
+            sp.out_map7 = cp.d_maps + 5;
             sp.NB = nb;
             sp.H = ot.H;
             sp.W = ot.W;
@@ -1129,6 +1137,29 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
         cp.use_halo = true;
       }
     }
+    // Per-tap kernel launches (1x1 and stride-2 convolutions): epilogue through shared memory + TMA store
+    // where the tile is a plain box of the output tensor (conv_tc.cuh)
+    p.out_map = p.res_map = nullptr;
+    if (!cp.use_halo && !cp.use_halo2 && !cp.grouped_s2 && !e->no_tc_smem_epilogue && !e->no_tma_epilogue && !cp.ps &&
+        ot.dtype == 0 && op.cout % 64 == 0 && cp.BN % 64 == 0 && cp.BN * cp.n_tiles == op.cout) {
+      const bool has_res = op.res >= 0;
+      const size_t budget = 206 * 1024 - vsb::conv_tc_epilogue_bytes(has_res);
+      const int stages = std::min<int>(vsb::TC_MAX_STAGES, (int)(budget / p.stage_bytes));
+      if (stages >= 2) {
+        TmaDesc m2[2];
+        memset(m2, 0, sizeof(m2));
+        int rc = make_tensor_map(e, &m2[0], ot, nb, false, 64, bw, bh, ntile);
+        if (rc) return rc;
+        if (has_res) {
+          rc = make_tensor_map(e, &m2[1], e->tens[op.res], nb, false, 64, bw, bh, ntile);
+          if (rc) return rc;
+        }
+        CK(cudaMemcpy(cp.d_maps + VSB_MAX_SRC, m2, sizeof(m2), cudaMemcpyHostToDevice));
+        p.out_map = cp.d_maps + VSB_MAX_SRC;
+        p.res_map = has_res ? cp.d_maps + VSB_MAX_SRC + 1 : nullptr;
+        p.num_stages = stages;
+      }
+    }
   }
   return VSB_OK;
 }
@@ -1213,6 +1244,7 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
     vsb::ConvStemParams sp = cp.sparams;
     sp.NB = nb;
     sp.n_base = n0;
+    sp.dbg = e->stem_dbg;
     ProfScope ps(e, PC_STEM, oi);
     CK(vsb::launch_conv_stem(sp, e->num_sms, e->stream));
     return VSB_OK;
@@ -1313,7 +1345,7 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
   if (cp.depthwise && e->conv_impl != 2) {
     a.weights = cp.d_whalo;
     ProfScope ps(e, PC_OTHER, oi);
-    vsb::launch_dwconv3x3(a, e->stream);
+    vsb::launch_dwconv3x3(a, e->stream, !e->no_dw_tiled);
     CK(cudaGetLastError());
     return VSB_OK;
   }
@@ -1916,6 +1948,9 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
   else if (n == "sync_each") e->sync_each = value != 0;
   else if (n == "fuse_pool") { e->no_fuse_pool = value == 0; free_workspace(e); }
   else if (n == "stem") { e->stem_version = value; free_workspace(e); }
+  else if (n == "stem_dbg") e->stem_dbg = value;
+  else if (n == "dw_tiled") e->no_dw_tiled = value == 0;
+  else if (n == "tc_smem_epilogue") { e->no_tc_smem_epilogue = value == 0; free_workspace(e); }
   else if (n == "halo_ab") { e->halo_ab_override = value; free_workspace(e); }
   else if (n == "halo_mt_bn") { e->halo_mt_max_bn = value; free_workspace(e); }
   else if (n == "halo_mt") { e->no_halo_mt = value < 2; free_workspace(e); }

@@ -60,7 +60,7 @@ void launch_stem7x7(const uint16_t* in, int NB, int Hin, int Win, const void* w_
 void launch_maxpool3x3s2(const uint16_t* in, int NB, int Hin, int Win, int C, uint16_t* out,
                          cudaStream_t st);
 void launch_conv_simt(const ConvArgs& a, cudaStream_t st);
-void launch_dwconv3x3(const ConvArgs& a, cudaStream_t st);  // a.weights = [9][C] repacked
+void launch_dwconv3x3(const ConvArgs& a, cudaStream_t st, bool tiled = true);  // a.weights = [9][C] repacked
 size_t gap_scratch_bytes(int NB, int C);  // fp32 partial sums of the two-phase global average pool
 void launch_gap(const uint16_t* in, int NB, int H, int W, int C, uint16_t* out, float* scratch, cudaStream_t st);
 void launch_upsample(const uint16_t* in, int NB, int Hin, int Win, int C, int Hout, int Wout,
