@@ -475,98 +475,99 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(ConvArgs a) {
 // instead of 36 -- which matters because every input pixel of the atrous branches (2048
 // channels, d = 12 / 24 / 36) is otherwise fetched nine times from L2 (measured 1.2 - 1.4 TB/s
 // algorithmic for the one-output-per-thread kernel above).
-__global__ void __launch_bounds__(256) dwconv3x3_tiled_kernel(ConvArgs a) {
-  const int C8 = a.cout >> 3, d = a.dil;
-  const int by_n = (a.H + 2 * d - 1) / (2 * d), bx_n = (a.W + 2 * d - 1) / (2 * d);
-  const int64_t rows = (int64_t)by_n * d, cols = (int64_t)bx_n * d;  // block origins per image
-  const int64_t total = (int64_t)a.NB * rows * cols * C8;
+// grid = (ceil(cols * C8 / 256), rows, NB): one division (by C8) per thread, everything else 32-bit
+__global__ void __launch_bounds__(256) dwconv3x3_tiled_kernel(ConvArgs a, int cols) {
+  const uint32_t C8 = (uint32_t)a.cout >> 3;
+  const int d = a.dil;
+  const uint32_t flat = blockIdx.x * 256u + threadIdx.x;
+  const uint32_t xo = flat / C8;
+  if (xo >= (uint32_t)cols) return;
+  const int c = (int)(flat - xo * C8) * 8;
+  const uint32_t yo = blockIdx.y, n = blockIdx.z;
+  // origin index -> (block, residue): x0 = 2 * d * bx + rx
+  const int x0 = (int)(xo / (uint32_t)d) * 2 * d + (int)(xo % (uint32_t)d), y0 = (int)(yo / (uint32_t)d) * 2 * d + (int)(yo % (uint32_t)d);
   const uint16_t* __restrict__ wt = (const uint16_t*)a.weights;  // [9][C]
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C8) * 8;
-    const int64_t xo = (i / C8) % cols;
-    const int64_t yo = (i / (C8 * cols)) % rows;
-    const int64_t n = i / (C8 * cols * rows);
-    // origin index -> (block, residue): x0 = 2 * d * bx + rx
-    const int x0 = (int)(xo / d) * 2 * d + (int)(xo % d), y0 = (int)(yo / d) * 2 * d + (int)(yo % d);
-    int s = 0, cb = 0;
-    while (s + 1 < a.n_src && c >= cb + a.src[s].C) cb += a.src[s++].C;
-    const SrcView& sv = a.src[s];
-    uint4 w[9];
+  int s = 0, cb = 0;
+  while (s + 1 < a.n_src && c >= cb + a.src[s].C) cb += a.src[s++].C;
+  const SrcView& sv = a.src[s];
+  uint4 w[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) w[t] = __ldg(reinterpret_cast<const uint4*>(wt + t * a.cout + c));
-    float acc[4][8];
+  for (int t = 0; t < 9; ++t) w[t] = __ldg(reinterpret_cast<const uint4*>(wt + t * a.cout + c));
+  float acc[4][8];
 #pragma unroll
-    for (int o = 0; o < 4; ++o)
+  for (int o = 0; o < 4; ++o)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[o][j] = a.bias ? a.bias[c + j] : 0.f;
-    const uint16_t* base = (const uint16_t*)sv.ptr + n * (int64_t)sv.H * sv.W * sv.C + (c - cb);
+    for (int j = 0; j < 8; ++j) acc[o][j] = a.bias ? a.bias[c + j] : 0.f;
+  const uint16_t* base = (const uint16_t*)sv.ptr + (size_t)n * sv.H * sv.W * sv.C + (c - cb);
+  const uint32_t pitch = (uint32_t)sv.W * (uint32_t)sv.C;  // elements per source row (< 2^31 for every supported shape)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int iy = y0 + (u - 1) * d;
-      if (iy < 0 || iy >= a.H) continue;
+  for (int u = 0; u < 4; ++u) {
+    const int iy = y0 + (u - 1) * d;
+    if (iy < 0 || iy >= a.H) continue;
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        const int ix = x0 + (v - 1) * d;
-        if (ix < 0 || ix >= a.W) continue;
-        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)iy * sv.W + ix) * sv.C));
-        const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
-        float xf[8];
+    for (int v = 0; v < 4; ++v) {
+      const int ix = x0 + (v - 1) * d;
+      if (ix < 0 || ix >= a.W) continue;
+      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)iy * pitch + (uint32_t)ix * (uint32_t)sv.C)));
+      const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      float xf[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_act2(xs[j]);
-          xf[2 * j] = f.x;
-          xf[2 * j + 1] = f.y;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_act2(xs[j]);
+        xf[2 * j] = f.x;
+        xf[2 * j + 1] = f.y;
+      }
 #pragma unroll
-        for (int oa = 0; oa < 2; ++oa) {
-          const int ky = u - oa;
-          if (ky < 0 || ky > 2) continue;
+      for (int oa = 0; oa < 2; ++oa) {
+        const int ky = u - oa;
+        if (ky < 0 || ky > 2) continue;
 #pragma unroll
-          for (int ob = 0; ob < 2; ++ob) {
-            const int kx = v - ob;
-            if (kx < 0 || kx > 2) continue;
-            const uint4 wv = w[ky * 3 + kx];
-            const uint32_t ws[4] = {wv.x, wv.y, wv.z, wv.w};
+        for (int ob = 0; ob < 2; ++ob) {
+          const int kx = v - ob;
+          if (kx < 0 || kx > 2) continue;
+          const uint4 wv = w[ky * 3 + kx];
+          const uint32_t ws[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 wf = unpack_act2(ws[j]);
-              acc[oa * 2 + ob][2 * j] = fmaf(xf[2 * j], wf.x, acc[oa * 2 + ob][2 * j]);
-              acc[oa * 2 + ob][2 * j + 1] = fmaf(xf[2 * j + 1], wf.y, acc[oa * 2 + ob][2 * j + 1]);
-            }
+          for (int j = 0; j < 4; ++j) {
+            const float2 wf = unpack_act2(ws[j]);
+            acc[oa * 2 + ob][2 * j] = fmaf(xf[2 * j], wf.x, acc[oa * 2 + ob][2 * j]);
+            acc[oa * 2 + ob][2 * j + 1] = fmaf(xf[2 * j + 1], wf.y, acc[oa * 2 + ob][2 * j + 1]);
           }
         }
       }
     }
-#pragma unroll
-    for (int oa = 0; oa < 2; ++oa)
-#pragma unroll
-      for (int ob = 0; ob < 2; ++ob) {
-        const int oy = y0 + oa * d, ox = x0 + ob * d;
-        if (oy >= a.H || ox >= a.W) continue;
-        float* r = acc[oa * 2 + ob];
-        if (a.relu) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) r[j] = fmaxf(r[j], 0.f);
-        }
-        uint4 pk;
-        pk.x = pack_act2(r[0], r[1]);
-        pk.y = pack_act2(r[2], r[3]);
-        pk.z = pack_act2(r[4], r[5]);
-        pk.w = pack_act2(r[6], r[7]);
-        *reinterpret_cast<uint4*>((uint16_t*)a.out + (((n * a.H + oy) * (int64_t)a.W + ox) * a.cout + c)) = pk;
-      }
   }
+  uint16_t* obase = (uint16_t*)a.out + (size_t)n * a.H * a.W * a.cout + c;
+#pragma unroll
+  for (int oa = 0; oa < 2; ++oa)
+#pragma unroll
+    for (int ob = 0; ob < 2; ++ob) {
+      const int oy = y0 + oa * d, ox = x0 + ob * d;
+      if (oy >= a.H || ox >= a.W) continue;
+      float* r = acc[oa * 2 + ob];
+      if (a.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = fmaxf(r[j], 0.f);
+      }
+      uint4 pk;
+      pk.x = pack_act2(r[0], r[1]);
+      pk.y = pack_act2(r[2], r[3]);
+      pk.z = pack_act2(r[4], r[5]);
+      pk.w = pack_act2(r[6], r[7]);
+      *reinterpret_cast<uint4*>(obase + ((size_t)oy * a.W + ox) * a.cout) = pk;
+    }
 }
 
 void launch_dwconv3x3(const ConvArgs& a, cudaStream_t st, bool tiled) {
   if (tiled && a.pad == a.dil) {
     const int d = a.dil;
-    const int64_t rows = (int64_t)((a.H + 2 * d - 1) / (2 * d)) * d, cols = (int64_t)((a.W + 2 * d - 1) / (2 * d)) * d;
-    const int64_t total = (int64_t)a.NB * rows * cols * (a.cout / 8);
-    const int64_t blocks = (total + 255) / 256;
-    dwconv3x3_tiled_kernel<<<(int)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, st>>>(a);
-    return;
+    const int rows = ((a.H + 2 * d - 1) / (2 * d)) * d, cols = ((a.W + 2 * d - 1) / (2 * d)) * d;  // block origins per image
+    const int64_t per_row = (int64_t)cols * (a.cout / 8);
+    if (rows <= 65535 && a.NB <= 65535 && per_row < (1ll << 31)) {
+      dim3 grid((unsigned)((per_row + 255) / 256), (unsigned)rows, (unsigned)a.NB);
+      dwconv3x3_tiled_kernel<<<grid, 256, 0, st>>>(a, cols);
+      return;
+    }
   }
   const int64_t total = (int64_t)a.NB * a.H * a.W * (a.cout / 8);
   const int64_t blocks = (total + 255) / 256;
@@ -643,46 +644,45 @@ void launch_gap(const uint16_t* in, int NB, int H, int W, int C, uint16_t* out, 
 // 1x1 map (bilinear interpolation of a single pixel).  One thread = one output pixel x 8
 // channels (16-byte loads and stores); the interpolation arithmetic per element is the scalar
 // formula (1-ly)*((1-lx)*v00 + lx*v01) + ly*((1-lx)*v10 + lx*v11) in fp32.
+// grid = (ceil(Wout * C8 / 256), Hout, NB)
 __global__ void __launch_bounds__(256) upsample_kernel(const uint16_t* __restrict__ in, int NB,
                                                        int Hin, int Win, int C, int Hout, int Wout,
                                                        int mode, uint16_t* __restrict__ out) {
-  const int C8 = C >> 3;
-  const int64_t total = (int64_t)NB * Hout * Wout * C8;
+  const uint32_t C8 = (uint32_t)C >> 3;
+  const uint32_t flat = blockIdx.x * 256u + threadIdx.x;
+  const uint32_t ox = flat / C8;
+  if (ox >= (uint32_t)Wout) return;
+  const uint32_t c8 = flat - ox * C8;
+  const int oy = blockIdx.y;
+  const size_t n = blockIdx.z;
   const float sy = (Hout > 1) ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
   const float sx = (Wout > 1) ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    const int ox = (int)((i / C8) % Wout);
-    const int oy = (int)((i / ((int64_t)C8 * Wout)) % Hout);
-    const int64_t n = i / ((int64_t)C8 * Wout * Hout);
-    uint4 o;
-    if (mode == 1) {
-      o = __ldg(reinterpret_cast<const uint4*>(in + n * C + c8 * 8));
-    } else {
-      const float fy = sy * oy, fx = sx * ox;
-      const int y0 = (int)fy, x0 = (int)fx;
-      const int y1 = min(y0 + 1, Hin - 1), x1 = min(x0 + 1, Win - 1);
-      const float ly = fy - y0, lx = fx - x0;
-      const uint16_t* b = in + n * (int64_t)Hin * Win * C + c8 * 8;
-      const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(b + ((int64_t)y0 * Win + x0) * C));
-      const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(b + ((int64_t)y0 * Win + x1) * C));
-      const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(b + ((int64_t)y1 * Win + x0) * C));
-      const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(b + ((int64_t)y1 * Win + x1) * C));
-      const uint32_t a00[4] = {q00.x, q00.y, q00.z, q00.w}, a01[4] = {q01.x, q01.y, q01.z, q01.w};
-      const uint32_t a10[4] = {q10.x, q10.y, q10.z, q10.w}, a11[4] = {q11.x, q11.y, q11.z, q11.w};
-      uint32_t r[4];
+  uint4 o;
+  if (mode == 1) {
+    o = __ldg(reinterpret_cast<const uint4*>(in + n * C + c8 * 8));
+  } else {
+    const float fy = sy * oy, fx = sx * ox;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = min(y0 + 1, Hin - 1), x1 = min(x0 + 1, Win - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const uint16_t* b = in + n * (size_t)Hin * Win * C + c8 * 8;
+    const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(b + ((size_t)y0 * Win + x0) * C));
+    const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(b + ((size_t)y0 * Win + x1) * C));
+    const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(b + ((size_t)y1 * Win + x0) * C));
+    const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(b + ((size_t)y1 * Win + x1) * C));
+    const uint32_t a00[4] = {q00.x, q00.y, q00.z, q00.w}, a01[4] = {q01.x, q01.y, q01.z, q01.w};
+    const uint32_t a10[4] = {q10.x, q10.y, q10.z, q10.w}, a11[4] = {q11.x, q11.y, q11.z, q11.w};
+    uint32_t r[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 v00 = unpack_act2(a00[j]), v01 = unpack_act2(a01[j]), v10 = unpack_act2(a10[j]), v11 = unpack_act2(a11[j]);
-        const float lo = (1.f - ly) * ((1.f - lx) * v00.x + lx * v01.x) + ly * ((1.f - lx) * v10.x + lx * v11.x);
-        const float hi = (1.f - ly) * ((1.f - lx) * v00.y + lx * v01.y) + ly * ((1.f - lx) * v10.y + lx * v11.y);
-        r[j] = pack_act2(lo, hi);
-      }
-      o = make_uint4(r[0], r[1], r[2], r[3]);
+    for (int j = 0; j < 4; ++j) {
+      const float2 v00 = unpack_act2(a00[j]), v01 = unpack_act2(a01[j]), v10 = unpack_act2(a10[j]), v11 = unpack_act2(a11[j]);
+      const float lo = (1.f - ly) * ((1.f - lx) * v00.x + lx * v01.x) + ly * ((1.f - lx) * v10.x + lx * v11.x);
+      const float hi = (1.f - ly) * ((1.f - lx) * v00.y + lx * v01.y) + ly * ((1.f - lx) * v10.y + lx * v11.y);
+      r[j] = pack_act2(lo, hi);
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = o;
+    o = make_uint4(r[0], r[1], r[2], r[3]);
   }
+  *reinterpret_cast<uint4*>(out + ((n * Hout + oy) * (size_t)Wout + ox) * C + c8 * 8) = o;
 }
 // scalar fallback for channel counts that are not a multiple of 8
 __global__ void __launch_bounds__(256) upsample_scalar_kernel(const uint16_t* __restrict__ in, int NB,
@@ -717,12 +717,16 @@ __global__ void __launch_bounds__(256) upsample_scalar_kernel(const uint16_t* __
 }
 void launch_upsample(const uint16_t* in, int NB, int Hin, int Win, int C, int Hout, int Wout,
                      int mode, uint16_t* out, cudaStream_t st) {
-  const bool vec = (C & 7) == 0;
-  const int64_t total = (int64_t)NB * Hout * Wout * (vec ? C / 8 : C);
+  const bool vec = (C & 7) == 0 && Hout <= 65535 && NB <= 65535;
+  if (vec) {
+    dim3 grid3((unsigned)(((int64_t)Wout * (C / 8) + 255) / 256), (unsigned)Hout, (unsigned)NB);
+    upsample_kernel<<<grid3, 256, 0, st>>>(in, NB, Hin, Win, C, Hout, Wout, mode, out);
+    return;
+  }
+  const int64_t total = (int64_t)NB * Hout * Wout * C;
   const int64_t blocks = (total + 255) / 256;
   const int grid = (int)(blocks < 148 * 32 ? blocks : 148 * 32);
-  if (vec) upsample_kernel<<<grid, 256, 0, st>>>(in, NB, Hin, Win, C, Hout, Wout, mode, out);
-  else upsample_scalar_kernel<<<grid, 256, 0, st>>>(in, NB, Hin, Win, C, Hout, Wout, mode, out);
+  upsample_scalar_kernel<<<grid, 256, 0, st>>>(in, NB, Hin, Win, C, Hout, Wout, mode, out);
 }
 
 // ---------------------------------------------------------------------------
