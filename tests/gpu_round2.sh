@@ -81,5 +81,21 @@ try:
 except Exception as e: print('bench parse failed', e)
 PY
   ;;
+multicfg)
+  # the other BASELINE configurations on N GPUs (gpurun --gpus N)
+  N=$(nvidia-smi -L | wc -l)
+  for c in cfg4 cfg5; do
+    echo "== bench $c on $N GPUs"
+    timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29721 bench.py --gpus $N --config $c --steps 2 --warmup 3 --no-cpu > gpurun_out/r02_bench_${c}_${N}gpu.json 2> gpurun_out/r02_bench_${c}_${N}gpu.err
+    echo "rc=$?"; tail -3 gpurun_out/r02_bench_${c}_${N}gpu.err
+    python - $c $N <<'PY'
+import json,sys
+try:
+    d=json.loads(open(f'gpurun_out/r02_bench_{sys.argv[1]}_{sys.argv[2]}gpu.json').read().strip().splitlines()[-1])
+    print({k:d[k] for k in ('value','ms_per_step','gpu_launches','result_sha256')}, d['e2e']['value'])
+except Exception as e: print('bench parse failed', e)
+PY
+  done
+  ;;
 esac
 done

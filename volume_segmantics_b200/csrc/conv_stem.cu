@@ -53,6 +53,7 @@ struct StemCtl {
   uint64_t acc_empty[4];
   uint64_t out_full[2];
   uint64_t out_empty[2];
+  uint64_t staged_full[2];  // v3: staging warps -> pooling warps
   uint32_t tmem_base;
   uint32_t pad[3];
 };
@@ -389,10 +390,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_pool_kernel(const __grid_c
 // pixels whose windows it contains and stores conv rows 1..14; columns are stored per phase (the
 // staging order [row][i] of a phase makes the epilogue's shared-memory stores conflict-free), all
 // 32 of them -- columns 0 and 31 duplicate the neighbour tiles' identical values.
-//   warps 0..3  loaders (cp.async, two tiles ahead)             warp 4   MMA issuer (16 MMAs per tile)
-//   warp 5      weights, then TMA-store issuer (4 + 1 stores per tile; TMA stores must not start at a
+//   warps 0..1  loaders (cp.async, two tiles ahead)             warp 2   MMA issuer (16 MMAs per tile)
+//   warp 3      weights, then TMA-store issuer (4 + 1 stores per tile; TMA stores must not start at a
 //               negative coordinate either, see the shifted staging of the leftmost tiles)
-//   warps 6..13 epilogue: thread = (row, i) of two phases; bias, ReLU, pack, stage; 3x3 max
+//   warps 4..11 staging: thread = (row, i) of all four phases x half of the channels; bias, ReLU, pack, stage
+//   warps 12..15 pooling: 3x3 max over the staged tile, one pipeline step behind the staging warps
 // =====================================================================================
 namespace {
 constexpr int S3_PH = 7, S3_PW = 15;                 // pooled block
@@ -403,9 +405,10 @@ constexpr int S3_A_STAGE = 20 * 1024;                // 4 copies (19456 B), 1024
 constexpr int S3_PHASE_STAGE = S3_ROWS * 8 * 128;    // 16 KB: staged conv pixels of one phase
 constexpr int S3_POOL_BYTES = 14 * 1024;             // 105 pooled pixels x 128 B (13440), 1024-aligned
 constexpr int S3_OUT_BUF = 4 * S3_PHASE_STAGE + S3_POOL_BYTES;  // 78 KB
-constexpr int S3_LOAD_WARPS = 4;
-constexpr int S3_EPI_WARPS = 8;
-constexpr int S3_THREADS = 32 * (S3_LOAD_WARPS + 2 + S3_EPI_WARPS);
+constexpr int S3_LOAD_WARPS = 2;
+constexpr int S3_EPI_WARPS = 8;    // TMEM -> bias / ReLU / pack -> staging
+constexpr int S3_POOL_WARPS = 4;   // 3x3 max over the staged tile of the PREVIOUS step of the pipeline
+constexpr int S3_THREADS = 32 * (S3_LOAD_WARPS + 2 + S3_EPI_WARPS + S3_POOL_WARPS);
 
 __device__ __forceinline__ uint64_t s3_desc_a(uint32_t addr, bool swap) {  // K-major, no swizzle: LBO = 128 B, SBO = 256 B
   const uint64_t lbo = swap ? 256u : 128u, sbo = swap ? 128u : 256u;
@@ -447,7 +450,8 @@ __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __gri
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->acc_full[i], 1);
       mbar_init(&ctl->acc_empty[i], S3_EPI_WARPS);
-      mbar_init(&ctl->out_full[i], S3_EPI_WARPS);
+      mbar_init(&ctl->staged_full[i], S3_EPI_WARPS);
+      mbar_init(&ctl->out_full[i], S3_POOL_WARPS);
       mbar_init(&ctl->out_empty[i], 1);
     }
     fence_mbar_init();
@@ -607,31 +611,20 @@ __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __gri
       }
       tma_store_wait_all<0>();
     }
-  } else {
-    // ===================== epilogue + pool =====================
-    // Epilogue: a warp owns one TMEM lane quarter (32 conv pixels per phase) and ONE HALF of the channels for all
-    // four phases, so its 32 bias values live in registers for the whole kernel (a float4 broadcast from shared
-    // memory costs four LSU wavefronts; ncu showed the bias reads as a third of this kernel's shared-memory traffic).
+  } else if (warp < S3_LOAD_WARPS + 2 + S3_EPI_WARPS) {
+    // ===================== staging warps: TMEM -> bias, ReLU, 16-bit -> swizzled tile =====================
+    // A warp owns one TMEM lane quarter (32 conv pixels per phase) and ONE HALF of the channels for all four phases,
+    // so its 32 bias values live in registers for the whole kernel (a float4 broadcast from shared memory costs four
+    // LSU wavefronts; ncu showed the bias reads as a third of the first version's shared-memory traffic).
     const int ew = warp - (S3_LOAD_WARPS + 2);  // 0..7
     const int quarter = warp & 3;     // TMEM lane quarter
     const int chalf = ew >> 2;        // channels 32 * chalf .. 32 * chalf + 31
     const int m = quarter * 32 + lane;
     const int ry = m >> 3, i = m & 7;
-    const int et = ew * 32 + lane;    // 0..255
     const uint32_t stage0 = smem_u32(out_stage);
     float bias_r[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) bias_r[j] = bias_s[chalf * 32 + j];
-    // Pool: thread = (pooled column, 8-channel chunk, upper / lower half of the pooled rows); the 3-wide row maxima of
-    // 9 (or 7) consecutive conv rows are reduced in registers: 27 (21) loads for 4 (3) pooled pixels instead of 36 (27).
-    const int phalf = et >= 120 ? 1 : 0, pc = et - phalf * 120;
-    const int pxl = pc >> 3, pch = pc & 7;
-    uint32_t pcol[3];
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int wx = 2 * pxl + dx, slot = wx >> 2;
-      pcol[dx] = (uint32_t)(wx & 3) * S3_PHASE_STAGE + (uint32_t)slot * 128u + ((uint32_t)(pch ^ slot) << 4);
-    }
     int acc = 0, ob = 0;
     uint32_t acc_phase = 0, oph = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -676,41 +669,74 @@ __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __gri
         }
       }
       tc_fence_before_sync();
+      fence_proxy_async_smem();  // the staged pixels are read by TMA (store) as well as by the pooling warps
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->acc_empty[acc]);
-      st_bar_sync(1, 32 * S3_EPI_WARPS);  // the whole 16 x 32 region is staged
+      if (lane == 0) {
+        mbar_arrive(&ctl->acc_empty[acc]);
+        mbar_arrive(&ctl->staged_full[ob]);
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+      if (++ob == 2) {
+        ob = 0;
+        oph ^= 1;
+      }
+    }
+  } else {
+    // ===================== pooling warps: 3x3 / stride 2 max over the staged tile =====================
+    // One tile behind the staging warps (they already fill the other buffer).  Thread = (pooled column, 8-channel
+    // chunk): the 3-wide row maxima of the 15 conv rows are reduced in registers, 45 loads for 7 pooled pixels.
+    const int et = (warp - (S3_LOAD_WARPS + 2 + S3_EPI_WARPS)) * 32 + lane;  // 0..127
+    const uint32_t stage0 = smem_u32(out_stage);
+    const int pxl = et >> 3, pch = et & 7;  // et < 120 active
+    uint32_t pcol[3];
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int wx = 2 * pxl + dx, slot = wx >> 2;
+      pcol[dx] = (uint32_t)(wx & 3) * S3_PHASE_STAGE + (uint32_t)slot * 128u + ((uint32_t)(pch ^ slot) << 4);
+    }
+    int ob = 0;
+    uint32_t sph = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int px0, py0, n;
+      decode(t, px0, py0, n);
+      const bool shift0 = px0 == 0;
+      mbar_wait(&ctl->staged_full[ob], sph);
+      const uint32_t stage = stage0 + (uint32_t)ob * S3_OUT_BUF;
       const uint32_t pool_stage = stage + 4u * S3_PHASE_STAGE;
       if (!shift0) {
-        if (et < 240) {
-          const int row0 = phalf ? 8 : 0, nrow = phalf ? 7 : 9;
-          uint4 h[9];
+        if (et < S3_PW * 8) {
+          uint4 h0, h1, h2;  // row maxima of conv rows 2j, 2j + 1, 2j + 2
+          auto rowmax = [&](int q) {
+            const uint32_t ra = stage + (uint32_t)q * 1024u;
+            const uint4 a0 = st_lds128(ra + pcol[0]), a1 = st_lds128(ra + pcol[1]), a2 = st_lds128(ra + pcol[2]);
+            uint4 h;
+            h.x = st_max2(st_max2(a0.x, a1.x), a2.x);
+            h.y = st_max2(st_max2(a0.y, a1.y), a2.y);
+            h.z = st_max2(st_max2(a0.z, a1.z), a2.z);
+            h.w = st_max2(st_max2(a0.w, a1.w), a2.w);
+            return h;
+          };
+          h0 = rowmax(0);
 #pragma unroll
-          for (int q = 0; q < 9; ++q) {
-            if (q < nrow) {
-              const uint32_t ra = stage + (uint32_t)(row0 + q) * 1024u;
-              const uint4 a0 = st_lds128(ra + pcol[0]), a1 = st_lds128(ra + pcol[1]), a2 = st_lds128(ra + pcol[2]);
-              h[q].x = st_max2(st_max2(a0.x, a1.x), a2.x);
-              h[q].y = st_max2(st_max2(a0.y, a1.y), a2.y);
-              h[q].z = st_max2(st_max2(a0.z, a1.z), a2.z);
-              h[q].w = st_max2(st_max2(a0.w, a1.w), a2.w);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (2 * j + 2 < nrow) {
-              uint4 mx;
-              mx.x = st_max2(st_max2(h[2 * j].x, h[2 * j + 1].x), h[2 * j + 2].x);
-              mx.y = st_max2(st_max2(h[2 * j].y, h[2 * j + 1].y), h[2 * j + 2].y);
-              mx.z = st_max2(st_max2(h[2 * j].z, h[2 * j + 1].z), h[2 * j + 2].z);
-              mx.w = st_max2(st_max2(h[2 * j].w, h[2 * j + 1].w), h[2 * j + 2].w);
-              const int pp = (phalf * 4 + j) * S3_PW + pxl;
-              st_sts128(pool_stage + (uint32_t)pp * 128u + ((uint32_t)(pch ^ (pp & 7)) << 4), mx);
-            }
+          for (int j = 0; j < S3_PH; ++j) {
+            h1 = rowmax(2 * j + 1);
+            h2 = rowmax(2 * j + 2);
+            uint4 mx;
+            mx.x = st_max2(st_max2(h0.x, h1.x), h2.x);
+            mx.y = st_max2(st_max2(h0.y, h1.y), h2.y);
+            mx.z = st_max2(st_max2(h0.z, h1.z), h2.z);
+            mx.w = st_max2(st_max2(h0.w, h1.w), h2.w);
+            const int pp = j * S3_PW + pxl;
+            st_sts128(pool_stage + (uint32_t)pp * 128u + ((uint32_t)(pch ^ (pp & 7)) << 4), mx);
+            h0 = h2;
           }
         }
       } else {
         // leftmost tiles: phase 0 is staged in the shifted 7-wide order (generic item loop)
-        for (int it = et; it < S3_PH * S3_PW * 8; it += 32 * S3_EPI_WARPS) {
+        for (int it = et; it < S3_PH * S3_PW * 8; it += 32 * S3_POOL_WARPS) {
           const int ch = it & 7, pp = it >> 3;
           const int pyl = pp / S3_PW, px_ = pp - pyl * S3_PW;
           uint4 mx = make_uint4(0u, 0u, 0u, 0u);
@@ -737,13 +763,9 @@ __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_v3_kernel(const __gri
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->out_full[ob]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
       if (++ob == 2) {
         ob = 0;
-        oph ^= 1;
+        sph ^= 1;
       }
     }
   }
