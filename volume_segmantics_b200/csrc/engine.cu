@@ -162,6 +162,7 @@ struct vsb_engine {
   size_t gap_scratch_bytes = 0;
 
   int batch_override = 0;
+  int64_t row_batch_px = 0;      // vsb_set_flag("row_batch_mpx", n): padded pixels per launch sequence for row directions (0 = 128 Mi)
   int conv_impl = 0;
   bool no_halo = false;
   bool no_tma_epilogue = false;  // vsb_set_flag("tma_epilogue", 0): per-thread global stores in the halo epilogue
@@ -1456,10 +1457,13 @@ int run_network(vsb_engine* e, int nb, int* head_idx) {
 
 int auto_batch(const vsb_engine* e, int64_t Hp, int64_t Wp, int64_t S, bool xplane) {
   if (e->batch_override > 0) return (int)std::min<int64_t>(e->batch_override, S);
-  // measured: 32 slices of 1024^2 per launch beat 16 by 6 %, larger batches are neutral for the
-  // network.  x-plane directions (slice index along x) take 128 slices: the slicer then reads 128
-  // contiguous bytes per (row, column) and the head merges 1 KB runs of keys instead of 256 B.
-  const int64_t target_px = xplane ? (128ll << 20) : (32ll << 20);
+  // 128 slices of 1024^2 per launch sequence for every direction.  Round 1 used 32 for the row directions
+  // ("larger batches are neutral"); with the per-launch fixed cost now about 20 us against 180 us of work per
+  // 32-slice launch, 128 measured 3.3 % faster (266 -> 258 us per slice, tests/exp_stem.sh).  x-plane
+  // directions (slice index along x) need 128 anyway: the slicer then reads 128 contiguous bytes per
+  // (row, column) and the head merges 1 KB runs of keys instead of 256 B.
+  (void)xplane;
+  const int64_t target_px = e->row_batch_px > 0 && !xplane ? e->row_batch_px : (128ll << 20);
   int64_t nb = std::max<int64_t>(1, target_px / (Hp * Wp));
   nb = std::min<int64_t>(nb, 256);
   if (nb >= 32) nb = nb / 32 * 32;
@@ -1949,6 +1953,7 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
   else if (n == "fuse_pool") { e->no_fuse_pool = value == 0; free_workspace(e); }
   else if (n == "stem") { e->stem_version = value; free_workspace(e); }
   else if (n == "stem_dbg") e->stem_dbg = value;
+  else if (n == "row_batch_mpx") e->row_batch_px = (int64_t)value << 20;
   else if (n == "dw_tiled") e->no_dw_tiled = value == 0;
   else if (n == "tc_smem_epilogue") { e->no_tc_smem_epilogue = value == 0; free_workspace(e); }
   else if (n == "halo_ab") { e->halo_ab_override = value; free_workspace(e); }
