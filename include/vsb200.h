@@ -67,7 +67,16 @@ typedef struct {
   int32_t kh, kw, stride, pad, dil, groups;
   int32_t relu;
   int32_t mode, factor;        /* UPSAMPLE: mode/factor. HEAD: factor = bilinear
-                                  upsampling of the logits (1 = none)         */
+                                  upsampling of the logits (1 = none).
+                                  CONV: mode 2 = the blob also holds, at byte
+                                  offset factor * 256, the 16-bit weights
+                                  [4*cout][3][3][C0 + 4*(cin - C0)] of the same
+                                  layer as a convolution between space-to-depth
+                                  tensors at half the output resolution (source
+                                  0 up-sampled with C0 channels, then the
+                                  (py, px, c) sub-pixels of the other sources;
+                                  output channel (a*2+b)*cout + c = pixel
+                                  (2i+a, 2j+b)); the engine may run either form */
   int64_t w_off;               /* byte offset in the weight blob of 16-bit
                                   [cout][kh][kw][cin/groups] (OHWI)           */
   int64_t b_off;               /* byte offset of f32 [cout] bias              */
@@ -218,6 +227,9 @@ int vsb_set_conv_impl(vsb_engine* e, int32_t impl);
  *   "stem" (3)            stem + pool kernel: 3 = raw input window read in place by shifted no-swizzle descriptors, pool
  *                         computed inside the CTA; 2 = im2col rows built by loader warps, pool inside the CTA;
  *                         1 = im2col + pooling by red.global.max into a zeroed tensor (round-1 kernel)
+ *   "s2d_up" (1)          decoder `upsample x2 + concat -> conv3x3` layers whose op carries mode 2 run as a
+ *                         space-to-depth convolution at half resolution (summed up-sample taps: same arithmetic up
+ *                         to summation order and one rounding of the summed weights); 0: parity-split kernels
  *   "fuse_head" (0)       softmax/argmax/merge inside the last conv's epilogue (bit-identical, measured slower)
  *   "sub_batch_mb" (0)    L2 budget for depth-first sub-batches, 0 = off
  * Debugging aids: "sync_each" (synchronise after every op and name the one that failed), "halo_prof" (per-launch

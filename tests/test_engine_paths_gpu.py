@@ -78,6 +78,33 @@ def test_s2d_tail_matches_plain_tail(engine, monkeypatch, classes):
     assert (lab1 == lab0).mean() > 0.995  # random-init weights: every voxel sits near a decision boundary
 
 
+@pytest.mark.parametrize("mt,arch,enc,classes,shape", [
+    ("U_NET", "unet", "resnet34", 4, (2, 150, 200)),       # several tiles per launch, overhanging tiles
+    ("U_NET", "unet", "resnet34", 4, (3, 300, 420)),
+    ("U_NET", "unet", "resnet50", 2, (2, 70, 100)),        # skip tensors of 256 / 512 / 1024 channels
+    ("U_NET_PLUS_PLUS", "unetplusplus", "resnext50_32x4d", 6, (2, 70, 100)),  # several skip sources per layer
+])
+def test_s2d_up_concat_matches_parity_split(engine, mt, arch, enc, classes, shape):
+    """Decoder conv1 layers as space-to-depth convolutions (conv_halo_el_kernel, vsb_op.mode == 2)  vs  the
+    parity-split kernels on the same plan: the up-sampled taps are summed before the one rounding to 16 bit
+    and the products are accumulated in another order, so logits agree to 16-bit noise."""
+    oracle = make_random_model(arch, enc, classes, seed=6)
+    model = B200SegmentationModel(mt, enc, classes)
+    model.load_state_dict(oracle.state_dict())
+    x = _inputs(shape, 13)
+    got = engine.forward_logits(model, x)
+    engine.set_flag("s2d_up", 0)
+    try:
+        want = engine.forward_logits(model, x)
+    finally:
+        engine.set_flag("s2d_up", 1)
+    err = np.abs(got - want).max()
+    print(f"[s2d_up {mt}/{enc} {shape}] max |logit diff| {err:.2e} (|logits| max {np.abs(want).max():.3f}), "
+          f"identical {np.array_equal(got, want)}")
+    assert not np.array_equal(got, want), "the space-to-depth path did not run"
+    assert err < 5e-3 * max(1.0, np.abs(want).max())
+
+
 def test_s2d_head_against_oracle_three_axes(engine, unet_r34):
     """Z / Y axes use the row head kernel, X the x-plane kernel; probabilities within the BASELINE tolerance."""
     oracle, model = unet_r34

@@ -116,6 +116,40 @@ def test_plan_lowering_tables():
             assert op.w_off + op.cout * op.kh * op.kw * (op.cin // op.groups) * 2 <= p.blob.size
 
 
+def test_space_to_depth_lowering_of_upsample_concat_conv():
+    """plan.s2d_up_concat_weights: cat(nearest-x2 upsample(x), skip) -> conv3x3  ==  conv3x3 at the resolution of
+    x over [x, space-to-depth(skip)] followed by depth-to-space (the form conv_halo_el_kernel runs)."""
+    import torch.nn.functional as F
+
+    from volume_segmantics_b200.plan import s2d_up_concat_weights
+
+    torch.manual_seed(0)
+    o, cu, cs = 8, 6, 5
+    w = torch.randn(o, cu + cs, 3, 3)
+    x, skip = torch.randn(2, cu, 5, 7), torch.randn(2, cs, 10, 14)
+    want = F.conv2d(torch.cat([F.interpolate(x, scale_factor=2, mode="nearest"), skip], 1), w, padding=1)
+
+    def s2d(t):  # [N, C, 2H, 2W] -> [N, 4C, H, W], channel = (a*2 + b)*C + c for pixel (2i+a, 2j+b)
+        n, c, h, wd = t.shape
+        return t.reshape(n, c, h // 2, 2, wd // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(n, 4 * c, h // 2, wd // 2)
+
+    got = F.conv2d(torch.cat([x, s2d(skip)], 1), s2d_up_concat_weights(w, cu), padding=1)
+    n, _, h, wd = got.shape
+    got = got.reshape(n, 2, 2, o, h, wd).permute(0, 3, 4, 1, 5, 2).reshape(n, o, 2 * h, 2 * wd)
+    assert torch.allclose(got, want, atol=1e-5)
+
+
+def test_plan_marks_decoder_conv1_for_the_space_to_depth_kernel():
+    p = lower_to_plan(B200SegmentationModel("U_NET", "resnet34", 4))
+    dec = [op for op in p.ops if op.kind == _lib.VSB_OP_CONV and op.n_src == 2]
+    assert [op.mode for op in dec] == [2, 2, 2, 2]
+    for op in dec:
+        c_up = p.tensors[op.src[0]].channels
+        k2 = c_up + 4 * (op.cin - c_up)
+        assert op.factor > 0 and op.factor * 256 + 4 * op.cout * 9 * k2 * 2 <= p.blob.size
+    assert all(op.mode == 0 for op in p.ops if op.kind == _lib.VSB_OP_CONV and op.n_src == 1)
+
+
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
 @pytest.mark.parametrize("shape", [(64, 64, 64), (20, 40, 45), (2048, 2048, 512)])
 def test_partition_covers_everything_once(world, shape):

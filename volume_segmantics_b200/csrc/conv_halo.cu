@@ -652,6 +652,328 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 }
 
 // =====================================================================================
+// Entry-list halo kernel (see conv_halo.cuh, ConvHaloElParams): TMA halo boxes from several
+// sources, weight images streamed with per-image GEMM column ranges, direct epilogue that
+// un-shuffles the space-to-depth columns into the plain output tensor.
+//   warp 0      A producer: one TMA halo box per (tile, slab ref)
+//   warp 1      TMEM allocator + MMA issuer
+//   warp 2      B producer: one bulk copy per entry through the weight ring
+//   warps 3..10 epilogue
+// =====================================================================================
+namespace {
+struct HaloElTables {
+  HaloSlabRef slabs[HALO_EL_MAX_SLABS];
+  HaloEntry entries[HALO_EL_MAX_ENTRIES];
+};
+constexpr int kHaloElBiasBytes = 1024 * 4;  // n_tiles * BN <= 1024
+__device__ __forceinline__ void halo_el_decode(const ConvHaloElParams& p, int t, int& n_tile, int& X0, int& Y0, int& n) {
+  auto fdiv = [](uint32_t v, const FastDiv& f) { return f.m ? __umulhi(v, f.m) : v; };
+  uint32_t sp = fdiv((uint32_t)t, p.div_n_tiles);
+  n_tile = t - (int)(sp * p.div_n_tiles.d);
+  uint32_t q = fdiv(sp, p.div_tx);
+  const int tx = (int)(sp - q * p.div_tx.d);
+  sp = q;
+  q = fdiv(sp, p.div_ty);
+  const int ty = (int)(sp - q * p.div_ty.d);
+  n = (int)q + p.n_base;
+  X0 = tx * (8 * p.mt);
+  Y0 = ty * 16;
+}
+}  // namespace
+
+template <int MT>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv_halo_el_kernel(const __grid_constant__ ConvHaloElParams p) {
+  constexpr int P = 128, KSTEPS = 4;
+  constexpr int HW = 8 * MT + 2, HH = 18;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* b_area = smem + (size_t)p.a_stages * p.a_stage_bytes;
+  uint8_t* stage = b_area + (size_t)p.b_stages * p.b_bytes;  // 2 x 16 KB when out_map, 1024-aligned
+  HaloCtl* ctl = reinterpret_cast<HaloCtl*>(stage + (p.out_map ? 32768 : 0));
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + kHaloCtlBytes);
+  HaloElTables* tab = reinterpret_cast<HaloElTables*>(reinterpret_cast<uint8_t*>(bias_s) + kHaloElBiasBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.n_tiles * p.tiles_x * p.tiles_y * p.NB;
+  // Accumulators: one slot of BN columns per (stage, 8 x 16 tile of the stage); slot = stage * MT + m.
+  // MT * BN <= 256: two stages; MT * BN == 512 (BN = 256, MT = 2): one stage, and because every slot has its
+  // own full / empty barriers the MMA warp of tile m restarts as soon as the epilogue has drained ITS slot.
+  const int acc_stages = MT * p.BN <= 256 ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    // MT == 2: two MMA-issuing warps, one per 8 x 16 tile of the stage (a single warp issues an MMA every
+    // ~50 cycles, an N <= 96 MMA executes in 40..56); both commit to the operand rings' barriers
+    for (int i = 0; i < p.a_stages; ++i) {
+      mbar_init(&ctl->a_full[i], 1);
+      mbar_init(&ctl->a_empty[i], MT);
+    }
+    for (int i = 0; i < HALO_MAX_B_STAGES; ++i) {
+      mbar_init(&ctl->b_full[i], 1);
+      mbar_init(&ctl->b_empty[i], MT);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&ctl->acc_full[i], 1);
+      mbar_init(&ctl->acc_empty[i], 32 * HALO_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < p.n_tiles * p.BN; i += HALO_THREADS) bias_s[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.n_slabs; i += HALO_THREADS) tab->slabs[i] = p.slabs[i];
+  for (int i = threadIdx.x; i < p.n_entries; i += HALO_THREADS) tab->entries[i] = p.entries[i];
+  if (warp == 1) tmem_alloc<512>(&ctl->tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===================== A producer =====================
+    int as = 0;
+    uint32_t aph = 0;
+    constexpr uint32_t a_box_bytes = (uint32_t)(HW * HH * P);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n_tile, X0, Y0, n;
+      halo_el_decode(p, t, n_tile, X0, Y0, n);
+      for (int sr = p.tile_begin[n_tile]; sr < p.tile_begin[n_tile + 1]; ++sr) {
+        const HaloSlabRef s = tab->slabs[sr];
+        mbar_wait(&ctl->a_empty[as], aph ^ 1);
+        if (elect_one()) {
+          if (p.dbg & 1) {
+            mbar_arrive(&ctl->a_full[as]);
+          } else {
+            mbar_arrive_expect_tx(&ctl->a_full[as], a_box_bytes);
+            tma_load_5d(p.map + s.map, &ctl->a_full[as], a_ring + (size_t)as * p.a_stage_bytes, s.c, X0 - 1, s.p, Y0 - 1, n);
+          }
+        }
+        __syncwarp();
+        if (++as == p.a_stages) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== B producer =====================
+    int bs = 0;
+    uint32_t bph = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n_tile, X0, Y0, n;
+      halo_el_decode(p, t, n_tile, X0, Y0, n);
+      const int e_begin = tab->slabs[p.tile_begin[n_tile]].e_begin;
+      const int e_end = tab->slabs[p.tile_begin[n_tile + 1] - 1].e_end;
+      for (int ei = e_begin; ei < e_end; ++ei) {  // the entries of a tile's slab refs are consecutive
+        const HaloEntry en = tab->entries[ei];
+        const uint32_t bytes = en.grp & 0x7fffffffu;
+        if (!bytes) continue;  // not the first entry of its group
+        mbar_wait(&ctl->b_empty[bs], bph ^ 1);
+        if (elect_one()) {
+          if (p.dbg & 2) {
+            mbar_arrive(&ctl->b_full[bs]);
+          } else {
+            mbar_arrive_expect_tx(&ctl->b_full[bs], bytes);
+            bulk_load_1d(b_area + (size_t)bs * p.b_bytes, p.wpacked + en.w_off, bytes, &ctl->b_full[bs]);
+          }
+        }
+        __syncwarp();
+        if (++bs == p.b_stages) {
+          bs = 0;
+          bph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 || (MT == 2 && warp == HALO_MMA2_WARP)) {
+    // ===================== MMA issuer(s) =====================
+    // (a loop run by lane 0 alone instead of elect-per-entry measured 10 % slower)
+    const int mw = warp == 1 ? 0 : 1;  // the 8 x 16 tile of the stage this warp issues
+    int as = 0, bs = 0, acc = 0;
+    uint32_t aph = 0, bph = 0, acc_phase = 0;
+    const uint64_t a_desc0 = desc_add(desc_compact<P>(smem_u32(a_ring), (uint32_t)HW * P), mw * 8 * (P / 16));
+    const uint64_t b_desc0 = desc_compact<P>(smem_u32(b_area), 8 * P);
+    const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4;
+    const uint32_t b_step = (uint32_t)p.b_bytes >> 4;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n_tile, X0, Y0, n;
+      halo_el_decode(p, t, n_tile, X0, Y0, n);
+      const int slot = acc * MT + mw;
+      mbar_wait(&ctl->acc_empty[slot], acc_phase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(slot * p.BN);
+      const int sr_end = p.tile_begin[n_tile + 1];
+      uint32_t accf = 0;  // the first entry of a tile covers all BN columns (host guarantee)
+      for (int sr = p.tile_begin[n_tile]; sr < sr_end; ++sr) {
+        const HaloSlabRef s = tab->slabs[sr];
+        mbar_wait(&ctl->a_full[as], aph);
+        tc_fence_after_sync();
+        const uint64_t a_stage_desc = desc_add(a_desc0, as * a_step);
+        for (int ei = s.e_begin; ei < s.e_end; ++ei) {
+          const HaloEntry en = tab->entries[ei];
+          if (en.grp & 0x7fffffffu) {  // first entry of a group: its images have landed
+            mbar_wait(&ctl->b_full[bs], bph);
+            tc_fence_after_sync();
+          }
+          const bool last = (en.grp >> 31) != 0;
+          if (elect_one()) {
+            const uint32_t ncol0 = en.ncol0_n & 0xffffu, nn = en.ncol0_n >> 16;
+            const uint32_t idesc = umma_idesc_act(128, (int)nn);
+            const uint64_t at = desc_add(a_stage_desc, en.ab_off16 & 0xffffu);
+            const uint64_t bt = desc_add(b_desc0, bs * b_step + (en.ab_off16 >> 16));
+            const uint32_t d = d_tmem + ncol0;
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              if (k == 0 || !(p.dbg & 8)) umma_bf16_ss(d, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc, k != 0 ? 1u : accf);
+            if (last) umma_commit(&ctl->b_empty[bs]);
+            if (ei == s.e_end - 1) {
+              umma_commit(&ctl->a_empty[as]);
+              if (sr == sr_end - 1) umma_commit(&ctl->acc_full[slot]);
+            }
+          }
+          __syncwarp();
+          accf = 1;
+          if (last && ++bs == p.b_stages) {
+            bs = 0;
+            bph ^= 1;
+          }
+        }
+        if (++as == p.a_stages) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+      if (++acc == acc_stages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp < 3 + HALO_EPI_WARPS && p.out_map) {
+    // ===================== epilogue through shared memory + TMA store =====================
+    // Work unit = (8 x 16 tile m, 64-column group g): 128 pixels x 64 channels = 16 KB, staged in the SW128
+    // layout of the FOLDED output map (px*C + c, x/2, py, y/2, n): the 64 columns are the two horizontal
+    // sub-pixels of 32 channels, or 64 channels of one sub-pixel, of row parity a -- one box {64, 8, 1, 16, 1}.
+    // Buffers alternate; one barrier per unit: [all: stage unit j] -> [thread 0: wait until the stores of
+    // units < j have been read] -> barrier -> [thread 0: store unit j] (conv_tc.cu has the same scheme).
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int quarter = warp & 3;
+    const int half = (warp - 3) >> 2;
+    const int row = quarter * 32 + lane;
+    const bool issuer = warp == 3 && lane == 0;
+    const uint32_t stage0 = smem_u32(stage);
+    const bool relu = p.relu != 0;
+    uint32_t unit = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n_tile, X0, Y0, n;
+      halo_el_decode(p, t, n_tile, X0, Y0, n);
+      const int ch0 = n_tile * p.BN;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const int slot = acc * MT + m;
+        mbar_wait(&ctl->acc_full[slot], acc_phase);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + (uint32_t)(slot * p.BN) + ((uint32_t)(quarter * 32) << 16);
+        for (int g = 0; g * 64 < p.BN; ++g, ++unit) {
+          const int c = g * 64 + half * 32;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c, v);
+          tmem_ld_wait();
+          if (g * 64 + 64 >= p.BN) {  // this thread's last read of the slot
+            tc_fence_before_sync();
+            mbar_arrive(&ctl->acc_empty[slot]);
+          }
+          const float* bs = bias_s + ch0 + c;
+          const uint32_t rowa = stage0 + (unit & 1u) * 16384u + (uint32_t)row * 128u;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bs + q * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bs + q * 8 + 4);
+            const float f0 = __uint_as_float(v[q * 8 + 0]) + b0.x, f1 = __uint_as_float(v[q * 8 + 1]) + b0.y;
+            const float f2 = __uint_as_float(v[q * 8 + 2]) + b0.z, f3 = __uint_as_float(v[q * 8 + 3]) + b0.w;
+            const float f4 = __uint_as_float(v[q * 8 + 4]) + b1.x, f5 = __uint_as_float(v[q * 8 + 5]) + b1.y;
+            const float f6 = __uint_as_float(v[q * 8 + 6]) + b1.z, f7 = __uint_as_float(v[q * 8 + 7]) + b1.w;
+            uint4 pk;
+            if (relu) {
+              pk.x = pack2<true>(f0, f1); pk.y = pack2<true>(f2, f3); pk.z = pack2<true>(f4, f5); pk.w = pack2<true>(f6, f7);
+            } else {
+              pk.x = pack2<false>(f0, f1); pk.y = pack2<false>(f2, f3); pk.z = pack2<false>(f4, f5); pk.w = pack2<false>(f6, f7);
+            }
+            sts128(rowa + ((uint32_t)((half * 4 + q) ^ (row & 7)) << 4), pk);
+          }
+          fence_proxy_async_smem();
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(1, 32 * HALO_EPI_WARPS);
+          if (issuer && !(p.dbg & 4)) {
+            const int chs = ch0 + g * 64;
+            const int cls = chs >> p.cout_log2, cpl = chs & (p.cout - 1);
+            tma_store_5d(p.out_map, stage + (unit & 1u) * 16384u, (cls & 1) * p.cout + cpl, X0 + m * 8, cls >> 1, Y0, n);
+            tma_store_commit();
+          }
+        }
+      }
+      if (++acc == acc_stages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+  } else if (warp < 3 + HALO_EPI_WARPS) {
+    // ===================== direct epilogue (per-thread global stores) =====================
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int quarter = warp & 3;
+    const int half = (warp - 3) >> 2;
+    const int row = quarter * 32 + lane;
+    const int xi = row & 7, yi = row >> 3;
+    const EpiOut eo{p.out, nullptr, 0, p.relu, p.cout};
+    const int OW = 2 * p.W, OH = 2 * p.H;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n_tile, X0, Y0, n;
+      halo_el_decode(p, t, n_tile, X0, Y0, n);
+      const int ch0 = n_tile * p.BN;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const int slot = acc * MT + m;
+        mbar_wait(&ctl->acc_full[slot], acc_phase);
+        tc_fence_after_sync();
+        const int ox = X0 + m * 8 + xi, oy = Y0 + yi;
+        const bool valid = ox < p.W && oy < p.H && !(p.dbg & 4);
+        const uint32_t taddr = tmem_base + (uint32_t)(slot * p.BN) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = half * 32 + ci * 64;
+          if (c >= p.BN) break;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c, v);
+          tmem_ld_wait();
+          if (valid) {
+            // space-to-depth columns [chs, chs + 32): sub-pixel (a, b) = class, plain channels cpl .. cpl + 31
+            const int chs = ch0 + c;
+            const int cls = chs >> p.cout_log2, cpl = chs & (p.cout - 1);
+            const int64_t pix = ((int64_t)n * OH + 2 * oy + (cls >> 1)) * OW + 2 * ox + (cls & 1);
+            epilogue_chunk32(eo, v, bias_s + (chs - cpl), pix, cpl);
+          }
+        }
+        tc_fence_before_sync();
+        mbar_arrive(&ctl->acc_empty[slot]);
+      }
+      if (++acc == acc_stages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// =====================================================================================
 // Generalised halo kernel: cp.async-assembled A tiles (see conv_halo.cuh).
 //   warps 0..3   A loaders (128 threads): 16-byte cp.async copies, zero-filled outside
 //                the image, written at the swizzled position of a compact-pitch pixel row;
@@ -1255,6 +1577,29 @@ cudaError_t launch_conv_halo2(const ConvHalo2Params& p0, int num_sms, cudaStream
   return halo2_dispatch(p, grid, conv_halo2_smem_bytes(p), st, false);
 }
 
+size_t conv_halo_el_smem_bytes(const ConvHaloElParams& p) {
+  return (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_bytes + (p.out_map ? 32768 : 0) + kHaloCtlBytes +
+         kHaloElBiasBytes + sizeof(HaloElTables) + 1024;
+}
+
+cudaError_t launch_conv_halo_el(const ConvHaloElParams& p0, int num_sms, cudaStream_t st) {
+  ConvHaloElParams p = p0;
+  const int64_t total_tiles = (int64_t)p.n_tiles * p.tiles_x * p.tiles_y * p.NB;
+  const int64_t dmax = p.n_tiles > p.tiles_x ? (p.n_tiles > p.tiles_y ? p.n_tiles : p.tiles_y)
+                                             : (p.tiles_x > p.tiles_y ? p.tiles_x : p.tiles_y);
+  if (total_tiles * dmax >= (1ll << 32)) return cudaErrorInvalidValue;  // FastDiv exactness bound
+  if (p.n_slabs > HALO_EL_MAX_SLABS || p.n_entries > HALO_EL_MAX_ENTRIES || p.n_tiles > HALO_EL_MAX_NTILES ||
+      p.n_tiles * p.BN > 1024 || p.mt * p.BN > 512 || conv_halo_el_smem_bytes(p) > 227 * 1024)
+    return cudaErrorInvalidValue;
+  p.div_n_tiles = make_fastdiv((uint32_t)p.n_tiles);
+  p.div_tx = make_fastdiv((uint32_t)p.tiles_x);
+  p.div_ty = make_fastdiv((uint32_t)p.tiles_y);
+  const int grid = total_tiles < num_sms ? (int)total_tiles : num_sms;
+  if (p.mt == 2) conv_halo_el_kernel<2><<<grid, HALO_THREADS, conv_halo_el_smem_bytes(p), st>>>(p);
+  else conv_halo_el_kernel<1><<<grid, HALO_THREADS, conv_halo_el_smem_bytes(p), st>>>(p);
+  return cudaGetLastError();
+}
+
 size_t conv_halo_smem_bytes(const ConvHaloParams& p) {
   const size_t b = p.b_stages ? (size_t)p.b_stages * p.b_bytes : (size_t)p.ncs * 9 * p.b_bytes;
   return (size_t)p.a_stages * p.a_stage_bytes + b + (size_t)(p.out_bufs + p.res_bufs) * p.out_buf_bytes +
@@ -1265,6 +1610,10 @@ cudaError_t conv_halo_configure() {
   cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_halo_el_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_halo_el_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   ConvHalo2Params q{};
   q.stem = 1;
   if (e == cudaSuccess) e = halo2_dispatch(q, 0, 0, nullptr, true);

@@ -114,6 +114,58 @@ struct HeadFuse {
   int64_t base, stride_s, stride_r, stride_c;
   unsigned long long* keys;
 };
+// ---- entry-list variant (conv_halo_el_kernel): space-to-depth lowering of the decoder's
+// `nearest-x2 upsample -> concat(skip) -> conv3x3` (smp DecoderBlock.conv1).  The 2x2 output
+// pixels of a block become 4*Cout GEMM columns at HALF the output resolution; the
+// up-sampled source is then read at its own resolution (the 9 taps of the four sub-pixels
+// collapse onto a 3x3 low-resolution neighbourhood with summed weights: 16 instead of 36
+// (sub-pixel, tap) products), and the skip tensor is read through its "folded" tensor map
+// (px*C+c, x/2, py, y/2, n), whose boxes are the four parity planes.  Most (K-slab, tap)
+// weight images only feed some of the sub-pixels: every image carries the range of GEMM
+// columns it touches, the MMA is issued with that N into that column range, and images
+// that touch none are never loaded.  Compared with the parity-split kernels this issues
+// the same products for the skip tensor with 2-4x wider N (the narrow-N layers are bound
+// by the 128 B/clk shared-memory operand reads: A 4 KB + B N*32 B per MMA), and 2.25x fewer
+// products for the up-sampled tensor.
+struct HaloSlabRef {
+  int32_t map;            // source index (tensor map p.map[map])
+  int32_t c, p;           // box coordinates 0 (channel) and 2 (row parity of the folded view; 0 for plain maps)
+  int32_t e_begin, e_end; // entries of this slab
+};
+// Consecutive entries of a slab whose images fit one weight-ring stage together form a GROUP: one bulk copy,
+// one full/empty hand-off (the images of a group are consecutive in wpacked).
+struct HaloEntry {
+  uint32_t ab_off16;  // [15:0] tap offset inside the halo tile, [31:16] image offset inside the ring stage (16-byte units)
+  uint32_t w_off;     // byte offset of the image ([n][64] pre-swizzled rows) from wpacked
+  uint32_t ncol0_n;   // first GEMM column | columns << 16 (multiples of 16)
+  uint32_t grp;       // [30:0] bytes of the group, on its first entry (else 0); bit 31: last entry of its group
+};
+constexpr int HALO_EL_MAX_SLABS = 112, HALO_EL_MAX_ENTRIES = 352, HALO_EL_MAX_NTILES = 4;
+struct ConvHaloElParams {
+  const TmaDesc* map;          // [n_src] halo maps, box {64, 8*mt+2, 1, 18, 1}
+  const uint8_t* wpacked;
+  const float* bias;           // [n_tiles * BN], index = space-to-depth channel
+  void* out;                   // plain 16-bit NHWC [NB, 2H, 2W, cout]
+  const TmaDesc* out_map;      // folded map of `out`, box {64, 8, 1, 16, 1}: epilogue through shared memory + TMA store; null: per-thread stores
+  const HaloSlabRef* slabs;
+  const HaloEntry* entries;
+  int32_t tile_begin[HALO_EL_MAX_NTILES + 1];  // slab refs of N tile t: [tile_begin[t], tile_begin[t+1])
+  int32_t n_slabs, n_entries;
+  int32_t relu;
+  int32_t cout, cout_log2;     // channels of the plain output; space-to-depth channel = (a*2+b)*cout + c
+  int32_t BN, n_tiles;
+  int32_t NB, H, W;            // space-to-depth grid (half the output size)
+  int32_t n_base;
+  int32_t mt;                  // 8 x 16 tiles per stage (1 or 2)
+  int32_t dbg;                 // timing experiments (results wrong): 1 no halo loads, 2 no weight loads, 4 no stores, 8 one MMA per entry
+  int32_t tiles_x, tiles_y;
+  int32_t a_stages, a_stage_bytes;
+  int32_t b_stages, b_bytes;   // ring of BN * 128-byte stages
+  FastDiv div_n_tiles, div_tx, div_ty;  // set by the launcher
+};
+size_t conv_halo_el_smem_bytes(const ConvHaloElParams& p);
+cudaError_t launch_conv_halo_el(const ConvHaloElParams& p, int num_sms, cudaStream_t st);
+
 constexpr int HALO2_MAX_SLABS = 64;
 struct ConvHalo2Params {
   HaloSrc src[6];

@@ -104,6 +104,14 @@ struct ConvPlan {
   vsb::ConvStemParams sparams{};
   bool halo2_ok = false, use_halo2 = false;  // cp.async-assembled halo (concat / up-sampled / narrow sources)
   vsb::ConvHalo2Params h2params{};
+  // space-to-depth lowering of `upsample x2 + concat -> conv3x3` (op.mode == 2, conv_halo.cuh ConvHaloElParams)
+  bool el_ok = false, use_el = false;
+  uint8_t* d_wel = nullptr;
+  float* d_bias_el = nullptr;
+  vsb::HaloSlabRef* d_el_slabs = nullptr;
+  vsb::HaloEntry* d_el_entries = nullptr;
+  TmaDesc* d_el_maps = nullptr;  // [n_src] halo maps (per workspace)
+  vsb::ConvHaloElParams elparams{};
   // spatial-size dependent
   TmaDesc* d_maps = nullptr;
   vsb::ConvTcParams params{};
@@ -180,6 +188,9 @@ struct vsb_engine {
   bool no_halo2_tma = false;     // vsb_set_flag("halo2_tma", 0): cp.async loaders for every halo2 source
   bool halo2_mma2 = false;       // vsb_set_flag("halo2_mma2", 1): two MMA warps in the cp.async halo kernel as well
   bool no_mma2 = false;          // vsb_set_flag("mma_warps", 1): a single MMA issuing warp everywhere
+  bool no_s2d_up = false;        // vsb_set_flag("s2d_up", 0): decoder conv1 layers on the parity-split kernels
+  int el_a_stages = 2;           // vsb_set_flag("el_a_stages", n): halo ring depth of the entry-list kernel
+  bool no_el_tma_epilogue = false;  // vsb_set_flag("el_tma_epilogue", 0): per-thread stores in the entry-list kernel
   bool no_epi_groups = false;    // vsb_set_flag("epi_groups", 0): one epilogue group even for BN <= 64
   unsigned long long* d_halo_prof = nullptr;  // vsb_set_flag("halo_prof", 1): per-launch cycle accounting to stderr
   int halo_dbg = 0;              // vsb_set_flag("halo_dbg", bits): timing experiments, see ConvHaloParams::dbg
@@ -265,6 +276,145 @@ bool conv_tc_eligible(const vsb_engine* e, const vsb_op& op) {
   if (e->tdesc[op.out].ds_log2 < 0) return false;
   if ((op.cout + 15) / 16 * 16 > 2048) return false;
   return true;
+}
+
+// Space-to-depth lowering of a decoder convolution (op.mode == 2): the plan carries, at blob offset
+// op.factor * 256, the 16-bit weights [4*cout][3][3][Cup + 4*Cskip] of the equivalent 3x3 convolution at half
+// the output resolution (plan.py s2d_up_concat_weights: K = channels of the up-sampled source at its own
+// resolution, then the (py, px, c) sub-pixels of the concatenated skip sources).  Builds the slab refs,
+// the (slab, tap) entries with their non-zero GEMM column ranges and the packed weight images.
+int prepare_el_plan(vsb_engine* e, int oi) {
+  const vsb_op& op = e->ops[oi];
+  ConvPlan& cp = e->conv[oi];
+  cp.el_ok = false;
+  if (op.kind != VSB_OP_CONV || op.mode != 2) return VSB_OK;
+  if (op.kh != 3 || op.kw != 3 || op.stride != 1 || op.pad != 1 || op.dil != 1 || op.groups != 1 || op.res >= 0 ||
+      op.n_src < 2 || !op.src_up[0])
+    return fail(VSB_ERR_INVALID, "op %d: mode 2 needs conv3x3 pad 1 over [up-sampled source, skip sources...]", oi);
+  const vsb_tensor_desc& ot = e->tdesc[op.out];
+  const int cout = op.cout;
+  if (ot.dtype != 0 || ot.ds_log2 < 0 || (cout != 32 && cout != 64 && cout != 128 && cout != 256)) return VSB_OK;
+  const int Cup = e->tdesc[op.src[0]].channels;
+  if (Cup % 64 || e->tdesc[op.src[0]].dtype != 0 || e->tdesc[op.src[0]].ds_log2 != ot.ds_log2 + 1) return VSB_OK;
+  int Cskip = 0;
+  std::vector<int> skip_off(op.n_src, 0);
+  for (int s = 1; s < op.n_src; ++s) {
+    const vsb_tensor_desc& t = e->tdesc[op.src[s]];
+    if (op.src_up[s] || t.channels % 32 || t.dtype != 0 || t.ds_log2 != ot.ds_log2) return VSB_OK;
+    skip_off[s] = Cskip;
+    Cskip += t.channels;
+  }
+  if (Cup + Cskip != op.cin) return fail(VSB_ERR_INVALID, "op %d: cin %d != sum of sources", oi, op.cin);
+  const int K = Cup + 4 * Cskip, N = 4 * cout;
+  const int64_t woff = (int64_t)op.factor * 256;
+  if (op.factor <= 0 || (size_t)woff + (size_t)N * 9 * K * 2 > e->weight_bytes)
+    return fail(VSB_ERR_INVALID, "op %d: space-to-depth weight range", oi);
+  const uint16_t* w = reinterpret_cast<const uint16_t*>(e->h_weights.data() + woff);  // [N][3][3][K]
+  const int n_tiles = (N + 255) / 256, BN = N / n_tiles;
+  if (n_tiles > vsb::HALO_EL_MAX_NTILES) return VSB_OK;
+
+  // K-slabs of 64 channels: (source, box channel coordinate, row parity, K index of slab channel 0, run length)
+  // (box channel coordinate d = px*C + c of the folded view; a slab may straddle px when C = 32 mod 64, so the
+  // K index is kept per 32-channel half)
+  struct Slab { int map, c, p; int k0[2]; };
+  std::vector<Slab> slabs;
+  for (int c0 = 0; c0 < Cup; c0 += 64) slabs.push_back({0, c0, 0, {c0, c0 + 32}});
+  for (int s = 1; s < op.n_src; ++s) {
+    const int C = e->tdesc[op.src[s]].channels;
+    for (int py = 0; py < 2; ++py)
+      for (int d0 = 0; d0 < 2 * C; d0 += 64) {
+        auto kidx = [&](int d) { const int px = d / C, c = d % C; return Cup + (py * 2 + px) * Cskip + skip_off[s] + c; };
+        slabs.push_back({s, d0, py, {kidx(d0), kidx(d0 + 32)}});
+      }
+  }
+  const int mt = 2, HWt = 8 * mt + 2;
+  std::vector<vsb::HaloSlabRef> refs;
+  std::vector<vsb::HaloEntry> entries;
+  std::vector<uint8_t> packed;
+  int tile_begin[vsb::HALO_EL_MAX_NTILES + 1] = {0};
+  auto wv = [&](int o, int tap, int k) { return w[((int64_t)o * 9 + tap) * K + k]; };
+  for (int nt = 0; nt < n_tiles; ++nt) {
+    tile_begin[nt] = (int)refs.size();
+    bool first = true;
+    for (const Slab& sl : slabs) {
+      vsb::HaloSlabRef ref{sl.map, sl.c, sl.p, (int)entries.size(), 0};
+      int grp_first = -1, grp_rows = 0;  // open group of this slab
+      // the centre tap of the first slab goes first: it feeds every sub-pixel, so it initialises all BN columns
+      int order[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
+      for (int ti = 0; ti < 9; ++ti) {
+        const int tap = order[ti];
+        int r0 = BN, r1 = 0;  // non-zero row range of the image
+        for (int n = 0; n < BN; ++n) {
+          bool nz = false;
+          for (int h = 0; h < 2 && !nz; ++h)
+            for (int j = 0; j < 32 && !nz; ++j) nz = (wv(nt * BN + n, tap, sl.k0[h] + j) & 0x7fffu) != 0;
+          if (nz) { r0 = std::min(r0, n); r1 = std::max(r1, n + 1); }
+        }
+        if (first) { r0 = 0; r1 = BN; }
+        if (r1 <= r0) continue;
+        r0 = r0 / 16 * 16;
+        r1 = (r1 + 15) / 16 * 16;
+        vsb::HaloEntry en{};
+        if (grp_first < 0 || grp_rows + (r1 - r0) > BN) {  // close the group, open the next
+          if (grp_first >= 0) entries.back().grp |= 0x80000000u;
+          grp_first = (int)entries.size();
+          grp_rows = 0;
+        }
+        en.ab_off16 = (uint32_t)(((tap / 3) * HWt + tap % 3) * 8) | ((uint32_t)(grp_rows * 8) << 16);  // 128-byte pixels / rows
+        en.w_off = (uint32_t)packed.size();
+        en.ncol0_n = (uint32_t)r0 | ((uint32_t)(r1 - r0) << 16);
+        en.grp = 0;
+        grp_rows += r1 - r0;
+        const size_t base = packed.size();
+        packed.resize(base + (size_t)(r1 - r0) * 128, 0);
+        for (int n = r0; n < r1; ++n)
+          for (int ch = 0; ch < 8; ++ch) {  // 16-byte chunks of 8 channels, Swizzle<3,4,3>
+            const int h = ch / 4, j = (ch % 4) * 8;
+            memcpy(packed.data() + base + (size_t)(n - r0) * 128 + ((ch ^ (n & 7)) * 16),
+                   &w[((int64_t)(nt * BN + n) * 9 + tap) * K + sl.k0[h] + j], 16);
+          }
+        entries.push_back(en);
+        entries[grp_first].grp = (entries[grp_first].grp & 0x80000000u) | (uint32_t)(grp_rows * 128);
+        first = false;
+      }
+      if (grp_first >= 0) entries.back().grp |= 0x80000000u;
+      ref.e_end = (int)entries.size();
+      if (ref.e_end > ref.e_begin) refs.push_back(ref);
+    }
+    tile_begin[nt + 1] = (int)refs.size();
+    if (tile_begin[nt + 1] == tile_begin[nt]) return VSB_OK;
+  }
+  if ((int)refs.size() > vsb::HALO_EL_MAX_SLABS || (int)entries.size() > vsb::HALO_EL_MAX_ENTRIES) return VSB_OK;
+  CK(cudaMalloc(&cp.d_wel, packed.size()));
+  CK(cudaMemcpy(cp.d_wel, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&cp.d_el_slabs, refs.size() * sizeof(vsb::HaloSlabRef)));
+  CK(cudaMemcpy(cp.d_el_slabs, refs.data(), refs.size() * sizeof(vsb::HaloSlabRef), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&cp.d_el_entries, entries.size() * sizeof(vsb::HaloEntry)));
+  CK(cudaMemcpy(cp.d_el_entries, entries.data(), entries.size() * sizeof(vsb::HaloEntry), cudaMemcpyHostToDevice));
+  std::vector<float> bias(N, 0.f);
+  if (op.b_off >= 0)
+    for (int i = 0; i < N; ++i) memcpy(&bias[i], e->h_weights.data() + op.b_off + (size_t)(i % cout) * 4, 4);
+  CK(cudaMalloc(&cp.d_el_maps, sizeof(TmaDesc) * (VSB_MAX_SRC + 1)));  // sources, output
+  CK(cudaMalloc(&cp.d_bias_el, N * 4));
+  CK(cudaMemcpy(cp.d_bias_el, bias.data(), N * 4, cudaMemcpyHostToDevice));
+  vsb::ConvHaloElParams& h = cp.elparams;
+  h = vsb::ConvHaloElParams{};
+  h.wpacked = cp.d_wel;
+  h.bias = cp.d_bias_el;
+  h.slabs = cp.d_el_slabs;
+  h.entries = cp.d_el_entries;
+  for (int i = 0; i <= n_tiles; ++i) h.tile_begin[i] = tile_begin[i];
+  for (int i = n_tiles + 1; i <= vsb::HALO_EL_MAX_NTILES; ++i) h.tile_begin[i] = tile_begin[n_tiles];
+  h.n_slabs = (int)refs.size();
+  h.n_entries = (int)entries.size();
+  h.relu = op.relu;
+  h.cout = cout;
+  h.cout_log2 = ilog2(cout);
+  h.BN = BN;
+  h.n_tiles = n_tiles;
+  h.mt = mt;
+  cp.el_ok = true;
+  return VSB_OK;
 }
 
 int prepare_conv_plan(vsb_engine* e, int oi) {
@@ -1138,6 +1288,56 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
         cp.use_halo = true;
       }
     }
+    cp.use_el = false;
+    if (cp.el_ok && !(ot.H & 1) && !(ot.W & 1)) {
+      vsb::ConvHaloElParams& h = cp.elparams;
+      const int Hs = ot.H / 2, Ws = ot.W / 2;
+      const int tx = (Ws + 8 * h.mt - 1) / (8 * h.mt), ty = (Hs + 15) / 16;
+      const double eff = (double)Ws * Hs / ((double)tx * 8 * h.mt * ty * 16);
+      const int HW = 8 * h.mt + 2, HH = 18;
+      h.a_stage_bytes = (int)align_up((size_t)HW * HH * 128, 1024);
+      h.b_bytes = h.BN * 128;
+      // a slab feeds 16..72 MMAs, far longer than a halo box takes to arrive: two stages; the rest is weight ring
+      h.a_stages = e->el_a_stages;
+      const bool tma_epi = !e->no_el_tma_epilogue;
+      const size_t fixed = vsb::conv_halo_el_smem_bytes(vsb::ConvHaloElParams{}) + (tma_epi ? 32768 : 0);  // control, bias, tables, slack, staging
+      const size_t room = 227 * 1024 - fixed - (size_t)h.a_stages * h.a_stage_bytes;
+      h.b_stages = (int)std::min<size_t>(vsb::HALO_MAX_B_STAGES, room / h.b_bytes);
+      if (eff >= 0.55 && h.b_stages >= 2) {
+        TmaDesc maps[VSB_MAX_SRC];
+        memset(maps, 0, sizeof(maps));
+        bool ok = true;
+        for (int s = 0; s < op.n_src && ok; ++s) {
+          const TensorBuf& st = e->tens[op.src[s]];
+          if (s == 0) ok = st.H == Hs && st.W == Ws;
+          else ok = st.H == ot.H && st.W == ot.W;
+          if (!ok) break;
+          int rc = make_tensor_map(e, &maps[s], st, nb, s != 0, 64, HW, HH, 1);
+          if (rc) return rc;
+        }
+        TmaDesc om;
+        if (ok && tma_epi) {
+          int rc = make_tensor_map(e, &om, ot, nb, true, 64, 8, 16, 1);
+          if (rc) return rc;
+        }
+        if (ok) {
+          CK(cudaMemcpy(cp.d_el_maps, maps, sizeof(maps), cudaMemcpyHostToDevice));
+          h.out_map = nullptr;
+          if (tma_epi) {
+            CK(cudaMemcpy(cp.d_el_maps + VSB_MAX_SRC, &om, sizeof(om), cudaMemcpyHostToDevice));
+            h.out_map = cp.d_el_maps + VSB_MAX_SRC;
+          }
+          h.map = cp.d_el_maps;
+          h.out = ot.ptr;
+          h.NB = nb;
+          h.H = Hs;
+          h.W = Ws;
+          h.tiles_x = tx;
+          h.tiles_y = ty;
+          cp.use_el = true;
+        }
+      }
+    }
     // Per-tap kernel launches (1x1 and stride-2 convolutions): epilogue through shared memory + TMA store
     // where the tile is a plain box of the output tensor (conv_tc.cuh)
     p.out_map = p.res_map = nullptr;
@@ -1217,6 +1417,15 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
   const vsb_op& op = e->ops[oi];
   ConvPlan& cp = e->conv[oi];
   const TensorBuf& ot = e->tens[op.out];
+  if (cp.use_el && e->conv_impl == 0 && !e->no_halo && !e->no_s2d_up) {
+    vsb::ConvHaloElParams h = cp.elparams;
+    h.NB = nb;
+    h.n_base = n0;
+    h.dbg = e->halo_dbg;
+    ProfScope ps(e, PC_CONV_TC, oi);
+    CK(vsb::launch_conv_halo_el(h, e->num_sms, e->stream));
+    return VSB_OK;
+  }
   if (cp.tc && cp.use_halo && e->conv_impl == 0 && !e->no_halo) {
     vsb::ConvHaloParams h = cp.hparams;
     h.NB = nb;
@@ -1618,6 +1827,11 @@ static void free_plan(vsb_engine* e) {
     cudaFree(cp.d_runs);
     cudaFree(cp.d_wpacked);
     cudaFree(cp.d_whalo);
+    cudaFree(cp.d_wel);
+    cudaFree(cp.d_bias_el);
+    cudaFree(cp.d_el_slabs);
+    cudaFree(cp.d_el_entries);
+    cudaFree(cp.d_el_maps);
     cudaFree(cp.d_bias_pad);
     cudaFree(cp.d_maps);
   }
@@ -1696,6 +1910,8 @@ int vsb_load_plan(vsb_engine* e, const vsb_tensor_desc* tensors, int32_t n_tenso
   e->conv.assign(n_ops, ConvPlan());
   for (int i = 0; i < n_ops; ++i) {
     int rc = prepare_conv_plan(e, i);
+    if (rc) return rc;
+    rc = prepare_el_plan(e, i);
     if (rc) return rc;
   }
   e->has_plan = true;
@@ -1953,6 +2169,9 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
   else if (n == "fuse_pool") { e->no_fuse_pool = value == 0; free_workspace(e); }
   else if (n == "stem") { e->stem_version = value; free_workspace(e); }
   else if (n == "stem_dbg") e->stem_dbg = value;
+  else if (n == "s2d_up") e->no_s2d_up = value == 0;
+  else if (n == "el_tma_epilogue") { e->no_el_tma_epilogue = value == 0; free_workspace(e); }
+  else if (n == "el_a_stages") { e->el_a_stages = std::max(2, std::min(value, 4)); free_workspace(e); }
   else if (n == "row_batch_mpx") e->row_batch_px = (int64_t)value << 20;
   else if (n == "dw_tiled") e->no_dw_tiled = value == 0;
   else if (n == "tc_smem_epilogue") { e->no_tc_smem_epilogue = value == 0; free_workspace(e); }

@@ -168,6 +168,30 @@ def s2d_conv_weights(w: torch.Tensor) -> torch.Tensor:
     return out.reshape(4 * o, 4 * i, 3, 3)
 
 
+def s2d_up_concat_weights(w: torch.Tensor, c_up: int) -> torch.Tensor:
+    """[O, c_up + c_skip, 3, 3] of `cat(nearest-x2 upsample(x), skip) -> conv3x3 pad 1` (smp DecoderBlock.conv1)
+    -> [4*O, c_up + 4*c_skip, 3, 3]: the same layer as a 3x3 convolution at the resolution of x, whose inputs are
+    x itself and the space-to-depth view of the skip tensors and whose output is the space-to-depth view of the
+    layer's output (vsb200.h, vsb_op.mode == 2)."""
+    return torch.cat([s2d_upconv_weights(w[:, :c_up]), s2d_conv_weights(w[:, c_up:])], dim=1)
+
+
+def s2d_up_layer(spec: NetSpec, L: Layer) -> bool:
+    """Layers the engine can run in space-to-depth form (engine.cu prepare_el_plan)."""
+    import os
+
+    if os.environ.get("VSB200_S2D_UP", "1") == "0":
+        return False
+    if not (L.kind == "conv" and L.k == 3 and L.pad == 1 and L.stride == 1 and L.dil == 1 and L.groups == 1
+            and L.res < 0 and len(L.srcs) >= 2 and L.srcs[0][1] and not any(up for _, up in L.srcs[1:])):
+        return False
+    if L.cout not in (32, 64, 128, 256) or spec.tensors[L.out].dtype or spec.tensors[L.out].ds_log2 < 0:
+        return False
+    if spec.tensors[L.srcs[0][0]].channels % 64:
+        return False
+    return all(spec.tensors[t].channels % 32 == 0 for t, _ in L.srcs[1:])
+
+
 def find_s2d_tail(spec: NetSpec):
     """Indices (A, B, H, head) of the layers the S2D rewrite applies to, or None."""
     import os
@@ -267,6 +291,11 @@ def lower_to_plan(model: B200SegmentationModel) -> Plan:
             op.stride, op.pad, op.dil, op.groups, op.relu = L.stride, L.pad, L.dil, L.groups, int(L.relu)
             op.w_off = add(w)
             op.b_off = add(b)
+            if not (tail and i in tail[:3]) and s2d_up_layer(spec, L):
+                w2, _ = _pack(s2d_up_concat_weights(wf, spec.tensors[L.srcs[0][0]].channels), bf)
+                off2 = add(w2)
+                assert off2 % 256 == 0
+                op.mode, op.factor = 2, off2 // 256
         elif tail and i == tail[3]:
             op.mode = 1  # logits are S2D: [Hp/2, Wp/2, 4*classes]
         ops[i] = op
