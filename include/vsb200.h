@@ -230,6 +230,9 @@ int vsb_set_conv_impl(vsb_engine* e, int32_t impl);
  *   "s2d_up" (1)          decoder `upsample x2 + concat -> conv3x3` layers whose op carries mode 2 run as a
  *                         space-to-depth convolution at half resolution (summed up-sample taps: same arithmetic up
  *                         to summation order and one rounding of the summed weights); 0: parity-split kernels
+ *   "el_tma_epilogue" (1) epilogue of that kernel through shared memory + TMA store (folded output map); 0: per-thread stores
+ *   "res_inplace" (1)     halo kernel, 64-channel residual layers: the residual tile lands in the output staging buffer
+ *                         (frees shared memory for a fourth halo stage and the second MMA warp); 0: separate buffers
  *   "fuse_head" (0)       softmax/argmax/merge inside the last conv's epilogue (bit-identical, measured slower)
  *   "sub_batch_mb" (0)    L2 budget for depth-first sub-batches, 0 = off
  * Debugging aids: "sync_each" (synchronise after every op and name the one that failed), "halo_prof" (per-launch

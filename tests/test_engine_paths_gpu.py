@@ -26,7 +26,8 @@ def _inputs(shape=(2, 70, 100), seed=11):
 
 
 @pytest.mark.parametrize("flag,value", [("tma_epilogue", 0), ("mma_warps", 1), ("epi_groups", 0), ("fuse_pool", 0),
-                                        ("halo_a_stages", 2), ("halo2_mma2", 1), ("halo_mt", 1), ("halo2_tma", 0), ("stem", 2), ("stem", 1), ("tc_smem_epilogue", 0)])
+                                        ("halo_a_stages", 2), ("halo2_mma2", 1), ("halo_mt", 1), ("halo2_tma", 0), ("stem", 2), ("stem", 1), ("tc_smem_epilogue", 0),
+                                        ("res_inplace", 0), ("el_tma_epilogue", 0)])
 def test_pipeline_switches_are_bit_identical(engine, unet_r34, flag, value):
     _, model = unet_r34
     x = _inputs()
@@ -36,7 +37,8 @@ def test_pipeline_switches_are_bit_identical(engine, unet_r34, flag, value):
         got = engine.forward_logits(model, x)
     finally:
         engine.set_flag(flag, {"tma_epilogue": 1, "mma_warps": 2, "epi_groups": 1, "fuse_pool": 1,
-                               "halo_a_stages": 8, "halo2_mma2": 0, "halo_mt": 2, "halo2_tma": 1, "stem": 3, "tc_smem_epilogue": 1}[flag])
+                               "halo_a_stages": 8, "halo2_mma2": 0, "halo_mt": 2, "halo2_tma": 1, "stem": 3, "tc_smem_epilogue": 1,
+                               "res_inplace": 1, "el_tma_epilogue": 1}[flag])
     assert np.array_equal(got, want), f"{flag}={value}: max |diff| {np.abs(got - want).max()}"
 
 
@@ -45,7 +47,8 @@ def test_pipeline_switches_bit_identical_on_larger_images(engine, unet_r34):
     _, model = unet_r34
     x = _inputs((3, 300, 420), 5)
     want = engine.forward_logits(model, x)
-    for flag, value, back in (("tma_epilogue", 0, 1), ("mma_warps", 1, 2), ("halo_mt", 1, 2), ("stem", 2, 3), ("stem", 1, 3)):
+    for flag, value, back in (("tma_epilogue", 0, 1), ("mma_warps", 1, 2), ("halo_mt", 1, 2), ("stem", 2, 3), ("stem", 1, 3),
+                              ("res_inplace", 0, 1), ("el_tma_epilogue", 0, 1)):
         engine.set_flag(flag, value)
         try:
             got = engine.forward_logits(model, x)

@@ -186,8 +186,11 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   uint8_t* b_area = smem + (size_t)p.a_stages * p.a_stage_bytes;
   const size_t b_area_bytes = p.b_stages ? (size_t)p.b_stages * p.b_bytes : (size_t)p.ncs * 9 * p.b_bytes;
   uint8_t* out_stage = b_area + b_area_bytes;
-  uint8_t* res_stage = out_stage + (size_t)p.out_bufs * p.out_buf_bytes;
-  HaloCtl* ctl = reinterpret_cast<HaloCtl*>(res_stage + (size_t)p.res_bufs * p.out_buf_bytes);
+  // res_inplace: the residual tile is fetched INTO the staging buffer of its tile and overwritten by the output
+  // (each thread reads and writes the same 16-byte chunks) -- half the staging memory, which buys the fourth
+  // halo stage / second MMA warp for the 64-channel residual layers
+  uint8_t* res_stage = p.res_inplace ? out_stage : out_stage + (size_t)p.out_bufs * p.out_buf_bytes;
+  HaloCtl* ctl = reinterpret_cast<HaloCtl*>(out_stage + (size_t)(p.out_bufs + (p.res_inplace ? 0 : p.res_bufs)) * p.out_buf_bytes);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + kHaloCtlBytes);
   float* const bias_l = bias_s;  // launch-relative index (tile-local channel)
 
@@ -249,7 +252,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       int n_tile, X0, Y0, n;
       halo_decode(p, t, n_tile, X0, Y0, n);
       pc.count<2>();
-      if (p.res_map) {
+      if (p.res_map && !p.res_inplace) {
         // residual tile of this output tile, in the epilogue's staging layout
         mbar_wait(&ctl->res_empty[rb], rph ^ 1);
         if (elect_one()) {
@@ -306,6 +309,21 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       if (smem_epi && lane == 0) {
         int ob = 0;
         uint32_t oph = 0;
+        // in-place residual: this thread also fetches the residual tiles -- the tile that reuses a staging
+        // buffer is requested the moment TMA has read the previous output out of it
+        auto fetch_res = [&](int tt, int buf) {
+          if (tt >= total_tiles) return;
+          int n_tile, X0, Y0, n;
+          halo_decode(p, tt, n_tile, X0, Y0, n);
+          const int groups = (p.BN + 63) >> 6;
+          const uint32_t gbytes = p.BN >= 64 ? 16384u : 8192u;
+          mbar_arrive_expect_tx(&ctl->res_full[buf], groups * gbytes);
+          for (int g = 0; g < groups; ++g)
+            tma_load_5d(p.res_map, &ctl->res_full[buf], out_stage + (size_t)buf * p.out_buf_bytes + g * gbytes,
+                        p.cout_off + n_tile * p.BN + g * 64, X0, 0, Y0, n);
+        };
+        if (p.res_inplace)
+          for (int i = 0; i < p.out_bufs; ++i) fetch_res(blockIdx.x + i * (int)gridDim.x, i);
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
           mbar_wait(&ctl->out_full[ob], oph);
           if (!(p.dbg & 4)) {
@@ -324,7 +342,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           // this warp has nothing else to do; releasing one store late would make the two
           // epilogue groups wait for each other
           tma_store_wait_read<0>();
-          mbar_arrive(&ctl->out_empty[ob]);
+          if (p.res_inplace) fetch_res(t + p.out_bufs * (int)gridDim.x, ob);
+          else mbar_arrive(&ctl->out_empty[ob]);
           if (++ob == p.out_bufs) {
             ob = 0;
             oph ^= 1;
@@ -491,7 +510,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         if (c1 < p.BN) tmem_ld_32x32b_x32(taddr + c1, v[1]);
         tmem_ld_wait();
         if (has_res) mbar_wait(&ctl->res_full[rb], rph);
-        mbar_wait(&ctl->out_empty[ob], oph ^ 1);  // TMA has read the previous tile out of this buffer
+        // TMA has read the previous tile out of this buffer (in-place residual: implied by the residual's arrival)
+        if (!p.res_inplace) mbar_wait(&ctl->out_empty[ob], oph ^ 1);
         pc.lap<3>();
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
@@ -565,7 +585,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       if (lane == 0) {
         mbar_arrive(&ctl->out_full[ob]);
         mbar_arrive(&ctl->acc_empty[acc]);
-        if (has_res) mbar_arrive(&ctl->res_empty[rb]);
+        if (has_res && !p.res_inplace) mbar_arrive(&ctl->res_empty[rb]);
       }
       pc.lap<5>();
       acc += G;
@@ -1602,7 +1622,7 @@ cudaError_t launch_conv_halo_el(const ConvHaloElParams& p0, int num_sms, cudaStr
 
 size_t conv_halo_smem_bytes(const ConvHaloParams& p) {
   const size_t b = p.b_stages ? (size_t)p.b_stages * p.b_bytes : (size_t)p.ncs * 9 * p.b_bytes;
-  return (size_t)p.a_stages * p.a_stage_bytes + b + (size_t)(p.out_bufs + p.res_bufs) * p.out_buf_bytes +
+  return (size_t)p.a_stages * p.a_stage_bytes + b + (size_t)(p.out_bufs + (p.res_inplace ? 0 : p.res_bufs)) * p.out_buf_bytes +
          kHaloCtlBytes + kHaloBiasBytes + 1024;
 }
 

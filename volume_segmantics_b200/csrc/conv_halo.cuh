@@ -67,6 +67,7 @@ struct ConvHaloParams {
   const TmaDesc* out_map;   // box {64 ch (16 bit) | cout (f32), 8, 1, 16, 1}
   const TmaDesc* res_map;   // same box over the residual tensor, or null
   int32_t out_bufs, res_bufs;  // staging buffers (1 or 2 / 0, 1 or 2)
+  int32_t res_inplace;         // 1: residual tiles land in the output staging buffers (out_bufs == res_bufs == 2), fetched by the store thread
   int32_t out_buf_bytes;       // bytes per staging buffer (multiple of 1024)
   // epi_groups == 2 (BN <= 64, out_bufs == 2): the eight epilogue warps form two groups of
   // four that take alternate tiles, each with its own staging buffer -- the per-tile latency

@@ -189,6 +189,7 @@ struct vsb_engine {
   bool halo2_mma2 = false;       // vsb_set_flag("halo2_mma2", 1): two MMA warps in the cp.async halo kernel as well
   bool no_mma2 = false;          // vsb_set_flag("mma_warps", 1): a single MMA issuing warp everywhere
   bool no_s2d_up = false;        // vsb_set_flag("s2d_up", 0): decoder conv1 layers on the parity-split kernels
+  bool no_res_inplace = false;   // vsb_set_flag("res_inplace", 0): separate residual staging buffers in the halo kernel
   int el_a_stages = 2;           // vsb_set_flag("el_a_stages", n): halo ring depth of the entry-list kernel
   bool no_el_tma_epilogue = false;  // vsb_set_flag("el_tma_epilogue", 0): per-thread stores in the entry-list kernel
   bool no_epi_groups = false;    // vsb_set_flag("epi_groups", 0): one epilogue group even for BN <= 64
@@ -814,6 +815,7 @@ int configure_halo_pipeline(vsb_engine* e, ConvPlan& cp, vsb::ConvHaloParams& h,
   h.out_map = h.res_map = nullptr;
   h.out_bufs = h.res_bufs = 0;
   h.out_buf_bytes = 0;
+  h.res_inplace = 0;
   const bool has_res = op.res >= 0;
   bool tma_epi = !e->no_tma_epilogue && h.n_tiles == 1;
   if (ot.dtype == 0)
@@ -824,10 +826,11 @@ int configure_halo_pipeline(vsb_engine* e, ConvPlan& cp, vsb::ConvHaloParams& h,
                                     : (int)align_up((size_t)128 * op.cout * 4, 1024);
     h.out_bufs = h.out_buf_bytes <= 16384 ? 2 : 1;
     h.res_bufs = has_res ? h.out_bufs : 0;
+    h.res_inplace = (has_res && h.out_bufs == 2 && ot.dtype == 0 && !e->no_res_inplace) ? 1 : 0;
     // Only where the weights stay resident next to the staging buffers: streamed-weight
     // launches (BN >= 128) need the shared memory for their B ring (measured: 5 instead of 8
     // weight stages cost more than the scattered stores).
-    const size_t staging = (size_t)(h.out_bufs + h.res_bufs) * h.out_buf_bytes;
+    const size_t staging = (size_t)(h.out_bufs + (h.res_inplace ? 0 : h.res_bufs)) * h.out_buf_bytes;
     const size_t all = 227 * 1024 - 1024 - 1024 - 2048 * 4;
     if ((size_t)h.ncs * 9 * h.b_bytes + 3 * (size_t)h.a_stage_bytes + staging > all) {
       tma_epi = false;
@@ -835,9 +838,11 @@ int configure_halo_pipeline(vsb_engine* e, ConvPlan& cp, vsb::ConvHaloParams& h,
       h.out_buf_bytes = 0;
     }
   }
+  if (!tma_epi) h.res_inplace = 0;
   h.epi_groups = (tma_epi && h.out_bufs == 2 && h.BN <= 64 && !e->no_epi_groups) ? 2 : 1;
   h.mma_warps = 1;
-  const size_t usable = 227 * 1024 - 1024 - 1024 - 2048 * 4 - (size_t)(h.out_bufs + h.res_bufs) * h.out_buf_bytes;
+  const size_t usable =
+      227 * 1024 - 1024 - 1024 - 2048 * 4 - (size_t)(h.out_bufs + (h.res_inplace ? 0 : h.res_bufs)) * h.out_buf_bytes;
   const size_t res_bytes = (size_t)h.ncs * 9 * h.b_bytes;
   if (h.n_tiles == 1 && res_bytes + 2 * (size_t)h.a_stage_bytes <= usable) {
     h.b_stages = 0;
@@ -2170,6 +2175,7 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
   else if (n == "stem") { e->stem_version = value; free_workspace(e); }
   else if (n == "stem_dbg") e->stem_dbg = value;
   else if (n == "s2d_up") e->no_s2d_up = value == 0;
+  else if (n == "res_inplace") { e->no_res_inplace = value == 0; free_workspace(e); }
   else if (n == "el_tma_epilogue") { e->no_el_tma_epilogue = value == 0; free_workspace(e); }
   else if (n == "el_a_stages") { e->el_a_stages = std::max(2, std::min(value, 4)); free_workspace(e); }
   else if (n == "row_batch_mpx") e->row_batch_px = (int64_t)value << 20;
