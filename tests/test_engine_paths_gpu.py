@@ -87,22 +87,25 @@ def test_s2d_tail_matches_plain_tail(engine, monkeypatch, classes):
     ("U_NET", "unet", "resnet50", 2, (2, 70, 100)),        # skip tensors of 256 / 512 / 1024 channels
     ("U_NET_PLUS_PLUS", "unetplusplus", "resnext50_32x4d", 6, (2, 70, 100)),  # several skip sources per layer
 ])
-def test_s2d_up_concat_matches_parity_split(engine, mt, arch, enc, classes, shape):
+@pytest.mark.parametrize("flag", ["s2d_up", "el_conv"])
+def test_s2d_up_concat_matches_parity_split(engine, mt, arch, enc, classes, shape, flag):
     """Decoder conv1 layers as space-to-depth convolutions (conv_halo_el_kernel, vsb_op.mode == 2)  vs  the
     parity-split kernels on the same plan: the up-sampled taps are summed before the one rounding to 16 bit
-    and the products are accumulated in another order, so logits agree to 16-bit noise."""
+    and the products are accumulated in another order, so logits agree to 16-bit noise.
+    "el_conv": the same kernel for 32 -> 32 convolutions (space-to-depth form) and stride-2 3x3 convolutions (parity
+    planes of the input): identical products, another summation order."""
     oracle = make_random_model(arch, enc, classes, seed=6)
     model = B200SegmentationModel(mt, enc, classes)
     model.load_state_dict(oracle.state_dict())
     x = _inputs(shape, 13)
     got = engine.forward_logits(model, x)
-    engine.set_flag("s2d_up", 0)
+    engine.set_flag(flag, 0)
     try:
         want = engine.forward_logits(model, x)
     finally:
-        engine.set_flag("s2d_up", 1)
+        engine.set_flag(flag, 1)
     err = np.abs(got - want).max()
-    print(f"[s2d_up {mt}/{enc} {shape}] max |logit diff| {err:.2e} (|logits| max {np.abs(want).max():.3f}), "
+    print(f"[{flag} {mt}/{enc} {shape}] max |logit diff| {err:.2e} (|logits| max {np.abs(want).max():.3f}), "
           f"identical {np.array_equal(got, want)}")
     assert not np.array_equal(got, want), "the space-to-depth path did not run"
     assert err < 5e-3 * max(1.0, np.abs(want).max())

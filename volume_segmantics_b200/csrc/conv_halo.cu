@@ -837,14 +837,19 @@ conv_halo_el_kernel(const __grid_constant__ ConvHaloElParams p) {
           }
           const bool last = (en.grp >> 31) != 0;
           if (elect_one()) {
-            const uint32_t ncol0 = en.ncol0_n & 0xffffu, nn = en.ncol0_n >> 16;
+            const uint32_t ncol0 = en.ncol0_n & 0xfffu, nn = (en.ncol0_n >> 16) & 0xfffu, kmask = en.ncol0_n >> 28;
             const uint32_t idesc = umma_idesc_act(128, (int)nn);
             const uint64_t at = desc_add(a_stage_desc, en.ab_off16 & 0xffffu);
             const uint64_t bt = desc_add(b_desc0, bs * b_step + (en.ab_off16 >> 16));
             const uint32_t d = d_tmem + ncol0;
+            uint32_t af = accf;
 #pragma unroll
             for (int k = 0; k < KSTEPS; ++k)
-              if (k == 0 || !(p.dbg & 8)) umma_bf16_ss(d, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc, k != 0 ? 1u : accf);
+              if ((kmask >> k) & 1u) {  // K-steps whose weights are all zero are not issued
+                umma_bf16_ss(d, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc, af);
+                af = 1u;
+                if (p.dbg & 8) break;
+              }
             if (last) umma_commit(&ctl->b_empty[bs]);
             if (ei == s.e_end - 1) {
               umma_commit(&ctl->a_empty[as]);
@@ -926,8 +931,12 @@ conv_halo_el_kernel(const __grid_constant__ ConvHaloElParams p) {
           named_bar_sync(1, 32 * HALO_EPI_WARPS);
           if (issuer && !(p.dbg & 4)) {
             const int chs = ch0 + g * 64;
-            const int cls = chs >> p.cout_log2, cpl = chs & (p.cout - 1);
-            tma_store_5d(p.out_map, stage + (unit & 1u) * 16384u, (cls & 1) * p.cout + cpl, X0 + m * 8, cls >> 1, Y0, n);
+            if (p.s2d_out) {
+              const int cls = chs >> p.cout_log2, cpl = chs & (p.cout - 1);
+              tma_store_5d(p.out_map, stage + (unit & 1u) * 16384u, (cls & 1) * p.cout + cpl, X0 + m * 8, cls >> 1, Y0, n);
+            } else {
+              tma_store_5d(p.out_map, stage + (unit & 1u) * 16384u, chs, X0 + m * 8, 0, Y0, n);
+            }
             tma_store_commit();
           }
         }
@@ -970,9 +979,13 @@ conv_halo_el_kernel(const __grid_constant__ ConvHaloElParams p) {
           if (valid) {
             // space-to-depth columns [chs, chs + 32): sub-pixel (a, b) = class, plain channels cpl .. cpl + 31
             const int chs = ch0 + c;
-            const int cls = chs >> p.cout_log2, cpl = chs & (p.cout - 1);
-            const int64_t pix = ((int64_t)n * OH + 2 * oy + (cls >> 1)) * OW + 2 * ox + (cls & 1);
-            epilogue_chunk32(eo, v, bias_s + (chs - cpl), pix, cpl);
+            if (p.s2d_out) {
+              const int cls = chs >> p.cout_log2, cpl = chs & (p.cout - 1);
+              const int64_t pix = ((int64_t)n * OH + 2 * oy + (cls >> 1)) * OW + 2 * ox + (cls & 1);
+              epilogue_chunk32(eo, v, bias_s + (chs - cpl), pix, cpl);
+            } else {
+              epilogue_chunk32(eo, v, bias_s, ((int64_t)n * p.H + oy) * p.W + ox, chs);
+            }
           }
         }
         tc_fence_before_sync();

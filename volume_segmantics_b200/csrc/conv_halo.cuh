@@ -138,7 +138,7 @@ struct HaloSlabRef {
 struct HaloEntry {
   uint32_t ab_off16;  // [15:0] tap offset inside the halo tile, [31:16] image offset inside the ring stage (16-byte units)
   uint32_t w_off;     // byte offset of the image ([n][64] pre-swizzled rows) from wpacked
-  uint32_t ncol0_n;   // first GEMM column | columns << 16 (multiples of 16)
+  uint32_t ncol0_n;   // [11:0] first GEMM column, [27:16] columns (multiples of 16), [31:28] K-steps with non-zero weights
   uint32_t grp;       // [30:0] bytes of the group, on its first entry (else 0); bit 31: last entry of its group
 };
 constexpr int HALO_EL_MAX_SLABS = 112, HALO_EL_MAX_ENTRIES = 352, HALO_EL_MAX_NTILES = 4;
@@ -147,13 +147,14 @@ struct ConvHaloElParams {
   const uint8_t* wpacked;
   const float* bias;           // [n_tiles * BN], index = space-to-depth channel
   void* out;                   // plain 16-bit NHWC [NB, 2H, 2W, cout]
-  const TmaDesc* out_map;      // folded map of `out`, box {64, 8, 1, 16, 1}: epilogue through shared memory + TMA store; null: per-thread stores
+  const TmaDesc* out_map;      // map of `out` (folded when s2d_out), box {64, 8, 1, 16, 1}: epilogue through shared memory + TMA store; null: per-thread stores
   const HaloSlabRef* slabs;
   const HaloEntry* entries;
   int32_t tile_begin[HALO_EL_MAX_NTILES + 1];  // slab refs of N tile t: [tile_begin[t], tile_begin[t+1])
   int32_t n_slabs, n_entries;
   int32_t relu;
   int32_t cout, cout_log2;     // channels of the plain output; space-to-depth channel = (a*2+b)*cout + c
+  int32_t s2d_out;             // 1: GEMM columns are space-to-depth channels of an output of size 2H x 2W; 0: plain output H x W
   int32_t BN, n_tiles;
   int32_t NB, H, W;            // space-to-depth grid (half the output size)
   int32_t n_base;

@@ -106,6 +106,7 @@ struct ConvPlan {
   vsb::ConvHalo2Params h2params{};
   // space-to-depth lowering of `upsample x2 + concat -> conv3x3` (op.mode == 2, conv_halo.cuh ConvHaloElParams)
   bool el_ok = false, use_el = false;
+  int el_kind = 0;  // 1: space-to-depth output (grid = half the output size), 2: plain output (stride-2 lowering)
   uint8_t* d_wel = nullptr;
   float* d_bias_el = nullptr;
   vsb::HaloSlabRef* d_el_slabs = nullptr;
@@ -190,6 +191,7 @@ struct vsb_engine {
   bool no_mma2 = false;          // vsb_set_flag("mma_warps", 1): a single MMA issuing warp everywhere
   bool no_s2d_up = false;        // vsb_set_flag("s2d_up", 0): decoder conv1 layers on the parity-split kernels
   bool no_res_inplace = false;   // vsb_set_flag("res_inplace", 0): separate residual staging buffers in the halo kernel
+  bool no_el_conv = false;       // vsb_set_flag("el_conv", 0): 32 -> 32 and stride-2 3x3 convolutions on their round-1 kernels
   int el_a_stages = 2;           // vsb_set_flag("el_a_stages", n): halo ring depth of the entry-list kernel
   bool no_el_tma_epilogue = false;  // vsb_set_flag("el_tma_epilogue", 0): per-thread stores in the entry-list kernel
   bool no_epi_groups = false;    // vsb_set_flag("epi_groups", 0): one epilogue group even for BN <= 64
@@ -279,79 +281,50 @@ bool conv_tc_eligible(const vsb_engine* e, const vsb_op& op) {
   return true;
 }
 
-// Space-to-depth lowering of a decoder convolution (op.mode == 2): the plan carries, at blob offset
-// op.factor * 256, the 16-bit weights [4*cout][3][3][Cup + 4*Cskip] of the equivalent 3x3 convolution at half
-// the output resolution (plan.py s2d_up_concat_weights: K = channels of the up-sampled source at its own
-// resolution, then the (py, px, c) sub-pixels of the concatenated skip sources).  Builds the slab refs,
-// the (slab, tap) entries with their non-zero GEMM column ranges and the packed weight images.
-int prepare_el_plan(vsb_engine* e, int oi) {
+// ---- entry-list halo kernel (conv_halo.cuh ConvHaloElParams): three lowerings share one table builder ----
+// A lowered convolution is a 3x3 pad-1 stride-1 convolution on the "grid" (half the resolution of the folded
+// sources) with weights w[N][3][3][K]; `slabs` says where every 64-channel K-slab comes from.
+struct ElSlabSpec {
+  int map, c, p;  // source index, box channel coordinate (folded view: px*C + c), row parity
+  int k0[2];      // K index of channels 0 and 32 of the slab (a folded slab may straddle px when C = 32 mod 64)
+};
+// Builds slab refs, (slab, tap) entries with their non-zero GEMM column range and K-step mask, and the packed
+// weight images.  kind: 1 = space-to-depth output (N = 4*cout, un-shuffled by the epilogue), 2 = plain output.
+int build_el_tables(vsb_engine* e, int oi, const uint16_t* w, int N, int K, const std::vector<ElSlabSpec>& slabs,
+                    int kind) {
   const vsb_op& op = e->ops[oi];
   ConvPlan& cp = e->conv[oi];
-  cp.el_ok = false;
-  if (op.kind != VSB_OP_CONV || op.mode != 2) return VSB_OK;
-  if (op.kh != 3 || op.kw != 3 || op.stride != 1 || op.pad != 1 || op.dil != 1 || op.groups != 1 || op.res >= 0 ||
-      op.n_src < 2 || !op.src_up[0])
-    return fail(VSB_ERR_INVALID, "op %d: mode 2 needs conv3x3 pad 1 over [up-sampled source, skip sources...]", oi);
-  const vsb_tensor_desc& ot = e->tdesc[op.out];
-  const int cout = op.cout;
-  if (ot.dtype != 0 || ot.ds_log2 < 0 || (cout != 32 && cout != 64 && cout != 128 && cout != 256)) return VSB_OK;
-  const int Cup = e->tdesc[op.src[0]].channels;
-  if (Cup % 64 || e->tdesc[op.src[0]].dtype != 0 || e->tdesc[op.src[0]].ds_log2 != ot.ds_log2 + 1) return VSB_OK;
-  int Cskip = 0;
-  std::vector<int> skip_off(op.n_src, 0);
-  for (int s = 1; s < op.n_src; ++s) {
-    const vsb_tensor_desc& t = e->tdesc[op.src[s]];
-    if (op.src_up[s] || t.channels % 32 || t.dtype != 0 || t.ds_log2 != ot.ds_log2) return VSB_OK;
-    skip_off[s] = Cskip;
-    Cskip += t.channels;
-  }
-  if (Cup + Cskip != op.cin) return fail(VSB_ERR_INVALID, "op %d: cin %d != sum of sources", oi, op.cin);
-  const int K = Cup + 4 * Cskip, N = 4 * cout;
-  const int64_t woff = (int64_t)op.factor * 256;
-  if (op.factor <= 0 || (size_t)woff + (size_t)N * 9 * K * 2 > e->weight_bytes)
-    return fail(VSB_ERR_INVALID, "op %d: space-to-depth weight range", oi);
-  const uint16_t* w = reinterpret_cast<const uint16_t*>(e->h_weights.data() + woff);  // [N][3][3][K]
   const int n_tiles = (N + 255) / 256, BN = N / n_tiles;
-  if (n_tiles > vsb::HALO_EL_MAX_NTILES) return VSB_OK;
-
-  // K-slabs of 64 channels: (source, box channel coordinate, row parity, K index of slab channel 0, run length)
-  // (box channel coordinate d = px*C + c of the folded view; a slab may straddle px when C = 32 mod 64, so the
-  // K index is kept per 32-channel half)
-  struct Slab { int map, c, p; int k0[2]; };
-  std::vector<Slab> slabs;
-  for (int c0 = 0; c0 < Cup; c0 += 64) slabs.push_back({0, c0, 0, {c0, c0 + 32}});
-  for (int s = 1; s < op.n_src; ++s) {
-    const int C = e->tdesc[op.src[s]].channels;
-    for (int py = 0; py < 2; ++py)
-      for (int d0 = 0; d0 < 2 * C; d0 += 64) {
-        auto kidx = [&](int d) { const int px = d / C, c = d % C; return Cup + (py * 2 + px) * Cskip + skip_off[s] + c; };
-        slabs.push_back({s, d0, py, {kidx(d0), kidx(d0 + 32)}});
-      }
-  }
+  if (n_tiles > vsb::HALO_EL_MAX_NTILES || BN * n_tiles != N || BN % 16) return VSB_OK;
   const int mt = 2, HWt = 8 * mt + 2;
   std::vector<vsb::HaloSlabRef> refs;
   std::vector<vsb::HaloEntry> entries;
   std::vector<uint8_t> packed;
   int tile_begin[vsb::HALO_EL_MAX_NTILES + 1] = {0};
-  auto wv = [&](int o, int tap, int k) { return w[((int64_t)o * 9 + tap) * K + k]; };
   for (int nt = 0; nt < n_tiles; ++nt) {
     tile_begin[nt] = (int)refs.size();
     bool first = true;
-    for (const Slab& sl : slabs) {
+    for (const ElSlabSpec& sl : slabs) {
       vsb::HaloSlabRef ref{sl.map, sl.c, sl.p, (int)entries.size(), 0};
       int grp_first = -1, grp_rows = 0;  // open group of this slab
-      // the centre tap of the first slab goes first: it feeds every sub-pixel, so it initialises all BN columns
-      int order[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
+      // the centre tap of the first slab goes first: it must initialise all BN columns of the accumulator
+      const int order[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
       for (int ti = 0; ti < 9; ++ti) {
         const int tap = order[ti];
-        int r0 = BN, r1 = 0;  // non-zero row range of the image
+        int r0 = BN, r1 = 0;    // non-zero row range of the image
+        uint32_t kmask = 0;     // K-steps (16 channels) with any non-zero weight
         for (int n = 0; n < BN; ++n) {
+          const uint16_t* wr = w + ((int64_t)(nt * BN + n) * 9 + tap) * K;
           bool nz = false;
-          for (int h = 0; h < 2 && !nz; ++h)
-            for (int j = 0; j < 32 && !nz; ++j) nz = (wv(nt * BN + n, tap, sl.k0[h] + j) & 0x7fffu) != 0;
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint16_t* q = wr + sl.k0[ks >> 1] + (ks & 1) * 16;
+            bool z = true;
+            for (int j = 0; j < 16 && z; ++j) z = (q[j] & 0x7fffu) == 0;
+            if (!z) { kmask |= 1u << ks; nz = true; }
+          }
           if (nz) { r0 = std::min(r0, n); r1 = std::max(r1, n + 1); }
         }
-        if (first) { r0 = 0; r1 = BN; }
+        if (first) { r0 = 0; r1 = BN; kmask |= 1u; }
         if (r1 <= r0) continue;
         r0 = r0 / 16 * 16;
         r1 = (r1 + 15) / 16 * 16;
@@ -363,7 +336,7 @@ int prepare_el_plan(vsb_engine* e, int oi) {
         }
         en.ab_off16 = (uint32_t)(((tap / 3) * HWt + tap % 3) * 8) | ((uint32_t)(grp_rows * 8) << 16);  // 128-byte pixels / rows
         en.w_off = (uint32_t)packed.size();
-        en.ncol0_n = (uint32_t)r0 | ((uint32_t)(r1 - r0) << 16);
+        en.ncol0_n = (uint32_t)r0 | ((uint32_t)(r1 - r0) << 16) | (kmask << 28);
         en.grp = 0;
         grp_rows += r1 - r0;
         const size_t base = packed.size();
@@ -394,7 +367,7 @@ int prepare_el_plan(vsb_engine* e, int oi) {
   CK(cudaMemcpy(cp.d_el_entries, entries.data(), entries.size() * sizeof(vsb::HaloEntry), cudaMemcpyHostToDevice));
   std::vector<float> bias(N, 0.f);
   if (op.b_off >= 0)
-    for (int i = 0; i < N; ++i) memcpy(&bias[i], e->h_weights.data() + op.b_off + (size_t)(i % cout) * 4, 4);
+    for (int i = 0; i < N; ++i) memcpy(&bias[i], e->h_weights.data() + op.b_off + (size_t)(i % op.cout) * 4, 4);
   CK(cudaMalloc(&cp.d_el_maps, sizeof(TmaDesc) * (VSB_MAX_SRC + 1)));  // sources, output
   CK(cudaMalloc(&cp.d_bias_el, N * 4));
   CK(cudaMemcpy(cp.d_bias_el, bias.data(), N * 4, cudaMemcpyHostToDevice));
@@ -409,12 +382,110 @@ int prepare_el_plan(vsb_engine* e, int oi) {
   h.n_slabs = (int)refs.size();
   h.n_entries = (int)entries.size();
   h.relu = op.relu;
-  h.cout = cout;
-  h.cout_log2 = ilog2(cout);
+  h.cout = op.cout;
+  h.cout_log2 = ilog2(op.cout);
+  h.s2d_out = kind == 1;
   h.BN = BN;
   h.n_tiles = n_tiles;
   h.mt = mt;
+  cp.el_kind = kind;
   cp.el_ok = true;
+  return VSB_OK;
+}
+
+// K-slabs of the space-to-depth ("folded") view of source s: (py, 64 channels of px*C + c).
+static void el_folded_slabs(std::vector<ElSlabSpec>& slabs, int s, int C, int kbase, int Ctotal, int coff) {
+  for (int py = 0; py < 2; ++py)
+    for (int d0 = 0; d0 < 2 * C; d0 += 64) {
+      auto kidx = [&](int d) { const int px = d / C, c = d % C; return kbase + (py * 2 + px) * Ctotal + coff + c; };
+      slabs.push_back({s, d0, py, {kidx(d0), kidx(d0 + 32)}});
+    }
+}
+
+// Lowering 1 (op.mode == 2, written by plan.py s2d_up_concat_weights): decoder `upsample x2 + concat -> conv3x3`
+// as a convolution at half the output resolution.  The blob holds, at offset op.factor * 256, the weights
+// [4*cout][3][3][Cup + 4*Cskip]: K = channels of the up-sampled source at its own resolution, then the
+// (py, px, c) sub-pixels of the concatenated skip sources; output channel (a*2+b)*cout + c = pixel (2i+a, 2j+b).
+// Lowering 2 (built here, exact): a plain 3x3 stride-1 convolution with 32 output channels as a convolution
+// between the space-to-depth views of its input and output (N = 128 instead of 32).
+// Lowering 3 (built here, exact): a 3x3 stride-2 pad-1 convolution as a stride-1 convolution over the
+// space-to-depth view of its input -- the nine taps become nine (parity plane, offset) pairs of FOUR halo boxes.
+int prepare_el_plan(vsb_engine* e, int oi) {
+  const vsb_op& op = e->ops[oi];
+  ConvPlan& cp = e->conv[oi];
+  cp.el_ok = false;
+  if (op.kind != VSB_OP_CONV || op.kh != 3 || op.kw != 3 || op.pad != 1 || op.dil != 1 || op.groups != 1 || op.n_src < 1)
+    return VSB_OK;
+  const vsb_tensor_desc& ot = e->tdesc[op.out];
+  if (ot.dtype != 0 || ot.ds_log2 < 0 || op.res >= 0) return VSB_OK;
+  const int cout = op.cout;
+  std::vector<ElSlabSpec> slabs;
+  if (op.mode == 2) {
+    if (op.stride != 1 || op.n_src < 2 || !op.src_up[0])
+      return fail(VSB_ERR_INVALID, "op %d: mode 2 needs conv3x3 pad 1 over [up-sampled source, skip sources...]", oi);
+    if (cout != 32 && cout != 64 && cout != 128 && cout != 256) return VSB_OK;
+    const int Cup = e->tdesc[op.src[0]].channels;
+    if (Cup % 64 || e->tdesc[op.src[0]].dtype != 0 || e->tdesc[op.src[0]].ds_log2 != ot.ds_log2 + 1) return VSB_OK;
+    int Cskip = 0;
+    for (int s = 1; s < op.n_src; ++s) {
+      const vsb_tensor_desc& t = e->tdesc[op.src[s]];
+      if (op.src_up[s] || t.channels % 32 || t.dtype != 0 || t.ds_log2 != ot.ds_log2) return VSB_OK;
+      Cskip += t.channels;
+    }
+    if (Cup + Cskip != op.cin) return fail(VSB_ERR_INVALID, "op %d: cin %d != sum of sources", oi, op.cin);
+    const int K = Cup + 4 * Cskip, N = 4 * cout;
+    const int64_t woff = (int64_t)op.factor * 256;
+    if (op.factor <= 0 || (size_t)woff + (size_t)N * 9 * K * 2 > e->weight_bytes)
+      return fail(VSB_ERR_INVALID, "op %d: space-to-depth weight range", oi);
+    for (int c0 = 0; c0 < Cup; c0 += 64) slabs.push_back({0, c0, 0, {c0, c0 + 32}});
+    for (int s = 1, coff = 0; s < op.n_src; ++s) {
+      el_folded_slabs(slabs, s, e->tdesc[op.src[s]].channels, Cup, Cskip, coff);
+      coff += e->tdesc[op.src[s]].channels;
+    }
+    return build_el_tables(e, oi, reinterpret_cast<const uint16_t*>(e->h_weights.data() + woff), N, K, slabs, 1);
+  }
+  if (op.mode != 0) return VSB_OK;
+  int Cin = 0;
+  for (int s = 0; s < op.n_src; ++s) {
+    const vsb_tensor_desc& t = e->tdesc[op.src[s]];
+    if (op.src_up[s] || t.channels % 32 || t.dtype != 0 || t.ds_log2 < 0) return VSB_OK;
+    Cin += t.channels;
+  }
+  if (Cin != op.cin) return VSB_OK;
+  const uint16_t* w = reinterpret_cast<const uint16_t*>(e->h_weights.data() + op.w_off);  // [cout][3][3][Cin]
+  auto floordiv2 = [](int v) { return v >= 0 ? v / 2 : -((1 - v) / 2); };
+  if (op.stride == 1 && cout == 32 && Cin == 32 && op.n_src == 1) {
+    // lowering 2: W2[(a*2+b)*O + o][dy+1][dx+1][(a2*2+b2)*I + i] = w[o][ky][kx][i], a + ky - 1 = 2*dy + a2
+    const int K = 4 * Cin, N = 4 * cout;
+    std::vector<uint16_t> w2((size_t)N * 9 * K, 0);
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx) {
+            const int r = a + ky - 1, c = b + kx - 1;
+            const int dy = floordiv2(r), a2 = r - 2 * dy, dx = floordiv2(c), b2 = c - 2 * dx;
+            for (int o = 0; o < cout; ++o)
+              memcpy(&w2[(((size_t)((a * 2 + b) * cout + o) * 3 + dy + 1) * 3 + dx + 1) * K + (a2 * 2 + b2) * Cin],
+                     &w[(((size_t)o * 3 + ky) * 3 + kx) * Cin], (size_t)Cin * 2);
+          }
+    el_folded_slabs(slabs, 0, Cin, 0, Cin, 0);
+    return build_el_tables(e, oi, w2.data(), N, K, slabs, 1);
+  }
+  if (op.stride == 2 && (cout == 64 || cout == 128 || cout == 256 || cout == 512) && Cin % 64 == 0 && op.n_src == 1 &&
+      e->tdesc[op.src[0]].ds_log2 + 1 == ot.ds_log2) {
+    // lowering 3: W2[o][ty+1][tx+1][(qy*2+qx)*I + i] = w[o][ky][kx][i], ky - 1 = 2*ty + qy
+    const int K = 4 * Cin, N = cout;
+    std::vector<uint16_t> w2((size_t)N * 9 * K, 0);
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ty = floordiv2(ky - 1), qy = ky - 1 - 2 * ty, tx = floordiv2(kx - 1), qx = kx - 1 - 2 * tx;
+        for (int o = 0; o < cout; ++o)
+          memcpy(&w2[(((size_t)o * 3 + ty + 1) * 3 + tx + 1) * K + (qy * 2 + qx) * Cin], &w[(((size_t)o * 3 + ky) * 3 + kx) * Cin],
+                 (size_t)Cin * 2);
+      }
+    el_folded_slabs(slabs, 0, Cin, 0, Cin, 0);
+    return build_el_tables(e, oi, w2.data(), N, K, slabs, 2);
+  }
   return VSB_OK;
 }
 
@@ -1294,9 +1365,10 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
       }
     }
     cp.use_el = false;
-    if (cp.el_ok && !(ot.H & 1) && !(ot.W & 1)) {
+    if (cp.el_ok && (cp.el_kind == 2 || (!(ot.H & 1) && !(ot.W & 1)))) {
       vsb::ConvHaloElParams& h = cp.elparams;
-      const int Hs = ot.H / 2, Ws = ot.W / 2;
+      // the grid the lowered convolution runs on: half the output (space-to-depth output) or the output itself
+      const int Hs = cp.el_kind == 1 ? ot.H / 2 : ot.H, Ws = cp.el_kind == 1 ? ot.W / 2 : ot.W;
       const int tx = (Ws + 8 * h.mt - 1) / (8 * h.mt), ty = (Hs + 15) / 16;
       const double eff = (double)Ws * Hs / ((double)tx * 8 * h.mt * ty * 16);
       const int HW = 8 * h.mt + 2, HH = 18;
@@ -1314,15 +1386,15 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
         bool ok = true;
         for (int s = 0; s < op.n_src && ok; ++s) {
           const TensorBuf& st = e->tens[op.src[s]];
-          if (s == 0) ok = st.H == Hs && st.W == Ws;
-          else ok = st.H == ot.H && st.W == ot.W;
+          const bool folded = !(op.mode == 2 && s == 0);  // all but the up-sampled source are read as parity planes
+          ok = folded ? (st.H == 2 * Hs && st.W == 2 * Ws) : (st.H == Hs && st.W == Ws);
           if (!ok) break;
-          int rc = make_tensor_map(e, &maps[s], st, nb, s != 0, 64, HW, HH, 1);
+          int rc = make_tensor_map(e, &maps[s], st, nb, folded, 64, HW, HH, 1);
           if (rc) return rc;
         }
         TmaDesc om;
         if (ok && tma_epi) {
-          int rc = make_tensor_map(e, &om, ot, nb, true, 64, 8, 16, 1);
+          int rc = make_tensor_map(e, &om, ot, nb, cp.el_kind == 1, 64, 8, 16, 1);
           if (rc) return rc;
         }
         if (ok) {
@@ -1422,7 +1494,7 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
   const vsb_op& op = e->ops[oi];
   ConvPlan& cp = e->conv[oi];
   const TensorBuf& ot = e->tens[op.out];
-  if (cp.use_el && e->conv_impl == 0 && !e->no_halo && !e->no_s2d_up) {
+  if (cp.use_el && e->conv_impl == 0 && !e->no_halo && !(op.mode == 2 ? e->no_s2d_up : e->no_el_conv)) {
     vsb::ConvHaloElParams h = cp.elparams;
     h.NB = nb;
     h.n_base = n0;
@@ -2175,6 +2247,7 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
   else if (n == "stem") { e->stem_version = value; free_workspace(e); }
   else if (n == "stem_dbg") e->stem_dbg = value;
   else if (n == "s2d_up") e->no_s2d_up = value == 0;
+  else if (n == "el_conv") e->no_el_conv = value == 0;
   else if (n == "res_inplace") { e->no_res_inplace = value == 0; free_workspace(e); }
   else if (n == "el_tma_epilogue") { e->no_el_tma_epilogue = value == 0; free_workspace(e); }
   else if (n == "el_a_stages") { e->el_a_stages = std::max(2, std::min(value, 4)); free_workspace(e); }
