@@ -233,6 +233,8 @@ int vsb_set_conv_impl(vsb_engine* e, int32_t impl);
  *   "el_tma_epilogue" (1) epilogue of that kernel through shared memory + TMA store (folded output map); 0: per-thread stores
  *   "res_inplace" (1)     halo kernel, 64-channel residual layers: the residual tile lands in the output staging buffer
  *                         (frees shared memory for a fourth halo stage and the second MMA warp); 0: separate buffers
+ *   "el_conv" (1)         32 -> 32 and dense stride-2 3x3 convolutions on that kernel (exact re-arrangements); 0: round-1 kernels
+ *   "dw_tc" (1)           depthwise 3x3 convolutions as block-diagonal tensor-core convolutions; 0: CUDA-core kernel
  *   "fuse_head" (0)       softmax/argmax/merge inside the last conv's epilogue (bit-identical, measured slower)
  *   "sub_batch_mb" (0)    L2 budget for depth-first sub-batches, 0 = off
  * Debugging aids: "sync_each" (synchronise after every op and name the one that failed), "halo_prof" (per-launch

@@ -64,6 +64,15 @@ ncustem)
       python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_stem.log 2>&1
   echo "ncu stem rc=$?"
   ;;
+ncuel)
+  # entry-list kernel: decoder.blocks.3.conv1 (4th launch of the kernel in a batch: b0, b1, b2, b3 conv1 after layer2/3/4.0.conv1)
+  timeout 300 python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_plain.log 2>&1 && \
+  timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k 'regex:conv_halo_el_kernel' -c 8 -f -o gpurun_out/r02_el \
+      python tests/layer_profile.py 1024 16 16 > gpurun_out/r02_ncu_el.log 2>&1
+  echo "ncu el rc=$?"
+  ncu -i gpurun_out/r02_el.ncu-rep --page raw --csv --metrics gpu__time_duration.sum,sm__inst_executed_pipe_tensor_op_hmma.avg.pct_of_peak_sustained_active,sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed > gpurun_out/r02_el_raw.csv 2>/dev/null
+  head -c 3000 gpurun_out/r02_el_raw.csv
+  ;;
 deeplab)
   timeout 600 python tests/layer_profile.py 2048 32 0 DEEPLABV3_PLUS resnet50 4 > gpurun_out/r02_layers_deeplab.txt 2>&1; tail -3 gpurun_out/r02_layers_deeplab.txt
   ;;

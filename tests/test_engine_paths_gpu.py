@@ -143,3 +143,23 @@ def test_per_tap_smem_epilogue_bit_identical_on_bottleneck_encoders(engine, mt, 
     finally:
         engine.set_flag("tc_smem_epilogue", 1)
     assert np.array_equal(got, want), f"max |diff| {np.abs(got - want).max()}"
+
+
+@pytest.mark.parametrize("shape", [(2, 150, 200), (2, 520, 650)])
+def test_depthwise_on_tensor_cores_matches_cuda_core_kernel(engine, shape):
+    """DeepLabV3+ depthwise 3x3 convolutions (304 channels at 1/4 resolution: a last block of 48 channels; 256 and
+    2048 channels at 1/16 with dilation 1 / 12 / 24 / 36) as block-diagonal tensor-core convolutions  vs  the
+    CUDA-core depthwise kernel: same 16-bit weights and fp32 accumulation, exact zeros added, another order."""
+    oracle = make_random_model("deeplabv3plus", "resnet50", 4, seed=4)
+    model = B200SegmentationModel("DEEPLABV3_PLUS", "resnet50", 4)
+    model.load_state_dict(oracle.state_dict())
+    x = _inputs(shape, 17)
+    got = engine.forward_logits(model, x)
+    engine.set_flag("dw_tc", 0)
+    try:
+        want = engine.forward_logits(model, x)
+    finally:
+        engine.set_flag("dw_tc", 1)
+    err = np.abs(got - want).max()
+    print(f"[dw_tc {shape}] max |logit diff| {err:.2e} (|logits| max {np.abs(want).max():.3f}), identical {np.array_equal(got, want)}")
+    assert err < 2e-3 * max(1.0, np.abs(want).max())

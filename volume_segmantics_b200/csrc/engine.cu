@@ -92,6 +92,8 @@ struct ConvPlan {
   bool halo_ok = false;   // plan-level eligibility
   bool use_halo = false;  // decided per workspace (tile efficiency)
   uint8_t* d_whalo = nullptr;
+  uint8_t* d_wdw = nullptr;   // depthwise CUDA-core kernel: weights [9][C]
+  std::vector<int> blk_src, blk_cin_off;  // grouped halo launches: source and channel offset of every 64-channel block
   vsb::ConvHaloParams hparams{};
   bool depthwise = false;     // groups == cin == cout, 3x3 stride 1: vectorised depthwise kernel, weights [9][C]
   bool grouped_s2 = false;    // groups > 1, 3x3 stride 2: per-block launches of the per-tap kernel (folded maps)
@@ -191,6 +193,7 @@ struct vsb_engine {
   bool no_mma2 = false;          // vsb_set_flag("mma_warps", 1): a single MMA issuing warp everywhere
   bool no_s2d_up = false;        // vsb_set_flag("s2d_up", 0): decoder conv1 layers on the parity-split kernels
   bool no_res_inplace = false;   // vsb_set_flag("res_inplace", 0): separate residual staging buffers in the halo kernel
+  bool no_dw_tc = false;         // vsb_set_flag("dw_tc", 0): depthwise convolutions on the CUDA-core kernel
   bool no_el_conv = false;       // vsb_set_flag("el_conv", 0): 32 -> 32 and stride-2 3x3 convolutions on their round-1 kernels
   int el_a_stages = 2;           // vsb_set_flag("el_a_stages", n): halo ring depth of the entry-list kernel
   bool no_el_tma_epilogue = false;  // vsb_set_flag("el_tma_epilogue", 0): per-thread stores in the entry-list kernel
@@ -526,21 +529,40 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
       for (int c = 0; c < op.cout; ++c)
         for (int tap = 0; tap < 9; ++tap)
           memcpy(&w[(size_t)tap * op.cout + c], e->h_weights.data() + op.w_off + ((int64_t)c * 9 + tap) * 2, 2);
-      CK(cudaMalloc(&cp.d_whalo, w.size() * 2));
-      CK(cudaMemcpy(cp.d_whalo, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+      CK(cudaMalloc(&cp.d_wdw, w.size() * 2));
+      CK(cudaMemcpy(cp.d_wdw, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
       cp.depthwise = true;
-      return VSB_OK;
+      // Round 2: a depthwise convolution is the extreme grouped convolution (one channel per group) and runs on
+      // the tensor-core grouped paths below with block-diagonal (here: diagonal) 64 x 64 weight images -- 63/64 of
+      // the products are zeros, and it is still 2.5-4x faster than the CUDA-core kernel, which is bound by its
+      // 16-bit <-> fp32 conversions (1.1 TB/s).  The CUDA-core kernel stays as the small-image / cross-check path.
     }
   }
   cp.grouped_halo = false;
-  if (op.kind == VSB_OP_CONV && op.groups > 1 && op.n_src == 1 && !op.src_up[0] && op.kh == 3 && op.kw == 3 &&
-      op.stride == 1 && op.pad == op.dil && (op.dil == 1 || op.dil == 2) && op.cin == op.cout && op.cin % 64 == 0 &&
-      64 % (op.cin / op.groups) == 0 && e->tdesc[op.src[0]].dtype == 0 && e->tdesc[op.out].dtype == 0 &&
-      e->tdesc[op.out].ds_log2 >= 0) {
+  // 64-channel block b reads channels [blk_cin_off[b], +64) of source blk_src[b]: a depthwise convolution over a
+  // channel concat (DeepLabV3+ decoder: 256 up-sampled ASPP channels + 48 high-resolution channels) never
+  // materialises the concat as long as every source but the last holds a multiple of 64 channels
+  cp.blk_src.clear();
+  cp.blk_cin_off.clear();
+  bool blocks_ok = op.kind == VSB_OP_CONV && op.n_src >= 1 && (op.n_src == 1 || cp.depthwise);
+  for (int s = 0; s < op.n_src && blocks_ok; ++s) {
+    const vsb_tensor_desc& t = e->tdesc[op.src[s]];
+    blocks_ok = !op.src_up[s] && t.dtype == 0 && t.channels % 8 == 0 && (s == op.n_src - 1 || t.channels % 64 == 0);
+    for (int c0 = 0; c0 < t.channels; c0 += 64) {
+      cp.blk_src.push_back(s);
+      cp.blk_cin_off.push_back(c0);
+    }
+  }
+  if (blocks_ok && op.groups > 1 && op.kh == 3 && op.kw == 3 &&
+      op.stride == 1 && op.pad == op.dil && (op.dil == 1 || op.dil == 2) && op.cin == op.cout && op.cin % 8 == 0 &&
+      (op.cin % 64 == 0 || op.res < 0) && 64 % (op.cin / op.groups) == 0 &&
+      e->tdesc[op.out].dtype == 0 && e->tdesc[op.out].ds_log2 >= 0) {
     // Block-diagonal packing: the 64 output channels of block b only see the 64 input
     // channels of block b (groups never straddle a block); cross-group weights are zero.
+    // A last block of fewer than 64 channels reads / writes past the channel count: TMA zero-fills the box,
+    // the epilogue skips channels >= cout.
     const int cg = op.cin / op.groups;
-    cp.n_blocks = op.cin / 64;
+    cp.n_blocks = (op.cin + 63) / 64;
     cp.BN = 64;
     cp.n_tiles = 1;
     const size_t img = 64 * 128;
@@ -550,6 +572,7 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
         uint8_t* dst = hp.data() + ((size_t)b * 9 + tap) * img;
         for (int n = 0; n < 64; ++n) {
           const int o = b * 64 + n;
+          if (o >= op.cout) break;
           const int g0 = (o / cg) * cg - b * 64;  // first input channel (block-local) of o's group
           for (int j = 0; j < cg; ++j) {
             const int k = g0 + j;  // block-local input channel
@@ -561,17 +584,19 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
       }
     CK(cudaMalloc(&cp.d_whalo, hp.size()));
     CK(cudaMemcpy(cp.d_whalo, hp.data(), hp.size(), cudaMemcpyHostToDevice));
-    std::vector<float> bias(op.cout, 0.f);
+    std::vector<float> bias((size_t)cp.n_blocks * 64, 0.f);
     if (op.b_off >= 0) memcpy(bias.data(), e->h_weights.data() + op.b_off, (size_t)op.cout * 4);
-    CK(cudaMalloc(&cp.d_bias_pad, op.cout * 4));
-    CK(cudaMemcpy(cp.d_bias_pad, bias.data(), op.cout * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&cp.d_bias_pad, bias.size() * 4));
+    CK(cudaMemcpy(cp.d_bias_pad, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&cp.d_maps, sizeof(TmaDesc) * 2 * VSB_MAX_SRC));  // [0,6): per-tap / halo / epilogue maps, [6,12): halo2 source maps
     cp.grouped_halo = true;
     return VSB_OK;
   }
   cp.grouped_s2 = false;
+  // stride 2 (ResNeXt), or stride 1 with a dilation the halo kernel has no tile for (ASPP depthwise, rates 12 / 24 / 36)
   if (op.kind == VSB_OP_CONV && op.groups > 1 && op.n_src == 1 && !op.src_up[0] && op.kh == 3 && op.kw == 3 &&
-      op.stride == 2 && op.pad == 1 && op.dil == 1 && op.cin == op.cout && op.cin % 64 == 0 &&
+      ((op.stride == 2 && op.pad == 1 && op.dil == 1) || (op.stride == 1 && op.pad == op.dil && op.dil > 2)) &&
+      op.cin == op.cout && op.cin % 64 == 0 &&
       64 % (op.cin / op.groups) == 0 && e->tdesc[op.src[0]].dtype == 0 && e->tdesc[op.out].dtype == 0 &&
       e->tdesc[op.out].ds_log2 >= 0) {
     const int cg = op.cin / op.groups, C = op.cin;
@@ -579,7 +604,7 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
     cp.BN = 64;
     cp.n_tiles = 1;
     cp.kb = 64;
-    cp.s2 = true;
+    cp.s2 = op.stride == 2;
     cp.ps = false;
     cp.runs.clear();
     cp.num_slabs = 9;
@@ -591,10 +616,17 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
       run.w_off16 = (int32_t)(tap * img / 16);
       run.w_step16 = 0;
       const int ty = tap / 3 - 1, tx = tap % 3 - 1;
-      run.cls[0][0] = (tx & 1) * C;  // folded view: c' = parity_x * C + c
-      run.cls[0][1] = tx >> 1;
-      run.cls[0][2] = ty & 1;
-      run.cls[0][3] = ty >> 1;
+      if (cp.s2) {
+        run.cls[0][0] = (tx & 1) * C;  // folded view: c' = parity_x * C + c
+        run.cls[0][1] = tx >> 1;
+        run.cls[0][2] = ty & 1;
+        run.cls[0][3] = ty >> 1;
+      } else {
+        run.cls[0][0] = 0;
+        run.cls[0][1] = tx * op.dil;
+        run.cls[0][2] = 0;
+        run.cls[0][3] = ty * op.dil;
+      }
       cp.runs.push_back(run);
     }
     std::vector<uint8_t> hp((size_t)cp.n_blocks * 9 * img, 0);
@@ -624,7 +656,7 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
     cp.tc = true;  // shares the workspace-time tile / tensor-map set-up of the per-tap kernel
     return VSB_OK;
   }
-  if (!cp.tc) return VSB_OK;
+  if (!cp.tc || cp.depthwise) return VSB_OK;
   cp.ps = false;
   for (int s = 0; s < op.n_src; ++s) cp.ps |= op.src_up[s] != 0;
   cp.s2 = op.stride == 2;
@@ -639,7 +671,10 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
   int coff = 0;
   for (int s = 0; s < op.n_src; ++s) {
     const int C = e->tdesc[op.src[s]].channels;
-    const int kb = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
+    // A source of e.g. 304 channels (DeepLabV3+ decoder) is read in 64-channel slabs whose last one runs past the
+    // channel count (TMA zero-fills the box, the weight image is zero there): 5 slabs instead of 19 of 16 channels.
+    int kb = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
+    if (kb < 64 && C > 128 && C % 8 == 0) kb = 64;
     cp.kb = std::min(cp.kb, kb);
     src_c0.push_back(coff);
     coff += C;
@@ -660,7 +695,7 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
         const int C = e->tdesc[op.src[s]].channels;
         TcRun run{};
         run.map = s;
-        run.nblk = C / KB;
+        run.nblk = (C + KB - 1) / KB;
         run.w_off16 = (int32_t)(wbytes / 16);
         run.w_step16 = (int32_t)(slab_img / 16);
         const int dy = ky * op.dil - op.pad, dx = kx * op.dil - op.pad;
@@ -694,7 +729,9 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
           uint8_t* img = packed.data() + (size_t)run.w_off16 * 16 + (size_t)cb * slab_img;
           for (int n = 0; n < op.cout; ++n) {
             const int64_t wrow = (((int64_t)n * op.kh + ky) * op.kw + kx) * cin_g + src_c0[s] + cb * KB;
+            const int Cs = e->tdesc[op.src[s]].channels;
             for (int ch = 0; ch < rb / 16; ++ch) {  // 16-byte chunks of 8 channels
+              if (cb * KB + ch * 8 >= Cs) break;  // past the source's channels (partial last slab): zeros
               int sw;  // Swizzle<B,4,3> on the byte address within the slab image
               if (rb == 128) sw = ch ^ (n & 7);
               else if (rb == 64) sw = ch ^ ((n >> 1) & 3);
@@ -1175,10 +1212,13 @@ int build_workspace(vsb_engine* e, int Hp, int Wp, int nb) {
         vsb::ConvHaloParams& h = cp.hparams;
         h = vsb::ConvHaloParams{};
         const int HW = 8 + 2 * op.dil, HH = 16 + 2 * op.dil;
-        TmaDesc hm;
-        int rc = make_tensor_map(e, &hm, st, nb, false, 64, HW, HH, 1);
-        if (rc) return rc;
-        CK(cudaMemcpy(cp.d_maps, &hm, sizeof(hm), cudaMemcpyHostToDevice));
+        TmaDesc hm[VSB_MAX_SRC];
+        memset(hm, 0, sizeof(hm));
+        for (int s = 0; s < op.n_src; ++s) {
+          int rc = make_tensor_map(e, &hm[s], e->tens[op.src[s]], nb, false, 64, HW, HH, 1);
+          if (rc) return rc;
+        }
+        CK(cudaMemcpy(cp.d_maps, hm, sizeof(hm), cudaMemcpyHostToDevice));
         h.map = cp.d_maps;
         h.bias = cp.d_bias_pad;
         h.residual = op.res >= 0 ? (const uint16_t*)e->tens[op.res].ptr : nullptr;
@@ -1552,12 +1592,14 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
     CK(vsb::launch_conv_halo2(h, e->num_sms, e->stream));
     return VSB_OK;
   }
-  if (cp.grouped_halo && cp.use_halo && e->conv_impl == 0 && !e->no_halo) {
+  const bool dw_simt = cp.depthwise && e->no_dw_tc;  // vsb_set_flag("dw_tc", 0): depthwise on the CUDA-core kernel
+  if (cp.grouped_halo && cp.use_halo && e->conv_impl == 0 && !e->no_halo && !dw_simt) {
     for (int b = 0; b < cp.n_blocks; ++b) {
       vsb::ConvHaloParams h = cp.hparams;
       h.NB = nb;
       h.n_base = n0;
-      h.cin_off = b * 64;
+      h.map = cp.d_maps + cp.blk_src[b];
+      h.cin_off = cp.blk_cin_off[b];
       h.cout_off = b * 64;
       h.wpacked = cp.d_whalo + (size_t)b * 9 * 64 * 128;
       ProfScope ps(e, PC_CONV_TC, oi);
@@ -1577,7 +1619,7 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
     CK(vsb::launch_conv_halo2(h, e->num_sms, e->stream));
     return VSB_OK;
   }
-  if (cp.grouped_s2 && e->conv_impl == 0) {
+  if (cp.grouped_s2 && e->conv_impl == 0 && !dw_simt) {
     for (int b = 0; b < cp.n_blocks; ++b) {
       vsb::ConvTcParams p = cp.params;
       p.NB = nb;
@@ -1591,7 +1633,7 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
     }
     return VSB_OK;
   }
-  if (cp.tc && !cp.grouped_s2 && e->conv_impl == 0) {
+  if (cp.tc && !cp.grouped_s2 && !cp.depthwise && e->conv_impl == 0) {
     vsb::ConvTcParams p = cp.params;
     p.NB = nb;
     p.n_base = n0;
@@ -1630,7 +1672,7 @@ int run_conv(vsb_engine* e, int oi, int n0, int nb) {
   a.out = (uint8_t*)ot.ptr + out_off * (ot.dtype ? 4 : 2);
   a.out_f32 = ot.dtype;
   if (cp.depthwise && e->conv_impl != 2) {
-    a.weights = cp.d_whalo;
+    a.weights = cp.d_wdw;
     ProfScope ps(e, PC_OTHER, oi);
     vsb::launch_dwconv3x3(a, e->stream, !e->no_dw_tiled);
     CK(cudaGetLastError());
@@ -1904,6 +1946,7 @@ static void free_plan(vsb_engine* e) {
     cudaFree(cp.d_runs);
     cudaFree(cp.d_wpacked);
     cudaFree(cp.d_whalo);
+    cudaFree(cp.d_wdw);
     cudaFree(cp.d_wel);
     cudaFree(cp.d_bias_el);
     cudaFree(cp.d_el_slabs);
@@ -2248,6 +2291,7 @@ int vsb_set_flag(vsb_engine* e, const char* name, int32_t value) {
   else if (n == "stem_dbg") e->stem_dbg = value;
   else if (n == "s2d_up") e->no_s2d_up = value == 0;
   else if (n == "el_conv") e->no_el_conv = value == 0;
+  else if (n == "dw_tc") e->no_dw_tc = value == 0;
   else if (n == "res_inplace") { e->no_res_inplace = value == 0; free_workspace(e); }
   else if (n == "el_tma_epilogue") { e->no_el_tma_epilogue = value == 0; free_workspace(e); }
   else if (n == "el_a_stages") { e->el_a_stages = std::max(2, std::min(value, 4)); free_workspace(e); }
