@@ -593,9 +593,12 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
     return VSB_OK;
   }
   cp.grouped_s2 = false;
-  // stride 2 (ResNeXt), or stride 1 with a dilation the halo kernel has no tile for (ASPP depthwise, rates 12 / 24 / 36)
+  // stride 2 (ResNeXt).  (Stride 1 with the ASPP dilations 12 / 24 / 36 also runs here -- set VSB_DW_TC_DILATED -- but one
+  // box per tap reads the input nine times from L2 and the 2048-channel depthwise layers need 32 launches each:
+  // 4.5 ms against 3.5-3.8 ms of the CUDA-core kernel per 32 slices of 2048^2, so it is off.)
   if (op.kind == VSB_OP_CONV && op.groups > 1 && op.n_src == 1 && !op.src_up[0] && op.kh == 3 && op.kw == 3 &&
-      ((op.stride == 2 && op.pad == 1 && op.dil == 1) || (op.stride == 1 && op.pad == op.dil && op.dil > 2)) &&
+      ((op.stride == 2 && op.pad == 1 && op.dil == 1) ||
+       (op.stride == 1 && op.pad == op.dil && op.dil > 2 && getenv("VSB_DW_TC_DILATED") != nullptr)) &&
       op.cin == op.cout && op.cin % 64 == 0 &&
       64 % (op.cin / op.groups) == 0 && e->tdesc[op.src[0]].dtype == 0 && e->tdesc[op.out].dtype == 0 &&
       e->tdesc[op.out].ds_log2 >= 0) {
@@ -927,7 +930,9 @@ int configure_halo_pipeline(vsb_engine* e, ConvPlan& cp, vsb::ConvHaloParams& h,
   const bool has_res = op.res >= 0;
   bool tma_epi = !e->no_tma_epilogue && h.n_tiles == 1;
   if (ot.dtype == 0)
-    tma_epi = tma_epi && ((h.BN % 64 == 0 && h.BN <= 128 && op.cout % 64 == 0) || (h.BN == 32 && op.cout == 32));
+    // (grouped launches: a last block of fewer than 64 channels is clipped by the TMA store)
+    tma_epi = tma_epi && ((h.BN % 64 == 0 && h.BN <= 128 && (op.cout % 64 == 0 || (cp.grouped_halo && op.cout % 8 == 0))) ||
+                          (h.BN == 32 && op.cout == 32));
   else tma_epi = tma_epi && !has_res && op.cout % 4 == 0 && op.cout <= 32 && op.cout <= h.BN;
   if (tma_epi) {
     h.out_buf_bytes = ot.dtype == 0 ? (h.BN >= 64 ? (h.BN / 64) * 16384 : 8192)
