@@ -73,6 +73,15 @@ ncuel)
   ncu -i gpurun_out/r02_el.ncu-rep --page raw --csv --metrics gpu__time_duration.sum,sm__inst_executed_pipe_tensor_op_hmma.avg.pct_of_peak_sustained_active,sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed > gpurun_out/r02_el_raw.csv 2>/dev/null
   head -c 3000 gpurun_out/r02_el_raw.csv
   ;;
+ncudw)
+  # DeepLabV3+ CUDA-core kernels: dilated depthwise (ASPP), bilinear x4, generic head
+  timeout 300 python tests/layer_profile.py 2048 4 4 DEEPLABV3_PLUS resnet50 4 > gpurun_out/r02_ncu_plain_dl.log 2>&1 && \
+  timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k 'regex:dwconv3x3_tiled_kernel|upsample_kernel|head_kernel' -c 8 -f -o gpurun_out/r02_dl_simt \
+      python tests/layer_profile.py 2048 4 4 DEEPLABV3_PLUS resnet50 4 > gpurun_out/r02_ncu_dl.log 2>&1
+  echo "ncu dw rc=$?"
+  ncu -i gpurun_out/r02_dl_simt.ncu-rep --page raw --csv --metrics gpu__time_duration.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,dram__throughput.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio,l1tex__t_sector_hit_rate.pct > gpurun_out/r02_dl_simt_raw.csv 2>/dev/null
+  head -c 6000 gpurun_out/r02_dl_simt_raw.csv
+  ;;
 deeplab)
   timeout 600 python tests/layer_profile.py 2048 32 0 DEEPLABV3_PLUS resnet50 4 > gpurun_out/r02_layers_deeplab.txt 2>&1; tail -3 gpurun_out/r02_layers_deeplab.txt
   ;;
