@@ -736,9 +736,68 @@ __global__ void __launch_bounds__(256) upsample_scalar_kernel(const uint16_t* __
     out[i] = float_to_act(v);
   }
 }
+// Bilinear, four output rows per thread: the rows of an up-sampling by >= 2 mostly fall between the same pair of
+// source rows, so the four source vectors and their horizontal interpolation are shared (the one-row kernel is
+// issue-bound, ncu: 81 % issue-active, 2 divisions + 4 loads + 32 conversions per 16 bytes written).  The arithmetic
+// per element is the expression of upsample_kernel, evaluated in the same order.
+constexpr int UPS_ROWS = 4;
+__global__ void __launch_bounds__(256) upsample_rows_kernel(const uint16_t* __restrict__ in, int Hin, int Win, int C,
+                                                            int Hout, int Wout, float sy, float sx,
+                                                            uint16_t* __restrict__ out) {
+  const uint32_t C8 = (uint32_t)C >> 3;
+  const uint32_t flat = blockIdx.x * 256u + threadIdx.x;
+  const uint32_t ox = flat / C8;
+  if (ox >= (uint32_t)Wout) return;
+  const uint32_t c8 = flat - ox * C8;
+  const size_t n = blockIdx.z;
+  const float fx = sx * ox;
+  const int x0 = (int)fx, x1 = min(x0 + 1, Win - 1);
+  const float lx = fx - x0;
+  const uint16_t* b = in + n * (size_t)Hin * Win * C + c8 * 8;
+  uint16_t* o = out + (n * Hout * (size_t)Wout + ox) * C + c8 * 8;
+  int cy0 = -1;
+  float h0[8], h1[8];  // horizontal interpolation of source rows cy0 and min(cy0 + 1, Hin - 1)
+  const int oy_end = min((int)(blockIdx.y + 1) * UPS_ROWS, Hout);
+  for (int oy = blockIdx.y * UPS_ROWS; oy < oy_end; ++oy) {
+    const float fy = sy * oy;
+    const int y0 = (int)fy;
+    const float ly = fy - y0;
+    if (y0 != cy0) {
+      cy0 = y0;
+      const int y1 = min(y0 + 1, Hin - 1);
+      const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(b + ((size_t)y0 * Win + x0) * C));
+      const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(b + ((size_t)y0 * Win + x1) * C));
+      const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(b + ((size_t)y1 * Win + x0) * C));
+      const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(b + ((size_t)y1 * Win + x1) * C));
+      const uint32_t a00[4] = {q00.x, q00.y, q00.z, q00.w}, a01[4] = {q01.x, q01.y, q01.z, q01.w};
+      const uint32_t a10[4] = {q10.x, q10.y, q10.z, q10.w}, a11[4] = {q11.x, q11.y, q11.z, q11.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 v00 = unpack_act2(a00[j]), v01 = unpack_act2(a01[j]), v10 = unpack_act2(a10[j]), v11 = unpack_act2(a11[j]);
+        h0[2 * j] = (1.f - lx) * v00.x + lx * v01.x;
+        h0[2 * j + 1] = (1.f - lx) * v00.y + lx * v01.y;
+        h1[2 * j] = (1.f - lx) * v10.x + lx * v11.x;
+        h1[2 * j + 1] = (1.f - lx) * v10.y + lx * v11.y;
+      }
+    }
+    uint4 r;
+    r.x = pack_act2((1.f - ly) * h0[0] + ly * h1[0], (1.f - ly) * h0[1] + ly * h1[1]);
+    r.y = pack_act2((1.f - ly) * h0[2] + ly * h1[2], (1.f - ly) * h0[3] + ly * h1[3]);
+    r.z = pack_act2((1.f - ly) * h0[4] + ly * h1[4], (1.f - ly) * h0[5] + ly * h1[5]);
+    r.w = pack_act2((1.f - ly) * h0[6] + ly * h1[6], (1.f - ly) * h0[7] + ly * h1[7]);
+    *reinterpret_cast<uint4*>(o + (size_t)oy * Wout * C) = r;
+  }
+}
 void launch_upsample(const uint16_t* in, int NB, int Hin, int Win, int C, int Hout, int Wout,
                      int mode, uint16_t* out, cudaStream_t st) {
   const bool vec = (C & 7) == 0 && Hout <= 65535 && NB <= 65535;
+  if (vec && mode == 0 && Hout >= 2 * Hin) {
+    const float sy = (Hout > 1) ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
+    const float sx = (Wout > 1) ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
+    dim3 grid3((unsigned)(((int64_t)Wout * (C / 8) + 255) / 256), (unsigned)((Hout + UPS_ROWS - 1) / UPS_ROWS), (unsigned)NB);
+    upsample_rows_kernel<<<grid3, 256, 0, st>>>(in, Hin, Win, C, Hout, Wout, sy, sx, out);
+    return;
+  }
   if (vec) {
     dim3 grid3((unsigned)(((int64_t)Wout * (C / 8) + 255) / 256), (unsigned)Hout, (unsigned)NB);
     upsample_kernel<<<grid3, 256, 0, st>>>(in, NB, Hin, Win, C, Hout, Wout, mode, out);
