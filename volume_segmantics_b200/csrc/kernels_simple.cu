@@ -834,24 +834,54 @@ __device__ __forceinline__ float logit_at(const HeadArgs& a, int64_t n, int py, 
   return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
 }
 
-// softmax -> first-max label and probability of one padded pixel (py, px) of image n
+// softmax -> first-max label and probability of one padded pixel (py, px) of image n.
+// CT > 0: class count known at compile time (the logits stay in registers; with a run-time count the
+// array lives in local memory and the generic kernels spent ~600 instructions per pixel, ncu: 80 % issue-active).
+template <int CT>
 __device__ __forceinline__ void head_pixel(const HeadArgs& a, int64_t n, int py, int px, int Hl, int Wl,
                                            float& best, int& lab) {
-  float l[VSB_MAX_CLASSES];
+  float l[CT > 0 ? CT : VSB_MAX_CLASSES];
+  const int C = CT > 0 ? CT : a.C;
   float m = -INFINITY;
-  for (int k = 0; k < a.C; ++k) {
-    l[k] = logit_at(a, n, py, px, k, Hl, Wl);
-    m = fmaxf(m, l[k]);
+  if (a.factor == 1) {
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      l[k] = logit_at(a, n, py, px, k, Hl, Wl);
+      m = fmaxf(m, l[k]);
+    }
+  } else {
+    // bilinear x factor, align_corners=True: the four corners and weights of logit_at() once per pixel, the same
+    // expression per class (the per-class version recomputed two divisions and the index arithmetic C times)
+    const int Hout = Hl * a.factor, Wout = Wl * a.factor;
+    const float sy = (Hout > 1) ? (float)(Hl - 1) / (float)(Hout - 1) : 0.f;
+    const float sx = (Wout > 1) ? (float)(Wl - 1) / (float)(Wout - 1) : 0.f;
+    const float fy = sy * py, fx = sx * px;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = min(y0 + 1, Hl - 1), x1 = min(x0 + 1, Wl - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const float* b = a.logits + n * (int64_t)Hl * Wl * a.C;
+    const float* p00 = b + ((int64_t)y0 * Wl + x0) * a.C;
+    const float* p01 = b + ((int64_t)y0 * Wl + x1) * a.C;
+    const float* p10 = b + ((int64_t)y1 * Wl + x0) * a.C;
+    const float* p11 = b + ((int64_t)y1 * Wl + x1) * a.C;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      const float v00 = __ldg(p00 + k), v01 = __ldg(p01 + k), v10 = __ldg(p10 + k), v11 = __ldg(p11 + k);
+      l[k] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+      m = fmaxf(m, l[k]);
+    }
   }
   float sum = 0.f;
-  for (int k = 0; k < a.C; ++k) {
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
     l[k] = expf(l[k] - m);
     sum += l[k];
   }
   // probs = exp/sum; label = first index of the max prob (torch.argmax)
   best = -1.f;
   lab = 0;
-  for (int k = 0; k < a.C; ++k) {
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
     const float p = __fdiv_rn(l[k], sum);
     if (p > best) {
       best = p;
@@ -860,18 +890,29 @@ __device__ __forceinline__ void head_pixel(const HeadArgs& a, int64_t n, int py,
   }
 }
 
+template <int CT>
 __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   const vsb_direction& g = a.g;
   const int64_t total = (int64_t)a.nb * g.H * g.W;
   const int Hl = (int)(g.Hp / a.factor), Wl = (int)(g.Wp / a.factor);
+  const bool small = total < (1ll << 31);  // 32-bit pixel decode (64-bit divisions cost ~100 instructions each)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = i % g.W;
-    const int64_t r = (i / g.W) % g.H;
-    const int64_t s = i / (g.W * g.H);
+    int64_t c, r, s;
+    if (small) {
+      const uint32_t i32 = (uint32_t)i, W32 = (uint32_t)g.W, H32 = (uint32_t)g.H;
+      const uint32_t q = i32 / W32;
+      c = i32 - q * W32;
+      s = q / H32;
+      r = q - (uint32_t)s * H32;
+    } else {
+      c = i % g.W;
+      r = (i / g.W) % g.H;
+      s = i / (g.W * g.H);
+    }
     float best;
     int lab;
-    head_pixel(a, s, (int)(r + g.crop_top), (int)(c + g.crop_left), Hl, Wl, best, lab);
+    head_pixel<CT>(a, s, (int)(r + g.crop_top), (int)(c + g.crop_left), Hl, Wl, best, lab);
     const int64_t vox = g.base + (a.s0 + s) * g.stride_s + r * g.stride_r + c * g.stride_c;
     if (a.votes) {
       // one-hot vote (vol_seg_2d_predictor.py:118-136): uint8 counts, <= 12
@@ -889,6 +930,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
 // column fastest (coalesced), keys are transposed through shared memory and merged with
 // the slice index fastest, so a warp's 32 atomics hit 256 contiguous bytes of the key
 // volume instead of 32 different sectors.
+template <int CT>
 __global__ void __launch_bounds__(256) head_xplane_kernel(HeadArgs a) {
   __shared__ unsigned long long tile[32][33];
   const vsb_direction& g = a.g;
@@ -907,7 +949,7 @@ __global__ void __launch_bounds__(256) head_xplane_kernel(HeadArgs a) {
       if (s < a.nb && c < g.W) {
         float best;
         int lab;
-        head_pixel(a, s, (int)(r + g.crop_top), (int)(c + g.crop_left), Hl, Wl, best, lab);
+        head_pixel<CT>(a, s, (int)(r + g.crop_top), (int)(c + g.crop_left), Hl, Wl, best, lab);
         key = pack_key(__half_as_ushort(__float2half_rn(best)), a.d, (uint32_t)lab, __float_as_uint(best));
       }
       tile[si][tx] = key;
@@ -928,13 +970,32 @@ void launch_head(const HeadArgs& a, cudaStream_t st) {
   }
   if (!a.votes && a.g.stride_s == 1 && a.g.stride_c != 1 && a.nb >= 8) {
     const int64_t tiles = ((a.nb + 31) / 32) * a.g.H * ((a.g.W + 31) / 32);
-    head_xplane_kernel<<<(int)(tiles < 148 * 16 ? tiles : 148 * 16), 256, 0, st>>>(a);
+    const int grid = (int)(tiles < 148 * 16 ? tiles : 148 * 16);
+    switch (a.C) {
+      case 2: head_xplane_kernel<2><<<grid, 256, 0, st>>>(a); break;
+      case 3: head_xplane_kernel<3><<<grid, 256, 0, st>>>(a); break;
+      case 4: head_xplane_kernel<4><<<grid, 256, 0, st>>>(a); break;
+      case 5: head_xplane_kernel<5><<<grid, 256, 0, st>>>(a); break;
+      case 6: head_xplane_kernel<6><<<grid, 256, 0, st>>>(a); break;
+      case 7: head_xplane_kernel<7><<<grid, 256, 0, st>>>(a); break;
+      case 8: head_xplane_kernel<8><<<grid, 256, 0, st>>>(a); break;
+      default: head_xplane_kernel<0><<<grid, 256, 0, st>>>(a); break;
+    }
     return;
   }
   const int64_t total = (int64_t)a.nb * a.g.H * a.g.W;
   const int64_t blocks = (total + 255) / 256;
   const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
-  head_kernel<<<grid, 256, 0, st>>>(a);
+  switch (a.C) {
+    case 2: head_kernel<2><<<grid, 256, 0, st>>>(a); break;
+    case 3: head_kernel<3><<<grid, 256, 0, st>>>(a); break;
+    case 4: head_kernel<4><<<grid, 256, 0, st>>>(a); break;
+    case 5: head_kernel<5><<<grid, 256, 0, st>>>(a); break;
+    case 6: head_kernel<6><<<grid, 256, 0, st>>>(a); break;
+    case 7: head_kernel<7><<<grid, 256, 0, st>>>(a); break;
+    case 8: head_kernel<8><<<grid, 256, 0, st>>>(a); break;
+    default: head_kernel<0><<<grid, 256, 0, st>>>(a); break;
+  }
 }
 
 // Injected merge (test hook): slice-space fp32 prob + uint8 label of direction d.
