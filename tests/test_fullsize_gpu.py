@@ -79,3 +79,34 @@ def test_random_init_weights_at_1024(engine, unet_r34, name, shape, d, picks):
     engine.load_model(model)
     engine.set_volume(vol)
     _compare(name + "_random_init", engine, po.OraclePredictor(oracle_model, 4), vol, d, picks[:2], RANDOM_INIT_FLOOR)
+
+
+def test_unetplusplus_resnext50_at_256x320(engine):
+    """BASELINE cfg4's architecture at a size where the space-to-depth decoder kernel serves several
+    decoder levels (the small end-to-end volumes of test_arch_e2e_gpu.py fall back to the parity-split kernels below
+    the first level): Z slices of a ragged (3, 250, 300) volume, padded to 256 x 320, against the fp32 oracle."""
+    from oracle.smp_models import make_random_model
+    from volume_segmantics_b200.plan import B200SegmentationModel
+
+    oracle_model = make_random_model("unetplusplus", "resnext50_32x4d", 6, seed=5)
+    model = B200SegmentationModel("U_NET_PLUS_PLUS", "resnext50_32x4d", 6)
+    model.load_state_dict(oracle_model.state_dict())
+    vol = structured_volume((3, 250, 300), 77)
+    engine.load_model(model)
+    engine.set_volume(vol)
+    g = engine.geometry(0)
+    assert (g.Hp, g.Wp) == (256, 320)
+    engine.reset()
+    engine.predict_range(0, 0, g.S)
+    labels, probs = engine.fetch()
+    want_l, want_p, full = po.OraclePredictor(oracle_model, 6).predict_single_axis(vol, True, po.AXIS_Z, return_full=True)
+    perr = np.abs(probs.astype(np.float32) - want_p.astype(np.float32))
+    agree = labels == want_l
+    top2 = np.sort(full, axis=1)[:, -2:]
+    margin = top2[:, 1] - top2[:, 0]
+    worst = margin[~agree].max() if (~agree).any() else 0.0
+    print(f"[fullsize U-Net++/ResNeXt-50 C=6 256x320] agreement {agree.mean():.5f} max prob err {perr.max():.5f} "
+          f"largest reference margin at a disagreement {worst:.5f}")
+    assert perr.max() < PROB_TOL
+    assert worst < PROB_TOL
+    assert agree.mean() >= 0.99
