@@ -1145,7 +1145,7 @@ conv_halo2_kernel(const __grid_constant__ ConvHalo2Params p) {
     int rpos[2] = {0, 0};
     uint32_t rph[2] = {0, 0};
     int tile_k = 0;
-    uint8_t fifo[8];  // stages in issue order (at most a_stages <= 8 unpublished); 0xFF = fetched by TMA, nothing to publish
+    uint8_t fifo[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // stages in issue order (at most a_stages <= 8 unpublished); 0xFF = fetched by TMA, nothing to publish
     int fifo_head = 0, fifo_tail = 0;
     auto publish_oldest = [&]() {
       switch (depth) {  // all but the `depth` most recent groups have landed

@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_pool_kernel(const __grid_c
 // =====================================================================================
 namespace {
 constexpr int S3_PH = 7, S3_PW = 15;                 // pooled block
-constexpr int S3_ROWS = 16, S3_COLS = 32;            // conv region
+constexpr int S3_ROWS = 16;                          // conv region: 16 rows x 32 columns
 constexpr int S3_RAW_ROWS = 2 * (S3_ROWS - 1) + 8;   // 38 input rows (7 filter rows + the zero-weight 8th)
 constexpr int S3_COPY_BYTES = S3_RAW_ROWS * 128;     // 4864: one phase-shifted window, 64 px x 2 B per row
 constexpr int S3_A_STAGE = 20 * 1024;                // 4 copies (19456 B), 1024-aligned
@@ -413,12 +413,6 @@ constexpr int S3_THREADS = 32 * (S3_LOAD_WARPS + 2 + S3_EPI_WARPS + S3_POOL_WARP
 __device__ __forceinline__ uint64_t s3_desc_a(uint32_t addr, bool swap) {  // K-major, no swizzle: LBO = 128 B, SBO = 256 B
   const uint64_t lbo = swap ? 256u : 128u, sbo = swap ? 128u : 256u;
   return (uint64_t)((addr & 0x3ffffu) >> 4) | ((lbo >> 4) << 16) | ((sbo >> 4) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void tma_load_3d_plain(const void* desc, uint64_t* bar, uint32_t dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
 }
 // Phase 0 of the leftmost tiles (conv column -1 does not exist): pixels i = 1..7 of rows 1..14 are staged as a
 // dense 14 x 7 box at the start of the phase buffer (what its TMA store reads), rows 0 and 15 behind it.
