@@ -110,3 +110,35 @@ def test_unetplusplus_resnext50_at_256x320(engine):
     assert perr.max() < PROB_TOL
     assert worst < PROB_TOL
     assert agree.mean() >= 0.99
+
+
+def test_deeplabv3plus_resnet50_at_512x640(engine):
+    """BASELINE cfg5's architecture at a size where the depthwise convolutions run as block-diagonal tensor-core
+    convolutions (304 channels: partial last block), the 304-channel pointwise layer in zero-tailed 64-channel slabs,
+    the four-rows-per-thread bilinear kernel and the templated generic head: Z slices of a ragged (2, 500, 620)
+    volume, padded to 512 x 640, against the fp32 oracle."""
+    from oracle.smp_models import make_random_model
+    from volume_segmantics_b200.plan import B200SegmentationModel
+
+    oracle_model = make_random_model("deeplabv3plus", "resnet50", 4, seed=8)
+    model = B200SegmentationModel("DEEPLABV3_PLUS", "resnet50", 4)
+    model.load_state_dict(oracle_model.state_dict())
+    vol = structured_volume((2, 500, 620), 78)
+    engine.load_model(model)
+    engine.set_volume(vol)
+    g = engine.geometry(0)
+    assert (g.Hp, g.Wp) == (512, 640)
+    engine.reset()
+    engine.predict_range(0, 0, g.S)
+    labels, probs = engine.fetch()
+    want_l, want_p, full = po.OraclePredictor(oracle_model, 4).predict_single_axis(vol, True, po.AXIS_Z, return_full=True)
+    perr = np.abs(probs.astype(np.float32) - want_p.astype(np.float32))
+    agree = labels == want_l
+    top2 = np.sort(full, axis=1)[:, -2:]
+    margin = top2[:, 1] - top2[:, 0]
+    worst = margin[~agree].max() if (~agree).any() else 0.0
+    print(f"[fullsize DeepLabV3+/ResNet-50 C=4 512x640] agreement {agree.mean():.5f} max prob err {perr.max():.5f} "
+          f"largest reference margin at a disagreement {worst:.5f}")
+    assert perr.max() < PROB_TOL
+    assert worst < PROB_TOL
+    assert agree.mean() >= 0.99
