@@ -356,6 +356,9 @@ def run_ours(args, cfg):
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lt = torch.tensor([launches], dtype=torch.float64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)  # gpu_launches is the whole job's count, like `value`
+        launches = int(lt.item())
     ms_step = float(t.item()) / args.steps
     value = nvox / (ms_step * 1e-3)
 
@@ -369,7 +372,7 @@ def run_ours(args, cfg):
     conv_flops = 2.0 * macs_px * padded_px * args.steps
     roofline = None
     traffic = None  # DRAM bytes per conv launch from the committed ncu capture of one batch (profiles/)
-    tpath = ROOT / "profiles" / "r01_conv_traffic.json"
+    tpath = ROOT / "profiles" / "r02_conv_traffic.json"
     if tpath.exists() and cfg["key"] == "cfg3" and not args.size:
         traffic = json.loads(tpath.read_text()).get("dram_bytes_per_conv_launch")
     if conv_ms > 0:
@@ -377,7 +380,7 @@ def run_ours(args, cfg):
         roofline = {"bound": "tensor", "kernel": "tcgen05 conv kernels (conv_halo_kernel, conv_halo2_kernel<>, conv_tc_kernel<>)", "achieved": ach,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                     "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, average over the conv launches of one "
-                                      "batch of 32 slices of 1024^2 (profiles/r01_ncu_batch32_dram.csv)" if traffic else None,
+                                      "batch of 128 slices of 1024^2, the launch configuration of this run (profiles/r02_ncu_batch128_dram.csv)" if traffic else None,
                     "peak_source": peak_src,
                     "launches": conv_n, "avg_launch_ms": conv_ms / max(1, conv_n),
                     "flops_per_launch": conv_flops / max(1, conv_n),

@@ -82,6 +82,13 @@ ncudw)
   ncu -i gpurun_out/r02_dl_simt.ncu-rep --page raw --csv --metrics gpu__time_duration.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,dram__throughput.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio,l1tex__t_sector_hit_rate.pct > gpurun_out/r02_dl_simt_raw.csv 2>/dev/null
   head -c 6000 gpurun_out/r02_dl_simt_raw.csv
   ;;
+traffic)
+  # DRAM bytes per launch of one 128-slice batch (the benchmarked launch configuration), one ncu pass
+  timeout 300 python tests/layer_profile.py 1024 128 128 > gpurun_out/r02_ncu_plain128.log 2>&1 && \
+  timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --kernel-name-base demangled --csv \
+      --log-file gpurun_out/r02_ncu_batch128_dram.csv python tests/layer_profile.py 1024 128 128 > gpurun_out/r02_ncu_traffic.log 2>&1
+  echo "ncu traffic rc=$?"; wc -l gpurun_out/r02_ncu_batch128_dram.csv
+  ;;
 deeplab)
   timeout 600 python tests/layer_profile.py 2048 32 0 DEEPLABV3_PLUS resnet50 4 > gpurun_out/r02_layers_deeplab.txt 2>&1; tail -3 gpurun_out/r02_layers_deeplab.txt
   ;;
