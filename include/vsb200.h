@@ -231,6 +231,7 @@ int vsb_set_conv_impl(vsb_engine* e, int32_t impl);
  *                         space-to-depth convolution at half resolution (summed up-sample taps: same arithmetic up
  *                         to summation order and one rounding of the summed weights); 0: parity-split kernels
  *   "el_tma_epilogue" (1) epilogue of that kernel through shared memory + TMA store (folded output map); 0: per-thread stores
+ *   "el_a_stages" (2)     halo ring depth of that kernel, 2..4 (the rest of the shared memory is weight ring)
  *   "res_inplace" (1)     halo kernel, 64-channel residual layers: the residual tile lands in the output staging buffer
  *                         (frees shared memory for a fourth halo stage and the second MMA warp); 0: separate buffers
  *   "el_conv" (1)         32 -> 32 and dense stride-2 3x3 convolutions on that kernel (exact re-arrangements); 0: round-1 kernels

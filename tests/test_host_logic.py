@@ -148,6 +148,13 @@ def test_plan_marks_decoder_conv1_for_the_space_to_depth_kernel():
         k2 = c_up + 4 * (op.cin - c_up)
         assert op.factor > 0 and op.factor * 256 + 4 * op.cout * 9 * k2 * 2 <= p.blob.size
     assert all(op.mode == 0 for op in p.ops if op.kind == _lib.VSB_OP_CONV and op.n_src == 1)
+    # U-Net++: every dense node with >= 32 output channels (several skip sources); DeepLabV3+: none (no up-sampled concat)
+    pp = lower_to_plan(B200SegmentationModel("U_NET_PLUS_PLUS", "resnext50_32x4d", 6))
+    marked = [op for op in pp.ops if op.kind == _lib.VSB_OP_CONV and op.mode == 2]
+    assert len(marked) >= 9 and all(op.src_up[0] == 1 and not any(op.src_up[1:op.n_src]) and op.cout >= 32 for op in marked)
+    assert max(op.n_src for op in marked) >= 4
+    dl = lower_to_plan(B200SegmentationModel("DEEPLABV3_PLUS", "resnet50", 4))
+    assert not [op for op in dl.ops if op.kind == _lib.VSB_OP_CONV and op.mode == 2]
 
 
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
