@@ -544,7 +544,8 @@ int prepare_conv_plan(vsb_engine* e, int oi) {
   // materialises the concat as long as every source but the last holds a multiple of 64 channels
   cp.blk_src.clear();
   cp.blk_cin_off.clear();
-  bool blocks_ok = op.kind == VSB_OP_CONV && op.n_src >= 1 && (op.n_src == 1 || cp.depthwise);
+  // (at most three sources: slots VSB_MAX_SRC - 3 .. - 1 of the map array hold the epilogue maps of the halo launches)
+  bool blocks_ok = op.kind == VSB_OP_CONV && op.n_src >= 1 && op.n_src <= 3 && (op.n_src == 1 || cp.depthwise);
   for (int s = 0; s < op.n_src && blocks_ok; ++s) {
     const vsb_tensor_desc& t = e->tdesc[op.src[s]];
     blocks_ok = !op.src_up[s] && t.dtype == 0 && t.channels % 8 == 0 && (s == op.n_src - 1 || t.channels % 64 == 0);
