@@ -686,6 +686,8 @@ struct HaloElTables {
   HaloEntry entries[HALO_EL_MAX_ENTRIES];
 };
 constexpr int kHaloElBiasBytes = 1024 * 4;  // n_tiles * BN <= 1024
+static_assert(sizeof(HaloEntry) == 16 && (sizeof(HaloSlabRef) * HALO_EL_MAX_SLABS) % 16 == 0,
+              "the MMA warps read entries with 16-byte shared-memory loads");
 __device__ __forceinline__ void halo_el_decode(const ConvHaloElParams& p, int t, int& n_tile, int& X0, int& Y0, int& n) {
   auto fdiv = [](uint32_t v, const FastDiv& f) { return f.m ? __umulhi(v, f.m) : v; };
   uint32_t sp = fdiv((uint32_t)t, p.div_n_tiles);
@@ -815,6 +817,7 @@ conv_halo_el_kernel(const __grid_constant__ ConvHaloElParams p) {
     const uint64_t b_desc0 = desc_compact<P>(smem_u32(b_area), 8 * P);
     const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4;
     const uint32_t b_step = (uint32_t)p.b_bytes >> 4;
+    const uint32_t entries_s = smem_u32(tab->entries);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n_tile, X0, Y0, n;
       halo_el_decode(p, t, n_tile, X0, Y0, n);
@@ -826,11 +829,19 @@ conv_halo_el_kernel(const __grid_constant__ ConvHaloElParams p) {
       uint32_t accf = 0;  // the first entry of a tile covers all BN columns (host guarantee)
       for (int sr = p.tile_begin[n_tile]; sr < sr_end; ++sr) {
         const HaloSlabRef s = tab->slabs[sr];
+        // entries are read with explicit 16-byte shared-memory loads, one entry ahead (the compiler turned the
+        // struct read into three generic 4-byte loads at the head of a ~120-instruction dependent chain per entry)
+        uint4 nxt = lds128(entries_s + (uint32_t)s.e_begin * 16u);
         mbar_wait(&ctl->a_full[as], aph);
         tc_fence_after_sync();
         const uint64_t a_stage_desc = desc_add(a_desc0, as * a_step);
         for (int ei = s.e_begin; ei < s.e_end; ++ei) {
-          const HaloEntry en = tab->entries[ei];
+          HaloEntry en;
+          en.ab_off16 = nxt.x;
+          en.w_off = nxt.y;
+          en.ncol0_n = nxt.z;
+          en.grp = nxt.w;
+          if (ei + 1 < s.e_end) nxt = lds128(entries_s + (uint32_t)(ei + 1) * 16u);
           if (en.grp & 0x7fffffffu) {  // first entry of a group: its images have landed
             mbar_wait(&ctl->b_full[bs], bph);
             tc_fence_after_sync();
