@@ -818,6 +818,7 @@ conv_halo_el_kernel(const __grid_constant__ ConvHaloElParams p) {
     const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4;
     const uint32_t b_step = (uint32_t)p.b_bytes >> 4;
     const uint32_t entries_s = smem_u32(tab->entries);
+    const bool one_mma = (p.dbg & 8) != 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n_tile, X0, Y0, n;
       halo_el_decode(p, t, n_tile, X0, Y0, n);
@@ -853,14 +854,21 @@ conv_halo_el_kernel(const __grid_constant__ ConvHaloElParams p) {
             const uint64_t at = desc_add(a_stage_desc, en.ab_off16 & 0xffffu);
             const uint64_t bt = desc_add(b_desc0, bs * b_step + (en.ab_off16 >> 16));
             const uint32_t d = d_tmem + ncol0;
-            uint32_t af = accf;
+            if (kmask == 15u && !one_mma) {  // the common case, without per-K-step tests
+              umma_bf16_ss(d, at, bt, idesc, accf);
+              umma_bf16_ss(d, desc_add(at, 2), desc_add(bt, 2), idesc, 1u);
+              umma_bf16_ss(d, desc_add(at, 4), desc_add(bt, 4), idesc, 1u);
+              umma_bf16_ss(d, desc_add(at, 6), desc_add(bt, 6), idesc, 1u);
+            } else {
+              uint32_t af = accf;
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k)
-              if ((kmask >> k) & 1u) {  // K-steps whose weights are all zero are not issued
-                umma_bf16_ss(d, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc, af);
-                af = 1u;
-                if (p.dbg & 8) break;
-              }
+              for (int k = 0; k < KSTEPS; ++k)
+                if ((kmask >> k) & 1u) {  // K-steps whose weights are all zero are not issued
+                  umma_bf16_ss(d, desc_add(at, 2 * k), desc_add(bt, 2 * k), idesc, af);
+                  af = 1u;
+                  if (one_mma) break;
+                }
+            }
             if (last) umma_commit(&ctl->b_empty[bs]);
             if (ei == s.e_end - 1) {
               umma_commit(&ctl->a_empty[as]);
