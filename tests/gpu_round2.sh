@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 validation on ONE B200 (gpurun --timeout 3000 -- 'bash tests/gpu_round2.sh [stage ...]').
-# Stages: tests bench configs layers ncu.  Artefacts land in gpurun_out/ (copied to profiles/ by hand).
+# Stages: tests bench configs layers ncu ncustem ncuel ncudw traffic deeplab multi multicfg (the last two need gpurun --gpus N).
 mkdir -p gpurun_out
 STAGES="${@:-tests bench configs layers ncu}"
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader
